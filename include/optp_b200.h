@@ -1,0 +1,183 @@
+/* optp_b200.h -- C ABI of the B200-native pricing hot path.
+ *
+ * The reference (optpricer 0.3.0) is pure Python: it has no FFI layer, so the
+ * "interface each entry point replaces" is a Python function of the reference.
+ * Every declaration below cites that function (path:line under the reference's
+ * src/optpricer/).  The Python host package (optpricer_b200) keeps the reference's
+ * names/signatures and forwards to these symbols through ctypes.
+ *
+ * Conventions
+ *   - plain C types only; all pointers are HOST pointers unless the function name
+ *     ends in _dev (then they are DEVICE pointers on the current device and the
+ *     call is asynchronous on the given cudaStream_t, passed as void*).
+ *   - every function returns an int status: 0 ok, >0 argument error (OPTP_E_*),
+ *     <0 CUDA runtime error (-(cudaError_t)); optp_last_error() gives the text.
+ *   - the library keeps no pointer after a call returns.
+ *   - no CPU fallback exists: without a usable CUDA device every compute entry
+ *     point returns a negative status.
+ */
+#ifndef OPTP_B200_H
+#define OPTP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OPTP_ABI_VERSION 3
+
+/* argument errors */
+#define OPTP_E_ARG 1        /* bad scalar argument / null pointer            */
+#define OPTP_E_KIND 2       /* unknown process / payoff kind                 */
+#define OPTP_E_TOO_LARGE 3  /* N or table too large for the device kernels   */
+#define OPTP_E_NOINIT 4     /* optp_init was not called on this device       */
+
+/* ---- process kinds (reference processes.py) ------------------------------ */
+#define OPTP_PROC_GBM 0          /* gbm_paths                 processes.py:30-56   */
+#define OPTP_PROC_HESTON_FTE 1   /* heston_paths              processes.py:117-162 */
+#define OPTP_PROC_LV_MILSTEIN 2  /* milstein_local_vol_paths  processes.py:311-381 */
+#define OPTP_PROC_LV_EULER 3     /* local_vol_paths           processes.py:223-258 */
+#define OPTP_PROC_GBM_MILSTEIN 4 /* gbm_milstein_paths        processes.py:264-305 */
+#define OPTP_PROC_SABR 5         /* sabr_paths                processes.py:168-217 */
+#define OPTP_PROC_HESTON_QE 6    /* Andersen QE -- no reference code, parity unpinned */
+
+/* ---- payoff kinds (reference exotics.py) ---------------------------------- */
+#define OPTP_PAY_VANILLA 0   /* vanilla leg of barrier_price  exotics.py:83-88   */
+#define OPTP_PAY_DIGITAL 1   /* digital_price                 exotics.py:169-209 */
+#define OPTP_PAY_BARRIER 2   /* barrier_price                 exotics.py:33-96   */
+#define OPTP_PAY_ASIAN 3     /* asian_price                   exotics.py:102-163 */
+#define OPTP_PAY_LOOKBACK 4  /* lookback_price                exotics.py:215-273 */
+
+/* payoff flag bits */
+#define OPTP_F_CALL 1u        /* else put                                        */
+#define OPTP_F_UP 2u          /* barrier: up  (else down)                        */
+#define OPTP_F_IN 4u          /* barrier: knock-in (else knock-out)              */
+#define OPTP_F_GEOMETRIC 8u   /* asian: geometric (else arithmetic) average      */
+#define OPTP_F_FLOATING 16u   /* asian / lookback: floating strike (else fixed)  */
+
+/* ---- arithmetic / rng modes ------------------------------------------------ */
+#define OPTP_MODE_FP32_PHILOX 0 /* production: fp32 path state, Philox4x32-10 + Box-Muller in
+                                   registers, fp64 accumulators                              */
+#define OPTP_MODE_FP64_PHILOX 1 /* reference operation order in fp64, on-device Philox normals */
+#define OPTP_MODE_FP64_HOSTZ 2  /* deterministic check: fp64, consumes the caller's normals    */
+
+typedef struct optp_process {
+    int32_t kind;      /* OPTP_PROC_*                                             */
+    int32_t n_nodes;   /* sigma table: nodes per row (LV_* only)                  */
+    double S0, r, q, T;
+    double sigma;                      /* GBM, GBM_MILSTEIN                          */
+    double v0, kappa, theta, xi, rho;  /* HESTON_*; SABR: v0=alpha0, xi=nu, kappa=beta */
+    double dS_bump;                    /* LV_MILSTEIN (processes.py:320)             */
+    /* sigma(S,t) table, row i = step time i*T/n_steps (i < n_steps), n_nodes log-uniform
+       nodes ln S = x0 + h*j; linear interpolation in ln S, flat outside.  The table is
+       this library's statement of the sigma_loc callable contract, processes.py:361-369. */
+    const double* sigma_table;
+    double x0, h;
+} optp_process;
+
+typedef struct optp_payoff {
+    int32_t kind;    /* OPTP_PAY_*  */
+    uint32_t flags;  /* OPTP_F_*    */
+    double K, barrier, rebate, payout;
+    double r_disc, T_disc; /* the r,T the payoff function discounts with, exotics.py:22 */
+} optp_payoff;
+
+/* statistics block written by the Monte Carlo entry points:
+ *   [0] n (effective paths)  [1] sum X  [2] sum X^2  [3] sum Y  [4] sum Y^2  [5] sum XY
+ *   [6] number of table lookups clamped to the grid edge (LV_* only)  [7] reserved
+ * X = exp(-r_disc*T_disc)*payoff, Y = exp(-r_disc*T_disc)*S_T  (monte_carlo.py:54-64). */
+#define OPTP_NSTATS 8
+
+/* ---- lifetime ------------------------------------------------------------- */
+int optp_abi_version(void);
+/* Create (idempotent) the per-device context: stream, scratch arena, partial-sum buffers. */
+int optp_init(int device);
+int optp_shutdown(void);
+const char* optp_last_error(void);
+int optp_device_count(void);
+/* Number of kernels this library has launched since optp_init (bench.py "gpu_launches"). */
+uint64_t optp_launch_count(void);
+/* Pinned host staging memory for callers that want DMA-able buffers. */
+int optp_host_alloc(void** p, uint64_t bytes);
+int optp_host_free(void* p);
+
+/* ---- terminal-only European Monte Carlo ------------------------------------
+ * Replaces _mc_chunk_sumstats (monte_carlo.py:11-64): draws (or consumes) n_base normals,
+ * optional antithetic mirror, S_T = S0*exp((r-q-sigma^2/2)T + sigma*sqrt(T)*Z), and returns
+ * the six sufficient statistics.  The estimator (monte_carlo.py:142-167) stays on the host.
+ *   mode FP64_HOSTZ: z points to n_base fp64 normals (the reference's PCG64 draws).
+ *   fp32_cast != 0 reproduces dtype=np.float32 (monte_carlo.py:35,42) in HOSTZ mode.
+ *   path_offset: global index of the first base path (Philox counter; multi-GPU sharding). */
+int optp_mc_terminal(double S0, double K, double T, double r, double q, double sigma,
+                     int is_call, uint64_t n_base, int antithetic, int mode, int fp32_cast,
+                     uint64_t seed, uint64_t path_offset, const double* z,
+                     double stats_out[OPTP_NSTATS]);
+int optp_mc_terminal_dev(double S0, double K, double T, double r, double q, double sigma,
+                         int is_call, uint64_t n_base, int antithetic, int mode, int fp32_cast,
+                         uint64_t seed, uint64_t path_offset, const double* z_dev,
+                         double* stats_dev, void* stream);
+
+/* ---- fused path simulation + payoff reduction ------------------------------
+ * Replaces the pair  <generator>(...) -> ndarray -> <payoff>_price(paths, ...)
+ * (processes.py:30-56,117-162,311-381 + exotics.py:18-273) without materialising paths.
+ *   n_payoffs payoffs are evaluated on the SAME simulated path set (price_book.py:80,92-93
+ *   seeds every row alike, i.e. common random numbers); stats_out holds n_payoffs blocks.
+ *   z (HOSTZ mode): n_streams consecutive (n_steps, n_base) C-order blocks, in the
+ *   reference's draw order (GBM/LV: Z; Heston/SABR: Z2 then Zp -- processes.py:138-139).
+ *   payoff_out (optional, may be NULL): n_payoffs x n_eff undiscounted per-path payoffs,
+ *   columns [0,n_base) base paths, [n_base,2n_base) antithetic mirrors (processes.py:49-50).
+ *   terminal_out (optional): n_eff terminal prices S_T. */
+int optp_mc_path(const optp_process* proc, const optp_payoff* payoffs, uint32_t n_payoffs,
+                 uint32_t n_steps, uint64_t n_base, int antithetic, int mode,
+                 uint64_t seed, uint64_t path_offset, const double* z,
+                 double* payoff_out, double* terminal_out, double* stats_out);
+/* Device-resident variant: the sigma table must already be uploaded with
+ * optp_sigma_table_upload (proc->sigma_table is ignored); stats_dev receives
+ * n_payoffs*OPTP_NSTATS doubles; asynchronous on stream. */
+int optp_mc_path_dev(const optp_process* proc, const optp_payoff* payoffs, uint32_t n_payoffs,
+                     uint32_t n_steps, uint64_t n_base, int antithetic, int mode,
+                     uint64_t seed, uint64_t path_offset, const double* z_dev,
+                     double* payoff_out_dev, double* terminal_out_dev, double* stats_dev,
+                     void* stream);
+/* Stage a sigma(S,t) table (n_steps x n_nodes fp64, host) in HBM for later _dev calls. */
+int optp_sigma_table_upload(const double* table, uint32_t n_steps, uint32_t n_nodes);
+
+/* Materialise paths for API compatibility with the generators' ndarray return value
+ * (processes.py:56,162,381): paths_out is (n_steps+1, n_eff) fp64 C-order with the t=0 row;
+ * var_out (optional, Heston return_variance=True, processes.py:147,161) has the same shape.
+ * mode must be FP64_PHILOX or FP64_HOSTZ. */
+int optp_paths(const optp_process* proc, uint32_t n_steps, uint64_t n_base, int antithetic,
+               int mode, uint64_t seed, uint64_t path_offset, const double* z,
+               double* paths_out, double* var_out);
+
+/* Payoff reduction over caller-supplied paths (the literal exotics.py:18-273 contract:
+ * a (n_rows, n_cols) fp64 C-order array whose row 0 is t=0).  One payoff per call. */
+int optp_payoff_from_paths(const double* paths, uint64_t n_rows, uint64_t n_cols,
+                           const optp_payoff* payoff, double* payoff_out,
+                           double stats_out[OPTP_NSTATS]);
+
+/* ---- batched CRR binomial ---------------------------------------------------
+ * Replaces crr (binomial.py:7-38) looped over a heterogeneous contract batch, and
+ * crr_vec (binomial.py:44-109) when S0,T,r,q,sigma are constant across the batch.
+ *   status_out[i] = 1 and price_out[i] = NaN when the risk-neutral p is outside (0,1)
+ *   (binomial.py:16-17); N <= 0 is an argument error (binomial.py:9-10). */
+int optp_crr_batch(const double* S0, const double* K, const double* T, const double* r,
+                   const double* q, const double* sigma, const uint8_t* is_call,
+                   uint64_t n, uint32_t N, int american, double* price_out,
+                   uint8_t* status_out);
+int optp_crr_batch_dev(const double* S0, const double* K, const double* T, const double* r,
+                       const double* q, const double* sigma, const uint8_t* is_call,
+                       uint64_t n, uint32_t N, int american, double* price_out,
+                       uint8_t* status_out, void* stream);
+
+/* ---- roofline microbenchmarks (bench.py only) ---------------------------------
+ * Measure the peaks MEASURED_PEAKS.json lacks, on the device, with CUDA events:
+ *   which = 0 FP32 FFMA lane-ops/s, 1 MUFU.EX2 ops/s, 2 FP64 DFMA lane-ops/s,
+ *           3 shared-memory bytes/s (LDS.64 conflict-free), 4 IMAD.WIDE lane-ops/s. */
+int optp_microbench(int which, double* per_second_out, double* sm_clock_mhz_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPTP_B200_H */

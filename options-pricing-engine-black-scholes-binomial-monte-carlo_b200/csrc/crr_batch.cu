@@ -1,0 +1,345 @@
+// Batched Cox-Ross-Rubinstein backward induction (fp64) for sm_100a.
+//
+// Replaces reference binomial.py:7-38 (crr) looped over a contract batch and
+// binomial.py:44-109 (crr_vec).  Recursion per level k = N-1..0 (binomial.py:28-36):
+//     V_k[j] = disc*(p*V_{k+1}[j+1] + (1-p)*V_{k+1}[j]);  American: V_k[j] = max(V_k[j], +-(S_kj - K))
+// with S_kj = S0*u^j*d^(k-j) = S0*u^(2j-k)  (d = 1/u, binomial.py:13).
+//
+// Kernel 1 (N <= 1023): ONE OPTION PER WARP, the whole level lives in registers.
+//   Lane l owns the B contiguous nodes [l*B, l*B+B); a level update is B independent
+//   (DFMA, DFMA, DSETP, 2 SEL) groups per lane plus ONE 64-bit shuffle for the neighbour's
+//   first node, so neither shared memory nor a block barrier sits on the critical path.
+//   Because level k has only k+1 live nodes, the warp re-packs its registers into a
+//   narrower layout (B = 32, 28, 24, ... 1) through a padded shared-memory tile whenever
+//   the live nodes fit; that keeps ~88 % of the issued node updates live (a fixed layout
+//   would idle half the lanes on average).
+//   Exercise values cost one DFMA per node: S_kj = base_k(l) * u^(2i), with u^(2i) (i < B)
+//   held in registers and base_k(l) = S0*u^(2lB-k) advanced by one DMUL per lane per level.
+// Kernel 2 (any N up to the shared-memory limit): one option per CTA, ping-pong level
+//   arrays in shared memory.
+#include <math.h>
+#include "optp_common.cuh"
+
+namespace optp {
+
+constexpr int kWarpsPerCta = 4;
+constexpr int kTileDoubles = 1024 + 40;  // padded re-pack tile per warp
+
+struct CrrArgs {
+    const double *S0, *K, *T, *r, *q, *sigma;
+    const uint8_t* is_call;
+    unsigned long long n;
+    int N;
+    double* price;
+    uint8_t* status;
+};
+
+struct Lattice {
+    double u, pu, pd, S0, sK, sgn;
+    double rho, inv_pd, u_pd;  // pu/pd, 1/pd, u/pd (scaled recursion of the warp kernel)
+    int R;                     // renormalisation interval
+    bool ok;
+};
+
+// binomial.py:11-17
+__device__ __forceinline__ Lattice make_lattice(const CrrArgs& a, unsigned long long o) {
+    Lattice L;
+    const double T = a.T[o], r = a.r[o], q = a.q[o], sg = a.sigma[o];
+    const double dt = T / (double)a.N;
+    L.u = exp(sg * sqrt(dt));
+    const double d = 1.0 / L.u;
+    const double disc = exp(-r * dt);
+    const double p = (exp((r - q) * dt) - d) / (L.u - d);
+    L.ok = (p > 0.0) && (p < 1.0);
+    L.pu = disc * p;
+    L.pd = disc * (1.0 - p);
+    L.S0 = a.S0[o];
+    L.sgn = a.is_call[o] ? 1.0 : -1.0;
+    L.sK = -L.sgn * a.K[o];
+    L.inv_pd = 1.0 / L.pd;
+    L.rho = L.pu * L.inv_pd;
+    L.u_pd = L.u * L.inv_pd;
+    const double al = fabs(log(L.pd));
+    L.R = (al * 16777216.0 > 138.0) ? max(1, (int)(138.0 / al)) : (1 << 24);
+    return L;
+}
+
+// signed base of lane `lane` in layout B at level k:  sgn*S0*u^(2*lane*B - k)
+__device__ __forceinline__ double lane_base(const Lattice& L, int lane, int B, int k) {
+    return L.sgn * L.S0 * pow(L.u, (double)(2 * lane * B - k));
+}
+
+// max(c, e) for c >= 0 and finite-or-inf e: one DSETP + two SELs (fmax() would add the
+// NaN-propagation sequence, ~6 more issue slots per node).
+__device__ __forceinline__ double pick_max(double c, double e) { return e > c ? e : c; }
+
+// Levels k_hi..k_lo in layout B.  To spend ONE DFMA on the continuation value the level is
+// stored scaled: A_k = V_k * pd^-(m), m = levels walked since the last renormalisation, so
+//     A_k[j] = (pu/pd)*A_{k+1}[j+1] + A_{k+1}[j]
+// and the exercise value is scaled alike (two DMULs per LANE per level keep its coefficients).
+// Every L.R levels (and at the end) the registers are multiplied back by pd^m; L.R bounds
+// pd^-m by 2^+-200, so no contract can overflow.  Rounding differs from binomial.py:29 by
+// O(1 ulp) per level -- far inside the 1e-10 parity bar.
+template <int B, bool AMER>
+__device__ __forceinline__ void run_levels(double (&v)[32], const double (&U2)[32], double sb,
+                                           const Lattice& L, int k_hi, int k_lo) {
+    int k = k_hi;
+    while (k >= k_lo) {
+        const int seg_lo = (k - L.R + 1 > k_lo) ? (k - L.R + 1) : k_lo;
+        double sbg = sb, sKg = L.sK, back = 1.0;
+        // the neighbour's first node of the NEXT level is requested as soon as this lane's
+        // first node is updated, so the shuffle latency overlaps the other B-1 updates
+        double nb = __shfl_down_sync(0xffffffffu, v[0], 1);
+        for (; k >= seg_lo; --k) {
+            sbg *= L.u_pd;
+            sKg *= L.inv_pd;
+            back *= L.pd;
+            sb *= L.u;
+            double nb_next = 0.0;
+#pragma unroll
+            for (int i = 0; i < B; ++i) {
+                const double up = (i + 1 < B) ? v[i + 1] : nb;
+                double c = fma(L.rho, up, v[i]);
+                if (AMER) c = pick_max(c, fma(sbg, U2[i], sKg));
+                v[i] = c;
+                if (i == 0) nb_next = __shfl_down_sync(0xffffffffu, c, 1);
+            }
+            nb = nb_next;
+        }
+#pragma unroll
+        for (int i = 0; i < B; ++i) v[i] *= back;
+    }
+}
+
+template <int B0, int B1>
+__device__ __forceinline__ void repack(double (&v)[32], double* tile, int lane) {
+    // keep the index arithmetic here (ptxas otherwise hoists ~100 addresses out of the
+    // option loop and spills)
+    asm volatile("" : "+r"(lane));
+#pragma unroll
+    for (int i = 0; i < B0; ++i) tile[lane * (B0 + 1) + i] = v[i];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < B1; ++i) {
+        const int j = lane * B1 + i;
+        v[i] = tile[j + j / B0];
+    }
+    __syncwarp();
+}
+
+// One stage of the schedule: layout B, entered from layout BPREV, followed by layout BN
+// (BN = 0 ends the schedule).  `k` is the next output level.  Once the walk has started
+// every later stage runs, so the previous layout is always the previous schedule entry.
+template <int BPREV, int B, int BN, bool AMER>
+__device__ __forceinline__ void stage(double (&v)[32], const double (&U2)[32], const Lattice& L,
+                                      int N, int& k, bool& started, double* tile, int lane) {
+    if (!started) {
+        // terminal payoff, binomial.py:20-25
+        const double sbN = lane_base(L, lane, B, N);
+#pragma unroll
+        for (int i = 0; i < B; ++i) v[i] = pick_max(0.0, fma(sbN, U2[i], L.sK));
+        started = true;
+    } else {
+        repack<BPREV, B>(v, tile, lane);
+    }
+    const int k_lo = (BN > 0) ? (32 * BN - 1) : 0;
+    const double sb = AMER ? lane_base(L, lane, B, k + 1) : 0.0;
+    run_levels<B, AMER>(v, U2, sb, L, k, k_lo);
+    k = k_lo - 1;
+}
+
+template <bool AMER>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
+crr_warp_kernel(CrrArgs a) {
+    __shared__ double tiles[kWarpsPerCta][kTileDoubles];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    double* tile = tiles[wib];
+    const unsigned long long warp0 = (unsigned long long)blockIdx.x * kWarpsPerCta + wib;
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * kWarpsPerCta;
+    for (unsigned long long o = warp0; o < a.n; o += nwarps) {
+        const Lattice L = make_lattice(a, o);
+        if (!L.ok) {  // binomial.py:16-17 -> per-contract status instead of raising
+            if (lane == 0) {
+                a.price[o] = nan("");
+                a.status[o] = 1;
+            }
+            continue;
+        }
+        double U2[32], v[32];
+        {
+            const double u2 = L.u * L.u;
+            U2[0] = 1.0;
+#pragma unroll
+            for (int i = 1; i < 32; ++i) U2[i] = U2[i - 1] * u2;
+        }
+        int k = a.N - 1;
+        bool started = false;
+        const int N = a.N;
+        // pick the first layout that holds the N+1 terminal nodes, then walk the schedule
+#define OPTP_STAGE(BP, B, BN)                                                         \
+    if (started || N + 1 > 32 * (BN))                                                 \
+        stage<BP, B, BN, AMER>(v, U2, L, N, k, started, tile, lane);
+        OPTP_STAGE(32, 32, 28)
+        OPTP_STAGE(32, 28, 24)
+        OPTP_STAGE(28, 24, 20)
+        OPTP_STAGE(24, 20, 16)
+        OPTP_STAGE(20, 16, 12)
+        OPTP_STAGE(16, 12, 8)
+        OPTP_STAGE(12, 8, 6)
+        OPTP_STAGE(8, 6, 4)
+        OPTP_STAGE(6, 4, 2)
+        OPTP_STAGE(4, 2, 1)
+        OPTP_STAGE(2, 1, 0)
+#undef OPTP_STAGE
+        if (lane == 0) {
+            a.price[o] = v[0];
+            a.status[o] = 0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- generic N: one option per CTA
+template <bool AMER>
+__global__ void __launch_bounds__(256) crr_cta_kernel(CrrArgs a) {
+    extern __shared__ double sm[];
+    const int N = a.N;
+    const int stride = N + 2;
+    double* bufA = sm;
+    double* bufB = sm + stride;
+    double* W = sm + 2 * stride;  // u^(2j)
+    for (unsigned long long o = blockIdx.x; o < a.n; o += gridDim.x) {
+        const Lattice L = make_lattice(a, o);
+        if (!L.ok) {
+            if (threadIdx.x == 0) {
+                a.price[o] = nan("");
+                a.status[o] = 1;
+            }
+            continue;
+        }
+        __syncthreads();
+        double sbk = L.sgn * L.S0 * pow(L.u, (double)(-N));
+        for (int j = threadIdx.x; j <= N; j += blockDim.x) {
+            const double w = pow(L.u, (double)(2 * j));
+            W[j] = w;
+            bufA[j] = pick_max(0.0, fma(sbk, w, L.sK));
+        }
+        __syncthreads();
+        double* src = bufA;
+        double* dst = bufB;
+        for (int k = N - 1; k >= 0; --k) {
+            sbk *= L.u;
+            for (int j = threadIdx.x; j <= k; j += blockDim.x) {
+                double c = fma(L.pd, src[j], L.pu * src[j + 1]);
+                if (AMER) c = pick_max(c, fma(sbk, W[j], L.sK));
+                dst[j] = c;
+            }
+            __syncthreads();
+            double* t = src;
+            src = dst;
+            dst = t;
+        }
+        if (threadIdx.x == 0) {
+            a.price[o] = src[0];
+            a.status[o] = 0;
+        }
+    }
+}
+
+static int launch_crr(const CrrArgs& a, int american, cudaStream_t st) {
+    Context& c = ctx();
+    if (a.n == 0) return 0;
+    if (a.N <= 1023) {
+        const unsigned long long want = (a.n + kWarpsPerCta - 1) / kWarpsPerCta;
+        int per_sm = 0;
+        if (american)
+            OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, crr_warp_kernel<true>,
+                                                                    kWarpsPerCta * 32, 0));
+        else
+            OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, crr_warp_kernel<false>,
+                                                                    kWarpsPerCta * 32, 0));
+        if (per_sm < 1) per_sm = 1;
+        // persistent warps: exactly one resident wave, options strided over warps
+        const unsigned long long cap = (unsigned long long)c.n_sm * per_sm;
+        const unsigned int grid = (unsigned int)(want < cap ? want : cap);
+        if (american)
+            crr_warp_kernel<true><<<grid, kWarpsPerCta * 32, 0, st>>>(a);
+        else
+            crr_warp_kernel<false><<<grid, kWarpsPerCta * 32, 0, st>>>(a);
+    } else {
+        const size_t smem = sizeof(double) * 3 * (size_t)(a.N + 2);
+        if (smem > 227 * 1024)
+            return set_error(OPTP_E_TOO_LARGE, "N=%d needs %zu B of shared memory (max 232448)", a.N,
+                             smem);
+        const unsigned long long cap = (unsigned long long)c.n_sm * 8;
+        const unsigned int grid = (unsigned int)(a.n < cap ? a.n : cap);
+        if (american) {
+            OPTP_CUDA(cudaFuncSetAttribute(crr_cta_kernel<true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            crr_cta_kernel<true><<<grid, 256, smem, st>>>(a);
+        } else {
+            OPTP_CUDA(cudaFuncSetAttribute(crr_cta_kernel<false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            crr_cta_kernel<false><<<grid, 256, smem, st>>>(a);
+        }
+    }
+    c.launches++;
+    OPTP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace optp
+
+using namespace optp;
+
+extern "C" int optp_crr_batch_dev(const double* S0, const double* K, const double* T,
+                                  const double* r, const double* q, const double* sigma,
+                                  const uint8_t* is_call, uint64_t n, uint32_t N, int american,
+                                  double* price_out, uint8_t* status_out, void* stream) {
+    if (int e = require_ready()) return e;
+    if (N == 0 || N > (1u << 24)) return set_error(OPTP_E_ARG, "N must be positive.");
+    if (n && (!S0 || !K || !T || !r || !q || !sigma || !is_call || !price_out || !status_out))
+        return set_error(OPTP_E_ARG, "null pointer argument");
+    CrrArgs a{S0, K, T, r, q, sigma, is_call, (unsigned long long)n, (int)N, price_out, status_out};
+    return launch_crr(a, american, (cudaStream_t)stream);
+}
+
+extern "C" int optp_crr_batch(const double* S0, const double* K, const double* T, const double* r,
+                              const double* q, const double* sigma, const uint8_t* is_call,
+                              uint64_t n, uint32_t N, int american, double* price_out,
+                              uint8_t* status_out) {
+    if (int e = require_ready()) return e;
+    if (N == 0 || N > (1u << 24)) return set_error(OPTP_E_ARG, "N must be positive.");
+    if (n == 0) return 0;
+    if (!S0 || !K || !T || !r || !q || !sigma || !is_call || !price_out || !status_out)
+        return set_error(OPTP_E_ARG, "null pointer argument");
+    Context& c = ctx();
+    OPTP_CUDA(cudaSetDevice(c.device));
+    // contract batch: six fp64 columns + one byte column, packed into one arena (SoA)
+    const size_t col = (size_t)n * sizeof(double);
+    const size_t colp = (col + 255) & ~(size_t)255;
+    if (int e = arena_reserve(c.in0, 6 * colp + n + 256)) return e;
+    if (int e = arena_reserve(c.out0, colp + n + 256)) return e;
+    char* in = (char*)c.in0.p;
+    const double* src[6] = {S0, K, T, r, q, sigma};
+    for (int i = 0; i < 6; ++i)
+        OPTP_CUDA(cudaMemcpyAsync(in + i * colp, src[i], col, cudaMemcpyHostToDevice, c.stream));
+    OPTP_CUDA(cudaMemcpyAsync(in + 6 * colp, is_call, n, cudaMemcpyHostToDevice, c.stream));
+    char* out = (char*)c.out0.p;
+    CrrArgs a{(const double*)(in),
+              (const double*)(in + colp),
+              (const double*)(in + 2 * colp),
+              (const double*)(in + 3 * colp),
+              (const double*)(in + 4 * colp),
+              (const double*)(in + 5 * colp),
+              (const uint8_t*)(in + 6 * colp),
+              (unsigned long long)n,
+              (int)N,
+              (double*)out,
+              (uint8_t*)(out + colp)};
+    if (int e = launch_crr(a, american, c.stream)) return e;
+    OPTP_CUDA(cudaMemcpyAsync(price_out, out, col, cudaMemcpyDeviceToHost, c.stream));
+    OPTP_CUDA(cudaMemcpyAsync(status_out, out + colp, n, cudaMemcpyDeviceToHost, c.stream));
+    OPTP_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}

@@ -1,0 +1,603 @@
+// Production Monte Carlo kernels (sm_100a): fp32 path state, Philox4x32-10 + Box-Muller
+// normals built in registers, payoff statistics accumulated in fp64.  Paths are never
+// written to HBM: each thread carries one base path AND its antithetic mirror (the mirror
+// re-uses the normal, so the RNG cost is halved per effective path-step), keeps the running
+// path state the payoffs need (max / min / sum S / sum ln S) in registers, and contributes
+// (X, X^2, XY, Y, Y^2) once per path to block-level fp64 partials.
+//
+//   terminal_fp32_kernel   <- _mc_chunk_sumstats          monte_carlo.py:28-64
+//   path_fp32_kernel<GBM>  <- gbm_paths + exotics          processes.py:44-55, exotics.py:18-273
+//   path_fp32_kernel<HES>  <- heston_paths + exotics       processes.py:134-160
+//   path_fp32_kernel<GBMM> <- gbm_milstein_paths           processes.py:284-303
+//   lv_fp32_kernel<LVM>    <- milstein_local_vol_paths     processes.py:345-379
+//   lv_fp32_kernel<LVE>    <- local_vol_paths              processes.py:240-256
+//
+// All log-space work is done in base 2 so exp/log are single MUFU.EX2 / MUFU.LG2 issues.
+// The Philox counter layout (path, step block, stream) is the same one mc_fp64.cu uses in
+// FP64_PHILOX mode, so both modes see the same normals and differ only in arithmetic.
+#include <math.h>
+#include "mc_kernels.cuh"
+
+namespace optp {
+
+constexpr uint32_t kTermStream = 0x7465726du;
+constexpr float kLog2e = 1.4426950408889634f;
+
+// per-step path state requested by the payoffs (finer than OBS_*: max and min are split so
+// an up-barrier does not pay for the running minimum)
+enum : int { M_MAX = 1, M_MIN = 2, M_SUM = 4, M_LOG = 8 };
+
+static int fine_mask(const optp_payoff* p, int n) {
+    int m = 0;
+    for (int i = 0; i < n; ++i) {
+        const bool call = (p[i].flags & OPTP_F_CALL) != 0;
+        switch (p[i].kind) {
+            case OPTP_PAY_BARRIER: m |= (p[i].flags & OPTP_F_UP) ? M_MAX : M_MIN; break;
+            case OPTP_PAY_LOOKBACK:
+                if (p[i].flags & OPTP_F_FLOATING) m |= call ? M_MIN : M_MAX;
+                else m |= call ? M_MAX : M_MIN;
+                break;
+            case OPTP_PAY_ASIAN: m |= (p[i].flags & OPTP_F_GEOMETRIC) ? M_LOG : M_SUM; break;
+            default: break;
+        }
+    }
+    return m;
+}
+
+// the instantiated state sets; a request is served by the first superset in this list
+static const int kMaskSets[] = {0, M_MAX, M_MIN, M_MAX | M_MIN, M_SUM, M_LOG,
+                                M_MAX | M_MIN | M_SUM | M_LOG};
+static int cover_mask(int m) {
+    for (int s : kMaskSets)
+        if ((s & m) == m) return s;
+    return M_MAX | M_MIN | M_SUM | M_LOG;
+}
+
+// ------------------------------------------------------------------ terminal (1 step / path)
+// Each thread owns Philox groups of four consecutive base paths.  Sums are kept in fp32 for
+// kFlush groups (<= 64 effective paths) and then folded into fp64 registers; the discount
+// factor is applied once, to the totals.
+struct TermConst {
+    float c0, sg2, sgn, sgnK;
+};
+
+__device__ __forceinline__ void term_accum(float st, const TermConst& k, float& sx, float& sxx,
+                                           float& sy, float& syy, float& sxy) {
+    const float pay = fmaxf(fmaf(k.sgn, st, k.sgnK), 0.0f);
+    sx += pay;
+    sxx = fmaf(pay, pay, sxx);
+    sy += st;
+    syy = fmaf(st, st, syy);
+    sxy = fmaf(pay, st, sxy);
+}
+
+template <bool ANTI>
+__global__ void __launch_bounds__(256) terminal_fp32_kernel(TermArgs a) {
+    __shared__ double red[32];
+    __shared__ double blockvals[8];
+    const double mu = (a.r - a.q - 0.5 * a.sigma * a.sigma) * a.T;
+    TermConst k;
+    k.c0 = (float)((mu + log(a.S0)) * 1.4426950408889634);
+    k.sg2 = (float)(a.sigma * sqrt(a.T) * 1.4426950408889634);
+    k.sgn = a.is_call ? 1.0f : -1.0f;
+    k.sgnK = (float)(a.is_call ? -a.K : a.K);
+    const double df = exp(-a.r * a.T);
+
+    const unsigned long long first = a.path_offset, last = a.path_offset + a.n_base;  // [first,last)
+    const unsigned long long g_lo = first >> 2, g_hi = (last + 3) >> 2;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    double dsx = 0, dsxx = 0, dsy = 0, dsyy = 0, dsxy = 0;
+    constexpr int kFlush = 8;
+    unsigned long long g = g_lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    while (g < g_hi) {
+        float sx = 0, sxx = 0, sy = 0, syy = 0, sxy = 0;
+#pragma unroll 1
+        for (int it = 0; it < kFlush && g < g_hi; ++it, g += stride) {
+            float z[4];
+            philox_normals4(a.seed, g, 0u, kTermStream, z);
+            const bool full = (g << 2) >= first && (g << 2) + 4 <= last;
+            if (full) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float x = k.sg2 * z[j];
+                    term_accum(mufu_ex2(k.c0 + x), k, sx, sxx, sy, syy, sxy);
+                    if (ANTI) term_accum(mufu_ex2(k.c0 - x), k, sx, sxx, sy, syy, sxy);
+                }
+            } else {
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned long long p = (g << 2) + j;
+                    if (p < first || p >= last) continue;
+                    const float x = k.sg2 * z[j];
+                    term_accum(mufu_ex2(k.c0 + x), k, sx, sxx, sy, syy, sxy);
+                    if (ANTI) term_accum(mufu_ex2(k.c0 - x), k, sx, sxx, sy, syy, sxy);
+                }
+            }
+        }
+        dsx += (double)sx;
+        dsxx += (double)sxx;
+        dsy += (double)sy;
+        dsyy += (double)syy;
+        dsxy += (double)sxy;
+    }
+    double vals[5] = {dsx * df, dsxx * df * df, dsy * df, dsyy * df * df, dsxy * df * df};
+    for (int i = 0; i < 5; ++i) {
+        const double t = block_sum(vals[i], red);
+        if (threadIdx.x == 0) blockvals[i] = t;
+    }
+    __syncthreads();
+    double* stats = a.stats;
+    const double n = (double)(ANTI ? 2 * a.n_base : a.n_base);
+    finalize_partials(a.partials, a.ticket, blockvals, 5, [=](int i, double s) {
+        stats[1 + i] = s;
+        if (i == 0) {
+            stats[0] = n;
+            stats[6] = 0.0;
+            stats[7] = 0.0;
+        }
+    });
+}
+
+int launch_terminal_fp32(const TermArgs& a, cudaStream_t st) {
+    const unsigned long long groups = (a.n_base + 3) / 4 + 1;
+    unsigned long long blocks = (groups + 255) / 256;
+    const unsigned long long cap = (unsigned long long)ctx().n_sm * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (a.anti)
+        terminal_fp32_kernel<true><<<(unsigned int)blocks, 256, 0, st>>>(a);
+    else
+        terminal_fp32_kernel<false><<<(unsigned int)blocks, 256, 0, st>>>(a);
+    ctx().launches++;
+    OPTP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------ per-path epilogue
+// Turns the running state of ONE effective path into payoffs and adds them to the thread's
+// fp64 accumulators (shared memory, acc[value][thread]).
+struct PathEnd {
+    float ST, smax, smin, avgA, avgG;
+};
+
+__device__ __forceinline__ void path_epilogue(const PathArgs& a, const PathEnd& e, float df,
+                                              unsigned long long col, unsigned long long n_eff,
+                                              double* acc) {
+    if (a.terminal_out) a.terminal_out[col] = (double)e.ST;
+    const float Y = df * e.ST;
+    acc_add(acc, 0, (double)Y);
+    acc_add(acc, 1, (double)Y * (double)Y);
+    for (int p = 0; p < a.n_pay; ++p) {
+        const float pay = eval_payoff<float>(a.pay[p], e.ST, e.smax, e.smin, e.avgA, e.avgG);
+        if (a.payoff_out) a.payoff_out[(size_t)p * n_eff + col] = (double)pay;
+        const float X = df * pay;
+        acc_add(acc, 3 + 3 * p, (double)X);
+        acc_add(acc, 4 + 3 * p, (double)X * (double)X);
+        acc_add(acc, 5 + 3 * p, (double)X * (double)Y);
+    }
+}
+
+// ------------------------------------------------------------------ GBM / Heston / GBM-Milstein
+// One thread = one base path (+ mirror).  State lives in log2(S/S0) for GBM and Heston.
+struct LogState {  // one effective path in log2 space
+    float x = 0.f, xmax = 0.f, xmin = 0.f, sum = 0.f, slog = 0.f;
+};
+
+template <int MASK>
+__device__ __forceinline__ void observe_log(LogState& s) {
+    if (MASK & M_MAX) s.xmax = fmaxf(s.xmax, s.x);
+    if (MASK & M_MIN) s.xmin = fminf(s.xmin, s.x);
+    if (MASK & M_SUM) s.sum += mufu_ex2(s.x);
+    if (MASK & M_LOG) s.slog += s.x;
+}
+
+template <int MASK>
+__device__ __forceinline__ PathEnd finish_log(const LogState& s, float S0, float inv_n) {
+    PathEnd e;
+    e.ST = S0 * mufu_ex2(s.x);
+    e.smax = (MASK & M_MAX) ? S0 * mufu_ex2(s.xmax) : e.ST;
+    e.smin = (MASK & M_MIN) ? S0 * mufu_ex2(s.xmin) : e.ST;
+    e.avgA = (MASK & M_SUM) ? S0 * s.sum * inv_n : 0.f;
+    e.avgG = (MASK & M_LOG) ? S0 * mufu_ex2(s.slog * inv_n) : 0.f;
+    return e;
+}
+
+struct LinState {  // one effective path in linear space (Milstein schemes)
+    float S, smax, smin, sum = 0.f, slog = 0.f;
+};
+
+template <int MASK>
+__device__ __forceinline__ void observe_lin(LinState& s) {
+    if (MASK & M_MAX) s.smax = fmaxf(s.smax, s.S);
+    if (MASK & M_MIN) s.smin = fminf(s.smin, s.S);
+    if (MASK & M_SUM) s.sum += s.S;
+    if (MASK & M_LOG) s.slog += mufu_lg2(s.S);
+}
+
+template <int MASK>
+__device__ __forceinline__ PathEnd finish_lin(const LinState& s, float inv_n) {
+    PathEnd e;
+    e.ST = s.S;
+    e.smax = (MASK & M_MAX) ? s.smax : s.S;
+    e.smin = (MASK & M_MIN) ? s.smin : s.S;
+    e.avgA = (MASK & M_SUM) ? s.sum * inv_n : 0.f;
+    e.avgG = (MASK & M_LOG) ? mufu_ex2(s.slog * inv_n) : 0.f;
+    return e;
+}
+
+struct StepConst {
+    // GBM (log2 units)
+    float vol2, drift2;
+    // Heston (x in log2 units, v in natural units)
+    float rho, rhoc, h_sdt2, h_mhalf2, h_rq2, h_c1, h_kt, h_xs;
+    // GBM Milstein (linear)
+    float m_c1, m_ssdt, m_hs2dt;
+};
+
+template <int PROC, int MASK, bool ANTI>
+__global__ void __launch_bounds__(256) path_fp32_kernel(PathArgs a) {
+    extern __shared__ double dyn[];
+    __shared__ double blockvals[kMaxVals];
+    double* acc = dyn;
+    acc_zero(acc, 3 + 3 * a.n_pay);
+
+    const unsigned int n_steps = a.n_steps;
+    const double dt = a.T / (double)n_steps;
+    const double sdt = sqrt(dt);
+    constexpr double L2E = 1.4426950408889634;
+    StepConst k;
+    k.vol2 = (float)(a.sigma * sdt * L2E);
+    k.drift2 = (float)((a.r - a.q - 0.5 * a.sigma * a.sigma) * dt * L2E);
+    k.rho = (float)a.rho;
+    k.rhoc = (float)sqrt(fmax(0.0, 1.0 - a.rho * a.rho));
+    k.h_sdt2 = (float)(sdt * L2E);
+    k.h_mhalf2 = (float)(-0.5 * dt * L2E);
+    k.h_rq2 = (float)((a.r - a.q) * dt * L2E);
+    k.h_c1 = (float)(1.0 - a.kappa * dt);
+    k.h_kt = (float)(a.kappa * a.theta * dt);
+    k.h_xs = (float)(a.xi * sdt);
+    k.m_c1 = (float)(1.0 + (a.r - a.q) * dt);
+    k.m_ssdt = (float)(a.sigma * sdt);
+    k.m_hs2dt = (float)(0.5 * a.sigma * a.sigma * dt);
+    const float S0 = (float)a.S0;
+    const float inv_n = (float)(1.0 / (double)n_steps);
+    const float df = (float)exp(-a.pay[0].r_disc * a.pay[0].T_disc);
+    const unsigned long long n_eff = ANTI ? 2 * a.n_base : a.n_base;
+    constexpr int kDims = (PROC == OPTP_PROC_HESTON_FTE) ? 2 : 1;
+    constexpr int kPerCall = 4 / kDims;
+    const unsigned int n_calls = (n_steps + kPerCall - 1) / kPerCall;
+
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+         b < a.n_base; b += stride) {
+        const unsigned long long gpath = a.path_offset + b;
+        PathEnd ep, em;
+        if (PROC == OPTP_PROC_GBM) {
+            // S_t = S0*2^(t*drift2 +- W_t), W_t = sum vol2*z  (processes.py:44-55)
+            LogState p, m;
+            float w = 0.f;
+            unsigned int t = 0;
+#pragma unroll 1
+            for (unsigned int c = 0; c < n_calls; ++c) {
+                float z[4];
+                philox_normals4(a.seed, gpath, c, 0u, z);
+#pragma unroll
+                for (int j = 0; j < 4; ++j, ++t) {
+                    if (t < n_steps) {
+                        const float td = (float)(t + 1) * k.drift2;
+                        w = fmaf(k.vol2, z[j], w);
+                        p.x = td + w;
+                        observe_log<MASK>(p);
+                        if (ANTI) {
+                            m.x = td - w;
+                            observe_log<MASK>(m);
+                        }
+                    }
+                }
+            }
+            ep = finish_log<MASK>(p, S0, inv_n);
+            if (ANTI) em = finish_log<MASK>(m, S0, inv_n);
+        } else if (PROC == OPTP_PROC_HESTON_FTE) {
+            // full-truncation Euler (processes.py:150-160); v >= 0 is re-established at the end
+            // of every step, so max(v,0) at the start of the next one is the identity.
+            LogState p, m;
+            float vp = fmaxf((float)a.v0, 0.f), vm = vp;
+            unsigned int t = 0;
+#pragma unroll 1
+            for (unsigned int c = 0; c < n_calls; ++c) {
+                float z[4];
+                philox_normals4(a.seed, gpath, c, 0u, z);
+#pragma unroll
+                for (int j = 0; j < 2; ++j, ++t) {
+                    if (t < n_steps) {
+                        const float z0 = z[2 * j], zc = fmaf(k.rho, z0, k.rhoc * z[2 * j + 1]);
+                        {
+                            const float sq = mufu_sqrt(vp);
+                            p.x = fmaf(sq * zc, k.h_sdt2, fmaf(vp, k.h_mhalf2, p.x + k.h_rq2));
+                            vp = fmaxf(fmaf(sq * z0, k.h_xs, fmaf(vp, k.h_c1, k.h_kt)), 0.f);
+                            observe_log<MASK>(p);
+                        }
+                        if (ANTI) {
+                            const float sq = mufu_sqrt(vm);
+                            m.x = fmaf(-(sq * zc), k.h_sdt2, fmaf(vm, k.h_mhalf2, m.x + k.h_rq2));
+                            vm = fmaxf(fmaf(-(sq * z0), k.h_xs, fmaf(vm, k.h_c1, k.h_kt)), 0.f);
+                            observe_log<MASK>(m);
+                        }
+                    }
+                }
+            }
+            ep = finish_log<MASK>(p, S0, inv_n);
+            if (ANTI) em = finish_log<MASK>(m, S0, inv_n);
+        } else {  // OPTP_PROC_GBM_MILSTEIN, processes.py:296-303
+            LinState p, m;
+            p.S = p.smax = p.smin = S0;
+            m = p;
+            unsigned int t = 0;
+#pragma unroll 1
+            for (unsigned int c = 0; c < n_calls; ++c) {
+                float z[4];
+                philox_normals4(a.seed, gpath, c, 0u, z);
+#pragma unroll
+                for (int j = 0; j < 4; ++j, ++t) {
+                    if (t < n_steps) {
+                        const float zs = k.m_ssdt * z[j];
+                        const float zq = fmaf(k.m_hs2dt * z[j], z[j], k.m_c1 - k.m_hs2dt);
+                        p.S = fmaxf(p.S * (zq + zs), 1e-10f);
+                        observe_lin<MASK>(p);
+                        if (ANTI) {
+                            m.S = fmaxf(m.S * (zq - zs), 1e-10f);
+                            observe_lin<MASK>(m);
+                        }
+                    }
+                }
+            }
+            ep = finish_lin<MASK>(p, inv_n);
+            if (ANTI) em = finish_lin<MASK>(m, inv_n);
+        }
+        path_epilogue(a, ep, df, b, n_eff, acc);
+        if (ANTI) path_epilogue(a, em, df, a.n_base + b, n_eff, acc);
+    }
+    reduce_and_emit(acc, blockvals, a.n_pay, (double)n_eff, a.partials, a.ticket, a.stats);
+}
+
+// ------------------------------------------------------------------ local volatility
+// sigma(S,t) table: row i (step time i*dt) holds n_nodes (value, next-value minus value) pairs
+// on a uniform ln S grid.  The CTA walks the steps in lock step: a chunk of rows is staged in
+// shared memory, every thread advances its paths through the chunk, the next chunk is staged.
+// Lookup: pos = (log2 S - x0_2)/h_2 clamped to [0, n-1]; the cell index comes from the
+// round-to-nearest "magic number" add (no F2I on the XU pipe), then one LDS.64 and one FFMA.
+struct LvConst {
+    float inv_h2, c0, pos_max, c_up, c_dn, k_up, k_dn, c1, sdt, hdt;
+    float e_sdt2, e_mhalf2, e_rq2;  // log-Euler variant
+};
+
+__device__ __forceinline__ float table_sigma32(const float2* row, float pos, float pos_max) {
+    const float pc = fminf(fmaxf(pos, 0.f), pos_max);
+    const float t = (pc - 0.5f) + 12582912.0f;
+    const int j = __float_as_int(t) - 0x4B400000;
+    const float w = pc - (t - 12582912.0f);
+    const float2 e = row[j];
+    return fmaf(w, e.y, e.x);
+}
+
+template <int PROC, int MASK>
+__device__ __forceinline__ void lv_step(LinState& s, const float2* row, const LvConst& k, float zs,
+                                        float zzh, float z, unsigned int& clamps) {
+    const float pos = fmaf(mufu_lg2(s.S), k.inv_h2, k.c0);
+    clamps += (pos < 0.f || pos > k.pos_max) ? 1u : 0u;
+    float sig = table_sigma32(row, pos, k.pos_max);
+    if (PROC == OPTP_PROC_LV_MILSTEIN) {
+        // processes.py:361-379.  s_up = S(1+b), s_dn = S(1-b): the bumped lookups are constant
+        // offsets in pos, and S cancels from d(sigma*S)/dS.
+        sig = fminf(fmaxf(sig, 1e-8f), 10.0f);
+        const float sig_up = table_sigma32(row, pos + k.c_up, k.pos_max);
+        const float sig_dn = table_sigma32(row, pos + k.c_dn, k.pos_max);
+        const float da = fmaf(sig_up, k.k_up, -(sig_dn * k.k_dn));
+        const float av = sig * s.S;
+        s.S = fmaxf(fmaf(av, fmaf(da, zzh, zs), s.S * k.c1), 1e-10f);
+    } else {  // LV_EULER, processes.py:253-256
+        sig = fmaxf(sig, 0.f);
+        const float ex = fmaf(sig * z, k.e_sdt2, fmaf(sig * sig, k.e_mhalf2, k.e_rq2));
+        s.S = s.S * mufu_ex2(ex);
+    }
+    observe_lin<MASK>(s);
+}
+
+constexpr int kLvThreads = 256;
+
+template <int PROC, int MASK, bool ANTI>
+__global__ void __launch_bounds__(kLvThreads) lv_fp32_kernel(PathArgs a, int rows_per_chunk) {
+    extern __shared__ double dyn[];
+    __shared__ double blockvals[kMaxVals];
+    const int n_vals = 3 + 3 * a.n_pay;
+    double* acc = dyn;
+    float2* rows = reinterpret_cast<float2*>(dyn + (size_t)n_vals * kLvThreads);
+    acc_zero(acc, n_vals);
+
+    const unsigned int n_steps = a.n_steps;
+    const double dt = a.T / (double)n_steps;
+    const double sdt = sqrt(dt);
+    constexpr double L2E = 1.4426950408889634, LN2 = 0.6931471805599453;
+    LvConst k;
+    k.inv_h2 = (float)(LN2 / a.h);              // d pos / d log2 S
+    k.c0 = (float)(-a.x0 / a.h);
+    k.pos_max = (float)(a.n_nodes - 1);
+    k.c_up = (float)(log1p(a.bump) / a.h);
+    k.c_dn = (float)(log1p(-fmin(a.bump, 0.999999)) / a.h);
+    k.k_up = (float)((1.0 + a.bump) / (2.0 * a.bump));
+    k.k_dn = (float)((1.0 - a.bump) / (2.0 * a.bump));
+    k.c1 = (float)(1.0 + (a.r - a.q) * dt);
+    k.sdt = (float)sdt;
+    k.hdt = (float)(0.5 * dt);
+    k.e_sdt2 = (float)(sdt * L2E);
+    k.e_mhalf2 = (float)(-0.5 * dt * L2E);
+    k.e_rq2 = (float)((a.r - a.q) * dt * L2E);
+    const float S0 = (float)a.S0;
+    const float inv_n = (float)(1.0 / (double)n_steps);
+    const float df = (float)exp(-a.pay[0].r_disc * a.pay[0].T_disc);
+    const unsigned long long n_eff = ANTI ? 2 * a.n_base : a.n_base;
+    const int n_ld = (a.n_nodes + 1) & ~1;  // padded row length of the fp32 table
+
+    const unsigned long long n_slabs = (a.n_base + kLvThreads - 1) / kLvThreads;
+    for (unsigned long long slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
+        const unsigned long long b = slab * kLvThreads + threadIdx.x;
+        const bool active = b < a.n_base;
+        const unsigned long long gpath = a.path_offset + b;
+        LinState p, m;
+        p.S = p.smax = p.smin = S0;
+        m = p;
+        unsigned int clamps = 0;
+        for (unsigned int t0 = 0; t0 < n_steps; t0 += rows_per_chunk) {
+            const unsigned int nr = min((unsigned int)rows_per_chunk, n_steps - t0);
+            __syncthreads();  // everyone is done with the previous chunk
+            {
+                const float4* src = reinterpret_cast<const float4*>(a.table32 + (size_t)t0 * n_ld);
+                float4* dst = reinterpret_cast<float4*>(rows);
+                const unsigned int n4 = nr * (unsigned int)n_ld / 2;
+                for (unsigned int i = threadIdx.x; i < n4; i += kLvThreads) dst[i] = __ldg(src + i);
+            }
+            __syncthreads();
+            if (active) {
+#pragma unroll 1
+                for (unsigned int r = 0; r < nr; r += 4) {
+                    float z[4];
+                    philox_normals4(a.seed, gpath, (t0 + r) >> 2, 0u, z);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (r + j < nr) {
+                            const float2* row = rows + (size_t)(r + j) * n_ld;
+                            const float zs = k.sdt * z[j];
+                            const float zzh = k.hdt * fmaf(z[j], z[j], -1.0f);
+                            lv_step<PROC, MASK>(p, row, k, zs, zzh, z[j], clamps);
+                            if (ANTI) lv_step<PROC, MASK>(m, row, k, -zs, zzh, -z[j], clamps);
+                        }
+                    }
+                }
+            }
+        }
+        if (active) {
+            acc_add(acc, 2, (double)clamps);
+            path_epilogue(a, finish_lin<MASK>(p, inv_n), df, b, n_eff, acc);
+            if (ANTI) path_epilogue(a, finish_lin<MASK>(m, inv_n), df, a.n_base + b, n_eff, acc);
+        }
+    }
+    reduce_and_emit(acc, blockvals, a.n_pay, (double)n_eff, a.partials, a.ticket, a.stats);
+}
+
+// fp64 table -> (value, slope) fp32 pairs, rows padded to an even node count (16-byte rows)
+__global__ void table_convert_kernel(const double* t64, float2* t32, unsigned int n_steps,
+                                     int n_nodes) {
+    const int n_ld = (n_nodes + 1) & ~1;
+    const size_t n = (size_t)n_steps * n_ld;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(i % n_ld);
+        const size_t r = i / n_ld;
+        const int jc = j < n_nodes ? j : n_nodes - 1;
+        const double v = t64[r * n_nodes + jc];
+        const double nx = (jc + 1 < n_nodes) ? t64[r * n_nodes + jc + 1] : v;
+        t32[i] = make_float2((float)v, (float)(nx - v));
+    }
+}
+
+int launch_table_convert(const double* t64, float2* t32, unsigned int n_steps, int n_nodes,
+                         cudaStream_t st) {
+    table_convert_kernel<<<64, 256, 0, st>>>(t64, t32, n_steps, n_nodes);
+    ctx().launches++;
+    OPTP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------ dispatch
+bool path_fp32_supported(int proc) {
+    return proc == OPTP_PROC_GBM || proc == OPTP_PROC_HESTON_FTE || proc == OPTP_PROC_GBM_MILSTEIN ||
+           proc == OPTP_PROC_LV_MILSTEIN || proc == OPTP_PROC_LV_EULER;
+}
+
+template <int PROC, int MASK, bool ANTI>
+static int launch_generic(const PathArgs& a, cudaStream_t st) {
+    const int threads = 256;
+    const size_t smem = sizeof(double) * (3 + 3 * a.n_pay) * threads;
+    if (smem > 48 * 1024)
+        OPTP_CUDA(cudaFuncSetAttribute(path_fp32_kernel<PROC, MASK, ANTI>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &per_sm, path_fp32_kernel<PROC, MASK, ANTI>, threads, smem));
+    if (per_sm < 1) per_sm = 1;
+    unsigned long long blocks = (a.n_base + threads - 1) / threads;
+    unsigned long long cap = (unsigned long long)ctx().n_sm * per_sm;
+    if (cap > kMaxBlocks) cap = kMaxBlocks;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    path_fp32_kernel<PROC, MASK, ANTI><<<(unsigned int)blocks, threads, smem, st>>>(a);
+    ctx().launches++;
+    OPTP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int PROC, int MASK, bool ANTI>
+static int launch_lv(const PathArgs& a, cudaStream_t st) {
+    const size_t acc_bytes = sizeof(double) * (3 + 3 * a.n_pay) * kLvThreads;
+    const size_t row_bytes = sizeof(float2) * (size_t)((a.n_nodes + 1) & ~1);
+    // chunk of rows: a multiple of 4 (one Philox call = 4 steps), about 32 KB
+    int rows = (int)((32 * 1024) / row_bytes) & ~3;
+    if (rows < 4) rows = 4;
+    const int max_rows = (int)((a.n_steps + 3) & ~3u);
+    if (rows > max_rows) rows = max_rows;
+    const size_t smem = acc_bytes + rows * row_bytes;
+    if (smem > 200 * 1024)
+        return set_error(OPTP_E_TOO_LARGE, "sigma table rows of %d nodes do not fit shared memory",
+                         a.n_nodes);
+    if (smem > 48 * 1024)
+        OPTP_CUDA(cudaFuncSetAttribute(lv_fp32_kernel<PROC, MASK, ANTI>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &per_sm, lv_fp32_kernel<PROC, MASK, ANTI>, kLvThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    unsigned long long blocks = (a.n_base + kLvThreads - 1) / kLvThreads;
+    unsigned long long cap = (unsigned long long)ctx().n_sm * per_sm;
+    if (cap > kMaxBlocks) cap = kMaxBlocks;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    lv_fp32_kernel<PROC, MASK, ANTI><<<(unsigned int)blocks, kLvThreads, smem, st>>>(a, rows);
+    ctx().launches++;
+    OPTP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int PROC, int MASK>
+static int launch_anti(const PathArgs& a, cudaStream_t st) {
+    if constexpr (PROC == OPTP_PROC_LV_MILSTEIN || PROC == OPTP_PROC_LV_EULER)
+        return a.anti ? launch_lv<PROC, MASK, true>(a, st) : launch_lv<PROC, MASK, false>(a, st);
+    else
+        return a.anti ? launch_generic<PROC, MASK, true>(a, st)
+                      : launch_generic<PROC, MASK, false>(a, st);
+}
+
+template <int PROC>
+static int launch_mask(const PathArgs& a, int mask, cudaStream_t st) {
+    switch (mask) {
+        case 0: return launch_anti<PROC, 0>(a, st);
+        case M_MAX: return launch_anti<PROC, M_MAX>(a, st);
+        case M_MIN: return launch_anti<PROC, M_MIN>(a, st);
+        case M_MAX | M_MIN: return launch_anti<PROC, M_MAX | M_MIN>(a, st);
+        case M_SUM: return launch_anti<PROC, M_SUM>(a, st);
+        case M_LOG: return launch_anti<PROC, M_LOG>(a, st);
+        default: return launch_anti<PROC, M_MAX | M_MIN | M_SUM | M_LOG>(a, st);
+    }
+}
+
+int launch_path_fp32(const PathArgs& a, cudaStream_t st) {
+    const int mask = cover_mask(fine_mask(a.pay, a.n_pay));
+    switch (a.proc) {
+        case OPTP_PROC_GBM: return launch_mask<OPTP_PROC_GBM>(a, mask, st);
+        case OPTP_PROC_HESTON_FTE: return launch_mask<OPTP_PROC_HESTON_FTE>(a, mask, st);
+        case OPTP_PROC_GBM_MILSTEIN: return launch_mask<OPTP_PROC_GBM_MILSTEIN>(a, mask, st);
+        case OPTP_PROC_LV_MILSTEIN: return launch_mask<OPTP_PROC_LV_MILSTEIN>(a, mask, st);
+        case OPTP_PROC_LV_EULER: return launch_mask<OPTP_PROC_LV_EULER>(a, mask, st);
+        default: return set_error(OPTP_E_KIND, "process kind %d has no fp32 kernel", a.proc);
+    }
+}
+
+}  // namespace optp

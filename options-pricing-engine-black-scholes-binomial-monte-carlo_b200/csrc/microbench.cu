@@ -1,0 +1,161 @@
+// Roofline denominators MEASURED_PEAKS.json does not carry: the FP32 FFMA issue rate, the MUFU
+// rate, the FP64 DFMA rate, shared-memory LDS.64 bandwidth and the IMAD.WIDE rate (the Philox
+// multiplier).  Each kernel keeps 8 independent dependency chains per thread, 1024 threads per
+// CTA and two CTAs per SM, so the measured figure is the pipe's issue limit, not its latency.
+// bench.py calls these in the same run as the timed kernels so the clock state is comparable.
+#include "optp_common.cuh"
+
+namespace optp {
+
+constexpr int kIters = 4096;
+constexpr int kChains = 8;
+
+template <int WHICH>
+__global__ void __launch_bounds__(1024, 2)
+peak_kernel(float* sink, long long* clocks, float seed_f, double seed_d, unsigned int seed_u) {
+    __shared__ double lds_buf[2048];
+    const long long c0 = clock64();
+    if (WHICH == 0) {  // FFMA
+        float v[kChains];
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) v[i] = seed_f + (float)(threadIdx.x + i);
+        const float m = seed_f * 0.5f + 0.999f, c = seed_f;
+#pragma unroll 1
+        for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int i = 0; i < kChains; ++i) v[i] = fmaf(v[i], m, c);
+        }
+        float s = 0;
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) s += v[i];
+        if (s == 123.456f) sink[0] = s;
+    } else if (WHICH == 1) {  // MUFU.EX2
+        float v[kChains];
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) v[i] = seed_f - (float)i * 0.01f;
+#pragma unroll 1
+        for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int i = 0; i < kChains; ++i) v[i] = mufu_ex2(v[i]);
+        }
+        float s = 0;
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) s += v[i];
+        if (s == 123.456f) sink[0] = s;
+    } else if (WHICH == 2) {  // DFMA
+        double v[kChains];
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) v[i] = seed_d + (double)(threadIdx.x + i);
+        const double m = seed_d * 0.5 + 0.999, c = seed_d;
+#pragma unroll 1
+        for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int i = 0; i < kChains; ++i) v[i] = fma(v[i], m, c);
+        }
+        double s = 0;
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) s += v[i];
+        if (s == 123.456) sink[0] = (float)s;
+    } else if (WHICH == 3) {  // LDS.64, conflict free (consecutive lanes, consecutive doubles)
+        for (int i = threadIdx.x; i < 2048; i += blockDim.x) lds_buf[i] = seed_d + i;
+        __syncthreads();
+        double s[kChains];
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) s[i] = 0.0;
+        unsigned int idx = threadIdx.x;
+#pragma unroll 1
+        for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                for (int i = 0; i < kChains; ++i) {
+                    const volatile double* p = lds_buf + ((idx + 32u * i) & 2047u);
+                    s[i] += *p;
+                }
+                idx += seed_u;
+            }
+        }
+        double t = 0;
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) t += s[i];
+        if (t == 123.456) sink[0] = (float)t;
+    } else {  // IMAD.WIDE (32x32 -> 64), the Philox round multiplier
+        unsigned int v[kChains];
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) v[i] = seed_u + threadIdx.x + i;
+#pragma unroll 1
+        for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int i = 0; i < kChains; ++i) {
+                    const unsigned long long p = (unsigned long long)v[i] * 0xD2511F53u;
+                    v[i] = (unsigned int)(p >> 32) ^ (unsigned int)p;
+                }
+        }
+        unsigned int s = 0;
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) s ^= v[i];
+        if (s == 0x12345u) sink[0] = (float)s;
+    }
+    const long long c1 = clock64();
+    if (blockIdx.x == 0 && threadIdx.x == 0) clocks[0] = c1 - c0;
+}
+
+template <int WHICH>
+static int run_peak(double* per_second, double* mhz) {
+    Context& c = ctx();
+    OPTP_CUDA(cudaSetDevice(c.device));
+    if (int e = arena_reserve(c.out1, 256)) return e;
+    float* sink = (float*)c.out1.p;
+    long long* clocks = (long long*)((char*)c.out1.p + 64);
+    const int grid = c.n_sm * 2;
+    cudaEvent_t e0, e1;
+    OPTP_CUDA(cudaEventCreate(&e0));
+    OPTP_CUDA(cudaEventCreate(&e1));
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {  // rep 0 warms up
+        OPTP_CUDA(cudaEventRecord(e0, c.stream));
+        peak_kernel<WHICH><<<grid, 1024, 0, c.stream>>>(sink, clocks, 1.0f, 1.0, 1u);
+        c.launches++;
+        OPTP_CUDA(cudaEventRecord(e1, c.stream));
+        OPTP_CUDA(cudaEventSynchronize(e1));
+        OPTP_CUDA(cudaGetLastError());
+        float ms = 0;
+        OPTP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best_ms) best_ms = ms;
+    }
+    long long cyc = 0;
+    OPTP_CUDA(cudaMemcpy(&cyc, clocks, sizeof(cyc), cudaMemcpyDeviceToHost));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double ops = (double)grid * 1024.0 * (double)kIters * 4.0 * kChains;
+    const double scale = (WHICH == 3) ? 8.0 : 1.0;  // bytes per LDS.64 lane-op
+    *per_second = ops * scale / (best_ms * 1e-3);
+    // one CTA's cycle count over the kernel's wall time: a lower bound of the SM clock
+    if (mhz) *mhz = (double)cyc / (best_ms * 1e-3) * 1e-6;
+    return 0;
+}
+
+}  // namespace optp
+
+using namespace optp;
+
+extern "C" int optp_microbench(int which, double* per_second_out, double* sm_clock_mhz_out) {
+    if (int e = require_ready()) return e;
+    if (!per_second_out) return set_error(OPTP_E_ARG, "null output pointer");
+    switch (which) {
+        case 0: return run_peak<0>(per_second_out, sm_clock_mhz_out);
+        case 1: return run_peak<1>(per_second_out, sm_clock_mhz_out);
+        case 2: return run_peak<2>(per_second_out, sm_clock_mhz_out);
+        case 3: return run_peak<3>(per_second_out, sm_clock_mhz_out);
+        case 4: return run_peak<4>(per_second_out, sm_clock_mhz_out);
+        default: return set_error(OPTP_E_ARG, "unknown microbenchmark %d", which);
+    }
+}

@@ -1,0 +1,132 @@
+// Context, error reporting and memory helpers of the C ABI (include/optp_b200.h).
+#include <stdarg.h>
+#include <string.h>
+#include "optp_common.cuh"
+
+namespace optp {
+
+static Context g_ctx;
+static thread_local char g_err[512] = "";
+
+Context& ctx() { return g_ctx; }
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    cudaGetLastError();  // clear the sticky flag for non-fatal errors
+    return -(int)e;
+}
+
+int arena_reserve(Arena& a, size_t bytes) {
+    if (bytes <= a.cap) return 0;
+    if (a.p) {
+        OPTP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+        OPTP_CUDA(cudaFree(a.p));
+        a.p = nullptr;
+        a.cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    OPTP_CUDA(cudaMalloc(&a.p, want));
+    a.cap = want;
+    return 0;
+}
+
+int require_ready() {
+    if (!g_ctx.ready) return set_error(OPTP_E_NOINIT, "optp_init() has not been called");
+    return 0;
+}
+
+static void arena_free(Arena& a) {
+    if (a.p) cudaFree(a.p);
+    a.p = nullptr;
+    a.cap = 0;
+}
+
+}  // namespace optp
+
+using namespace optp;
+
+extern "C" {
+
+int optp_abi_version(void) { return OPTP_ABI_VERSION; }
+
+const char* optp_last_error(void) { return g_err; }
+
+int optp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int optp_init(int device) {
+    Context& c = g_ctx;
+    if (c.ready && c.device == device) return 0;
+    if (c.ready) optp_shutdown();
+    int n = 0;
+    OPTP_CUDA(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n)
+        return set_error(OPTP_E_ARG, "device %d out of range (%d visible)", device, n);
+    OPTP_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    OPTP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return set_error(OPTP_E_ARG, "device %d is sm_%d%d; this library is built for sm_100a only",
+                         device, prop.major, prop.minor);
+    c.device = device;
+    c.n_sm = prop.multiProcessorCount;
+    OPTP_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    OPTP_CUDA(cudaMalloc(&c.partials, sizeof(double) * (size_t)kMaxBlocks * kMaxVals));
+    OPTP_CUDA(cudaMalloc(&c.ticket, sizeof(unsigned int)));
+    OPTP_CUDA(cudaMemset(c.ticket, 0, sizeof(unsigned int)));
+    OPTP_CUDA(cudaMalloc(&c.stats_dev, sizeof(double) * kMaxPayoffs * OPTP_NSTATS));
+    OPTP_CUDA(cudaHostAlloc(&c.stats_host, sizeof(double) * kMaxPayoffs * OPTP_NSTATS,
+                            cudaHostAllocDefault));
+    c.launches = 0;
+    c.ready = true;
+    return 0;
+}
+
+int optp_shutdown(void) {
+    Context& c = g_ctx;
+    if (!c.ready) return 0;
+    cudaSetDevice(c.device);
+    cudaStreamSynchronize(c.stream);
+    arena_free(c.in0);
+    arena_free(c.in1);
+    arena_free(c.out0);
+    arena_free(c.out1);
+    arena_free(c.table_f32);
+    arena_free(c.table_f64);
+    cudaFree(c.partials);
+    cudaFree(c.ticket);
+    cudaFree(c.stats_dev);
+    cudaFreeHost(c.stats_host);
+    cudaStreamDestroy(c.stream);
+    c = Context();
+    return 0;
+}
+
+uint64_t optp_launch_count(void) { return g_ctx.launches; }
+
+int optp_host_alloc(void** p, uint64_t bytes) {
+    if (!p) return set_error(OPTP_E_ARG, "null pointer");
+    OPTP_CUDA(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault));
+    return 0;
+}
+
+int optp_host_free(void* p) {
+    if (p) OPTP_CUDA(cudaFreeHost(p));
+    return 0;
+}
+
+}  // extern "C"

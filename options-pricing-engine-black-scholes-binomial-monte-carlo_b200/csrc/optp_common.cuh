@@ -1,0 +1,186 @@
+// Shared device/host helpers of the B200 pricing library: context, Philox4x32-10,
+// Box-Muller normals built in registers, fp64 block reduction with a deterministic
+// last-block finalise.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/optp_b200.h"
+
+namespace optp {
+
+// ------------------------------------------------------------------ host context
+struct Arena {          // grow-only device scratch
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct Context {
+    int device = -1;
+    bool ready = false;
+    int n_sm = 0;
+    cudaStream_t stream = nullptr;
+    double* partials = nullptr;   // [kMaxBlocks][kMaxVals]
+    unsigned int* ticket = nullptr;
+    double* stats_dev = nullptr;  // kMaxPayoffs * OPTP_NSTATS
+    double* stats_host = nullptr; // pinned mirror
+    Arena in0, in1, out0, out1, table_f32, table_f64;
+    uint32_t table_steps = 0, table_nodes = 0;
+    uint64_t launches = 0;
+};
+
+constexpr int kMaxPayoffs = 16;
+constexpr int kMaxBlocks = 148 * 16;
+constexpr int kMaxVals = 3 * kMaxPayoffs + 4;
+
+Context& ctx();
+int set_error(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+int arena_reserve(Arena& a, size_t bytes);
+int require_ready();
+
+#define OPTP_CUDA(call)                                           \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) return optp::cuda_fail(e__, #call); \
+    } while (0)
+
+// ------------------------------------------------------------------ Philox4x32-10
+// Salmon et al., "Parallel random numbers: as easy as 1, 2, 3" (SC11).  Counter-based:
+// the 128-bit counter is (base path index lo, hi, step block, stream), the 64-bit key is
+// the user's seed, so a draw depends only on (seed, path, step) -- never on the grid
+// shape or on how paths are sharded over GPUs.
+__host__ __device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2,
+                                                      uint32_t& c3, uint32_t k0, uint32_t k1) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+}
+
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                        uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------ uniforms / normals
+// One 32-bit word -> u in (0,1]:  top 23 bits build a float in [1,2) with bit operations
+// (no I2F, which would share the 16-lane XU pipe with the MUFU ops); u = 2 - f.  The lowest
+// cell (0, 2^-23] is refined with the 9 spare bits so the radius reaches 6.7 sigma.
+__device__ __forceinline__ float u01_open_low(uint32_t w) {
+    const float f = __uint_as_float(0x3f800000u | (w >> 9));
+    float u = 2.0f - f;
+    if ((w >> 9) == 0x7fffffu) u = ((float)(w & 511u) + 0.5f) * 2.3283064365386963e-10f;
+    return u;
+}
+
+__device__ __forceinline__ float mufu_lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float mufu_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float mufu_sqrt(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float mufu_sin(float x) {
+    float y;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float mufu_cos(float x) {
+    float y;
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Box-Muller on two words: radius from w0, angle from w1.  4 MUFU per pair.
+__device__ __forceinline__ void box_muller(uint32_t w0, uint32_t w1, float& z0, float& z1) {
+    const float u = u01_open_low(w0);
+    // r = sqrt(-2 ln u) = sqrt(-2 ln2 * lg2 u)
+    const float r = mufu_sqrt(-1.3862943611198906f * mufu_lg2(u));
+    // angle = 2*pi*(f-1), f in [1,2)
+    const float f = __uint_as_float(0x3f800000u | (w1 >> 9));
+    const float a = fmaf(f, 6.283185307179586f, -6.283185307179586f);
+    z0 = r * mufu_cos(a);
+    z1 = r * mufu_sin(a);
+}
+
+// Four normals of (seed, base path, block, stream).
+__device__ __forceinline__ void philox_normals4(uint64_t seed, uint64_t path, uint32_t block,
+                                                uint32_t stream, float z[4]) {
+    const uint4 w = philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), block, stream,
+                                  (uint32_t)seed, (uint32_t)(seed >> 32));
+    box_muller(w.x, w.y, z[0], z[1]);
+    box_muller(w.z, w.w, z[2], z[3]);
+}
+
+// ------------------------------------------------------------------ fp64 reductions
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum `v` over the block; result valid in thread 0.  `smem` needs 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* smem) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) smem[wid] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    double t = 0.0;
+    if (wid == 0) {
+        t = lane < nw ? smem[lane] : 0.0;
+        t = warp_sum(t);
+    }
+    return t;
+}
+
+// Each block deposits `n_vals` partial sums; the last block to arrive adds them in block
+// order (deterministic for a given grid) and writes totals through `emit`.
+template <class Emit>
+__device__ __forceinline__ void finalize_partials(double* partials, unsigned int* ticket,
+                                                  const double* block_vals_smem, int n_vals,
+                                                  Emit emit) {
+    __shared__ bool is_last;
+    for (int i = threadIdx.x; i < n_vals; i += blockDim.x)
+        partials[(size_t)blockIdx.x * kMaxVals + i] = block_vals_smem[i];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < n_vals; i += blockDim.x) {
+        double s = 0.0;
+        for (unsigned int b = 0; b < gridDim.x; ++b)
+            s += __ldcg(&partials[(size_t)b * kMaxVals + i]);
+        emit(i, s);
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+#endif  // __CUDACC__
+
+}  // namespace optp

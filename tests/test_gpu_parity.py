@@ -1,0 +1,448 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Every call goes through the public Python
+API of optpricer_b200, i.e. through the C ABI of liboptp_b200.so, and is compared with
+  * the golden fixtures produced by the unmodified reference (tests/golden/), and
+  * the numpy oracle (oracle/) on the same seeded inputs.
+Tolerances (BASELINE.json north_star):
+  check mode (reference's own PCG64 draws, fp64)   1e-12 relative on prices and per-path payoffs
+  on-device Philox (fp32 and fp64 arithmetic)      |price - ref| <= 3 reference standard errors
+  CRR                                              1e-10 relative
+"""
+import math
+
+import numpy as np
+import pytest
+
+from golden_io import load_json, load_npz, dupire_grid_arrays
+from oracle import terminal_mc, path_schemes, payoffs, crr_tree, sigma_grid
+
+pytestmark = pytest.mark.gpu
+
+REL_CHECK = 1e-12
+REL_SE = 1e-9
+REL_CRR = 1e-10
+
+
+@pytest.fixture(scope="module")
+def op():
+    import optpricer_b200 as o
+    from optpricer_b200 import _native
+    _native.init()
+    assert _native.LIB_PATH.endswith("liboptp_b200.so")
+    return o
+
+
+def rel(a, b):
+    return abs(a - b) / max(1.0, abs(b))
+
+
+# ------------------------------------------------------------------------------ euro_price_mc
+def _np_dtype(kw):
+    kw = dict(kw)
+    if kw.get("dtype") == "float32":
+        kw["dtype"] = np.float32
+    return kw
+
+
+def test_euro_mc_check_mode_matches_reference(op):
+    g = load_json("euro_mc.json")
+    for c in g["cases"]:
+        kw = _np_dtype(c["kwargs"])
+        tol = 2e-6 if kw.get("dtype") is np.float32 else REL_CHECK
+        price, se = op.euro_price_mc(op.OptionSpec(**c["opt"]), c["kind"], n_paths=c["n_paths"], seed=c["seed"],
+                                     mode="check", **kw)
+        assert rel(price, c["price"]) <= tol, (c, price)
+        assert rel(se, c["stderr"]) <= max(tol, REL_SE), (c, se)
+
+
+def test_euro_mc_chunk_statistics(op):
+    from optpricer_b200.monte_carlo import _mc_chunk_sumstats
+    g = load_json("euro_mc.json")
+    base = dict(S0=100.0, K=110.0, T=1.0, r=0.03, sigma=0.20, q=0.0)
+    for ss, ref in zip(np.random.SeedSequence(1).spawn(2), g["cfg1_chunk_stats"]):
+        got = _mc_chunk_sumstats(100_000, kind="call", antithetic=True, seed=ss, **base)
+        assert got[0] == ref[0]
+        for a, b in zip(got[1:], ref[1:]):
+            assert rel(a, b) <= REL_CHECK
+    assert _mc_chunk_sumstats(0, kind="call", antithetic=True, seed=1, **base) == (0, 0.0, 0.0, 0.0, 0.0, 0.0)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp64"])
+def test_euro_mc_philox_within_three_reference_se(op, mode):
+    g = load_json("euro_mc.json")
+    for c in g["cases"]:
+        kw = {k: v for k, v in c["kwargs"].items() if k in ("antithetic", "control_variate")}
+        for seed in (c["seed"], 12345):
+            # 16x the reference's paths: the bar is literally 3 reference standard errors
+            price, se = op.euro_price_mc(op.OptionSpec(**c["opt"]), c["kind"], n_paths=16 * c["n_paths"], seed=seed,
+                                         mode=mode, **kw)
+            assert abs(price - c["price"]) <= 3.0 * c["stderr"] + 1e-12, (c, price, se)
+            if c["n_paths"] > 1000:
+                assert 0.8 < 4.0 * se / c["stderr"] < 1.25
+
+
+def test_euro_mc_fp32_tracks_fp64_on_same_draws(op):
+    opt = op.OptionSpec(100.0, 110.0, 1.0, 0.03, 0.2)
+    for kind in ("call", "put"):
+        for anti in (True, False):
+            a = op.euro_price_mc(opt, kind, n_paths=1_000_003, seed=9, mode="fp32", antithetic=anti)
+            b = op.euro_price_mc(opt, kind, n_paths=1_000_003, seed=9, mode="fp64", antithetic=anti)
+            assert abs(a[0] - b[0]) <= 0.02 * b[1], (a, b)
+            assert rel(a[1], b[1]) < 1e-4
+
+
+def test_euro_mc_large_run_converges_to_black_scholes(op):
+    # cfg 1 contract at 2e8 base paths: |MC - BS| must be a few standard errors of ~1e-4
+    opt = op.OptionSpec(100.0, 110.0, 1.0, 0.03, 0.2)
+    bs_call = 5.293398058044907
+    p, se = op.euro_price_mc(opt, "call", n_paths=200_000_000, seed=3)
+    assert se < 4e-4
+    assert abs(p - bs_call) <= 4.0 * se + 2e-5
+
+
+def test_euro_mc_edge_cases(op):
+    opt = op.OptionSpec(100.0, 110.0, 1.0, 0.03, 0.2)
+    for mode in ("fp32", "fp64", "check"):
+        p, se = op.euro_price_mc(opt, "call", n_paths=0, seed=1, mode=mode)
+        assert p != p and se != se
+        p1 = op.euro_price_mc(opt, "call", n_paths=1, seed=1, mode=mode, return_stderr=False)
+        assert isinstance(p1, float)
+    with pytest.raises(ValueError, match="kind must be 'call' or 'put'"):
+        op.euro_price_mc(opt, "straddle", n_paths=10, seed=1)
+    # sharding invariance: statistics of [0,n) equal the sum over disjoint path ranges
+    from optpricer_b200.monte_carlo import terminal_stats
+    args = (100.0, 110.0, 1.0, 0.03, 0.0, 0.2, 1)
+    whole = terminal_stats(*args, 1_000_001, seed=5)
+    parts = [terminal_stats(*args, n, seed=5, path_offset=o) for o, n in ((0, 333_333), (333_333, 7), (333_340, 666_661))]
+    np.testing.assert_allclose(sum(parts)[:6], whole[:6], rtol=2e-6)
+    whole64 = terminal_stats(*args, 100_001, seed=5, mode="fp64")
+    parts64 = [terminal_stats(*args, n, seed=5, mode="fp64", path_offset=o) for o, n in ((0, 50_001), (50_001, 50_000))]
+    np.testing.assert_allclose(sum(parts64)[:6], whole64[:6], rtol=1e-12)
+
+
+# ------------------------------------------------------------------------------ CRR
+def test_crr_golden_cases(op):
+    g = load_json("crr.json")
+    for c in g["cases"]:
+        opt = op.OptionSpec(c["S0"], c["K"], c["T"], c["r"], c["sigma"], c["q"])
+        if "error" in c:
+            with pytest.raises(ValueError) as e:
+                op.crr(opt, c["kind"], c["N"], american=c["american"])
+            assert str(e.value) == c["error"]
+        else:
+            v = op.crr(opt, c["kind"], c["N"], american=c["american"])
+            assert rel(v, c["price"]) <= REL_CRR, (c, v)
+    with pytest.raises(ValueError, match="N must be positive."):
+        op.crr(op.OptionSpec(100, 100, 1, 0.05, 0.2), "call", 0)
+
+
+def test_crr_vec_golden_cases(op):
+    for c in load_json("crr.json")["crr_vec"]:
+        v = op.crr_vec(c["S0"], np.array(c["K"]), c["T"], c["r"], c["q"], c["sigma"], c["kind"], c["N"],
+                       american=c["american"])
+        assert v.shape == (len(c["K"]),)
+        np.testing.assert_allclose(v, c["prices"], rtol=REL_CRR, atol=REL_CRR)
+
+
+def test_crr_cfg2_batch_against_reference_and_oracle(op):
+    g = load_json("crr.json")
+    S0, K, T, r, q, sig, is_call = crr_tree.cfg2_contracts(1_000_000)
+    n = 4096
+    price, status = op.crr_batch(S0[:n], K[:n], T[:n], r[:n], q[:n], sig[:n], is_call[:n], 1000, american=True,
+                                 return_status=True)
+    assert not status.any()
+    ref64 = np.array(g["cfg2_first64_american_put_N1000"])
+    np.testing.assert_allclose(price[:64], ref64, rtol=REL_CRR, atol=REL_CRR)
+    oracle_p, _ = crr_tree.crr_loop(S0[64:96], K[64:96], T[64:96], r[64:96], q[64:96], sig[64:96], is_call[64:96],
+                                    1000, True)
+    np.testing.assert_allclose(price[64:96], oracle_p, rtol=REL_CRR, atol=REL_CRR)
+    # American put >= European put >= 0 and >= intrinsic, for the whole slice
+    euro = op.crr_batch(S0[:n], K[:n], T[:n], r[:n], q[:n], sig[:n], is_call[:n], 1000, american=False)
+    assert np.all(price >= euro - 1e-12) and np.all(price >= np.maximum(K[:n] - S0[:n], 0.0) - 1e-12)
+    # the result of a contract does not depend on its position or on the batch it is in
+    again = op.crr_batch(S0[100:229], K[100:229], T[100:229], r[100:229], q[100:229], sig[100:229], is_call[100:229],
+                         1000, american=True)
+    np.testing.assert_array_equal(again, price[100:229])
+
+
+@pytest.mark.parametrize("N", [1, 2, 31, 32, 33, 255, 256, 257, 1000, 1023, 1024, 1500])
+def test_crr_ragged_sizes_against_oracle(op, N):
+    g = np.random.default_rng(N)
+    n = 9
+    S0 = g.uniform(50, 150, n); K = S0 * g.uniform(0.8, 1.2, n); T = g.uniform(0.1, 2.0, n)
+    sig = g.uniform(0.1, 0.6, n); r = g.uniform(0.0, 0.08, n); q = g.uniform(0.0, 0.04, n)
+    is_call = (g.random(n) < 0.5).astype(np.uint8)
+    for american in (True, False):
+        ref, ref_status = crr_tree.crr_loop(S0, K, T, r, q, sig, is_call, N, american)
+        got, status = op.crr_batch(S0, K, T, r, q, sig, is_call, N, american=american, return_status=True)
+        np.testing.assert_array_equal(status, ref_status)
+        ok = ref_status == 0
+        np.testing.assert_allclose(got[ok], ref[ok], rtol=REL_CRR, atol=REL_CRR)
+        assert np.all(np.isnan(got[~ok]))
+
+
+def test_crr_batch_flags_bad_contracts_without_aborting(op):
+    S0 = np.array([100.0, 100.0, 100.0]); K = np.array([100.0, 100.0, 90.0])
+    T = np.array([1.0, 2.0, 1.0]); r = np.array([0.05, 0.30, 0.05]); q = np.zeros(3)
+    sig = np.array([0.2, 0.01, 0.2])
+    price, status = op.crr_batch(S0, K, T, r, q, sig, [1, 1, 0], 4, return_status=True)
+    assert status.tolist() == [0, 1, 0] and math.isnan(price[1])
+    assert rel(price[0], crr_tree.crr_scalar(100.0, 100.0, 1.0, 0.05, 0.2, 0.0, "call", 4)) <= REL_CRR
+    empty = op.crr_batch(np.empty(0), np.empty(0), np.empty(0), np.empty(0), np.empty(0), np.empty(0), np.empty(0), 10)
+    assert empty.shape == (0,)
+
+
+# ------------------------------------------------------------------------------ paths + payoffs
+def _spec(op, key, K):
+    from optpricer_b200 import exotics as ex
+    f = key.split("|")
+    if f[0] == "barrier":
+        return ex.barrier_spec(K, f[2], float(f[3]), f[1], float(f[4]))
+    if f[0] == "asian":
+        return ex.asian_spec(K, f[1], f[2], f[3])
+    if f[0] == "digital":
+        return ex.digital_spec(K, f[1], float(f[2]))
+    if f[0] == "lookback":
+        return ex.lookback_spec(f[1], K, f[2])
+    raise KeyError(key)
+
+
+def _oracle_payoff(paths, key, K):
+    f = key.split("|")
+    if f[0] == "barrier":
+        return payoffs.barrier_payoff(paths, K, f[2], float(f[3]), f[1], float(f[4]))
+    if f[0] == "asian":
+        return payoffs.asian_payoff(paths, K, f[1], f[2], f[3])
+    if f[0] == "digital":
+        return payoffs.digital_payoff(paths, K, f[1], float(f[2]))
+    return payoffs.lookback_payoff(paths, f[1], K, f[2])
+
+
+def _table(meta, npz):
+    if meta.get("sigma") == "lvm_table":
+        x0, h, dt = npz["lvm_table/grid"]
+        return npz["lvm_table/table"], float(x0), float(h), float(dt)
+    if meta.get("sigma") == "dupire_table_252x256":
+        return dupire_grid_arrays()
+    if meta.get("sigma") == "const0.2":
+        n_steps = meta["args"]["n_steps"]
+        return np.full((n_steps, 64), 0.2), math.log(meta["args"]["S0"]) - 1.6, 3.2 / 63, meta["args"]["T"] / n_steps
+    return None
+
+
+def _lazy(op, meta, npz, rng, mode="fp64", seed=None, n_mult=1):
+    from optpricer_b200 import processes as pr
+    a = dict(meta["args"])
+    a["n_paths"] *= n_mult
+    if seed is not None:
+        a["seed"] = seed
+    gen = meta["gen"]
+    kw = dict(rng=rng, mode=mode)
+    if gen == "gbm":
+        return pr.gbm_paths(**a, **kw)
+    if gen == "heston":
+        return pr.heston_paths(**a, **kw)
+    if gen == "gbm_milstein":
+        return pr.gbm_milstein_paths(**a, **kw)
+    if gen == "sabr":
+        kw["mode"] = "fp64"
+        return pr.sabr_paths(**a, **kw)
+    tab = pr.SigmaTable(*_table(meta, npz))
+    if gen == "lv_milstein":
+        return pr.milstein_local_vol_paths(sigma_loc=tab, dS_bump=meta.get("dS_bump", 0.01), **a, **kw)
+    return pr.local_vol_paths(sigma_loc=tab, **a, **kw)
+
+
+def _oracle_paths(meta, npz):
+    a = dict(meta["args"])
+    seed, n_steps, n_paths, anti = a.pop("seed"), a.pop("n_steps"), a.pop("n_paths"), a.pop("antithetic")
+    gen = meta["gen"]
+    if gen == "gbm":
+        (z,) = path_schemes.draw_normals(seed, n_steps, n_paths)
+        return path_schemes.gbm_exact(z, antithetic=anti, **a)
+    if gen == "heston":
+        z2, zp = path_schemes.draw_normals(seed, n_steps, n_paths, 2)
+        return path_schemes.heston_fte(z2, zp, antithetic=anti, **a)
+    if gen == "sabr":
+        z2, zp = path_schemes.draw_normals(seed, n_steps, n_paths, 2)
+        return path_schemes.sabr_lognormal_vol(z2, zp, antithetic=anti, **a)
+    (z,) = path_schemes.draw_normals(seed, n_steps, n_paths)
+    if gen == "gbm_milstein":
+        return path_schemes.gbm_milstein(z, antithetic=anti, **a)
+    tab = sigma_grid.SigmaGrid(*_table(meta, npz))
+    if gen == "lv_milstein":
+        return path_schemes.lv_milstein(z, tab, antithetic=anti, dS_bump=meta.get("dS_bump", 0.01), **a)
+    return path_schemes.lv_log_euler(z, tab, antithetic=anti, **a)
+
+
+SMALL = ["gbm_small_anti1", "gbm_small_anti0", "heston_small_anti1", "heston_small_anti0", "heston_trunc",
+         "lvm_const", "lvm_table_anti1", "lvm_table_anti0", "lvm_table_bump3", "lv_euler_table",
+         "gbm_milstein", "sabr_beta1.0", "sabr_beta0.5"]
+
+
+@pytest.mark.parametrize("tag", SMALL)
+def test_check_mode_small_cases(op, tag):
+    """Reference's own normals -> materialised paths, per-path payoffs and prices at 1e-12."""
+    from optpricer_b200 import exotics as ex
+    meta = load_json("mc_paths.json")[tag]
+    npz = load_npz("mc_paths_samples.npz")
+    lp = _lazy(op, meta, npz, rng="numpy")
+    ref_paths = _oracle_paths(meta, npz)
+    arr = np.asarray(lp)
+    assert arr.shape == ref_paths.shape == lp.shape
+    np.testing.assert_allclose(arr, ref_paths, rtol=REL_CHECK)
+    np.testing.assert_allclose(arr[npz[f"{tag}/rows"], :], npz[f"{tag}/row_values"], rtol=REL_CHECK)
+    if meta["gen"] == "heston":
+        _, var = lp.materialize(return_variance=True)
+        np.testing.assert_allclose(var[-1], npz[f"{tag}/var_terminal"], rtol=1e-11, atol=1e-15)
+    K, r, T = meta["K"], meta["r"], meta["T"]
+    keys = list(meta["prices"])
+    for chunk in (keys[:12], keys[12:]):
+        specs = [_spec(op, k, K) for k in chunk]
+        stats, pay, term = ex.path_stats(lp, specs, r, T, want_payoffs=True, want_terminal=True)
+        np.testing.assert_allclose(term, ref_paths[-1], rtol=REL_CHECK)
+        for i, k in enumerate(chunk):
+            want = _oracle_payoff(ref_paths, k, K)
+            np.testing.assert_allclose(pay[i], want, rtol=REL_CHECK, atol=1e-12, err_msg=k)
+            price, se = ex.estimate(stats[i])
+            assert rel(price, meta["prices"][k][0]) <= REL_CHECK, (tag, k)
+            assert rel(se, meta["prices"][k][1]) <= REL_SE, (tag, k)
+            assert stats[i][0] == ref_paths.shape[1]
+    # the array contract of exotics.py: reduce a caller-supplied ndarray on the device
+    for k in (keys[0], keys[8], keys[13], keys[18], keys[23]):
+        stats, pay = ex.array_stats(ref_paths, _spec(op, k, K), r, T, want_payoffs=True)
+        np.testing.assert_allclose(pay, _oracle_payoff(ref_paths, k, K), rtol=0, atol=0)
+        assert rel(ex.estimate(stats)[0], meta["prices"][k][0]) <= REL_CHECK
+
+
+BIG = ["gbm_test_exotics_500x100k", "heston_365x50k", "desk_table_252x100k"]
+
+
+@pytest.mark.parametrize("tag", BIG)
+def test_check_mode_reference_test_fixtures(op, tag):
+    """The reference tests' own configurations (tests/test_exotics.py:22-28, desk workflow) at full size."""
+    from optpricer_b200 import exotics as ex
+    meta = load_json("mc_paths.json")[tag]
+    lp = _lazy(op, meta, None, rng="numpy")
+    K, r, T = meta["K"], meta["r"], meta["T"]
+    keys = list(meta["prices"])
+    got = []
+    for chunk in (keys[:12], keys[12:]):
+        got += ex.price_payoffs(lp, [_spec(op, k, K) for k in chunk], r, T)
+    for k, (price, se) in zip(keys, got):
+        assert rel(price, meta["prices"][k][0]) <= REL_CHECK, (tag, k, price)
+        assert rel(se, meta["prices"][k][1]) <= REL_SE, (tag, k, se)
+    if "uo130" in meta:
+        p, se = op.barrier_price(lp, 100.0, 0.05, 1.0, "call", 130.0, "up-and-out")
+        assert rel(p, meta["uo130"][0]) <= REL_CHECK and rel(se, meta["uo130"][1]) <= REL_SE
+
+
+@pytest.mark.parametrize("tag", BIG + ["gbm_small_anti0", "heston_small_anti0", "lvm_table_anti0", "lv_euler_table",
+                                       "gbm_milstein"])
+@pytest.mark.parametrize("mode", ["fp32", "fp64"])
+def test_philox_within_three_reference_se(op, tag, mode):
+    from optpricer_b200 import exotics as ex
+    meta = load_json("mc_paths.json")[tag]
+    npz = load_npz("mc_paths_samples.npz")
+    K, r, T = meta["K"], meta["r"], meta["T"]
+    keys = list(meta["prices"])
+    # the device run uses 16x the reference's path count, so the difference is dominated by the
+    # reference's own sampling error and the bar is literally "3 reference standard errors"
+    for seed in (2024, 77):
+        lp = _lazy(op, meta, npz, rng="philox", mode=mode, seed=seed, n_mult=16)
+        got = []
+        for chunk in (keys[:12], keys[12:]):
+            got += ex.price_payoffs(lp, [_spec(op, k, K) for k in chunk], r, T)
+        for k, (price, se) in zip(keys, got):
+            ref_p, ref_se = meta["prices"][k]
+            assert abs(price - ref_p) <= 3.0 * ref_se + 1e-9, (tag, mode, seed, k, price, ref_p, ref_se)
+            if ref_se > 0 and lp.n_paths >= 16 * 50_000:
+                assert 0.85 < 4.0 * se / ref_se < 1.18, (tag, k, se, ref_se)
+
+
+@pytest.mark.parametrize("gen", ["gbm", "heston", "lvm", "lve", "gbmm"])
+def test_fp32_tracks_fp64_on_same_philox_draws(op, gen):
+    """Production fp32 arithmetic vs the reference operation order in fp64, SAME device normals:
+    the price difference must be a small fraction of the standard error."""
+    from optpricer_b200 import exotics as ex, processes as pr
+    table = pr.SigmaTable(*dupire_grid_arrays())
+    n = 200_000
+
+    def make(mode):
+        if gen == "gbm":
+            return pr.gbm_paths(100.0, 0.05, 0.0, 0.2, 1.0, 252, n, seed=11, mode=mode)
+        if gen == "heston":
+            return pr.heston_paths(100.0, 0.05, 0.0, 0.04, 2.0, 0.04, 0.3, -0.7, 1.0, 365, n, seed=11, mode=mode)
+        if gen == "lvm":
+            return pr.milstein_local_vol_paths(100.0, 0.05, 0.02, 1.0, 252, n, table, seed=11, mode=mode)
+        if gen == "lve":
+            return pr.local_vol_paths(100.0, 0.05, 0.02, 1.0, 252, n, table, seed=11, mode=mode)
+        return pr.gbm_milstein_paths(100.0, 0.05, 0.0, 0.2, 1.0, 252, n, seed=11, mode=mode)
+
+    specs = [ex.barrier_spec(100.0, "call", 130.0, "up-and-out"), ex.barrier_spec(100.0, "put", 85.0, "down-and-in"),
+             ex.asian_spec(100.0, "call"), ex.asian_spec(100.0, "put", "geometric", "floating"),
+             ex.lookback_spec("call"), ex.lookback_spec("put", 100.0, "fixed"), ex.vanilla_spec(100.0, "call"),
+             ex.digital_spec(100.0, "call")]
+    a = ex.price_payoffs(make("fp32"), specs, 0.05, 1.0)
+    b = ex.price_payoffs(make("fp64"), specs, 0.05, 1.0)
+    for (pa, sa), (pb, sb) in zip(a, b):
+        assert abs(pa - pb) <= 0.05 * sb, (gen, pa, pb, sb)
+        assert rel(sa, sb) < 2e-3
+
+
+def test_size_independent_properties_at_scale(op):
+    """BASELINE-scale path counts: identities that hold path by path, whatever the size."""
+    from optpricer_b200 import exotics as ex, processes as pr
+    n = 20_000_000
+    lp = pr.gbm_paths(100.0, 0.05, 0.0, 0.2, 1.0, 252, n, seed=1)
+    specs = [ex.barrier_spec(100.0, "call", 120.0, "up-and-out"), ex.barrier_spec(100.0, "call", 120.0, "up-and-in"),
+             ex.vanilla_spec(100.0, "call"), ex.asian_spec(100.0, "call", "arithmetic"),
+             ex.asian_spec(100.0, "call", "geometric"), ex.lookback_spec("call", 100.0, "fixed")]
+    stats, _, _ = ex.path_stats(lp, specs, 0.05, 1.0)
+    assert all(s[0] == 2 * n for s in stats)
+    # knock-in + knock-out == vanilla (exotics tests: tests/test_exotics.py:35-49), here to fp64 rounding
+    assert abs(stats[0][1] + stats[1][1] - stats[2][1]) <= 1e-9 * stats[2][1]
+    assert stats[3][1] >= stats[4][1]                      # arithmetic >= geometric
+    assert stats[5][1] >= stats[2][1]                      # fixed lookback call >= vanilla call
+    bs_call = 10.450583572185565
+    p, se = ex.estimate(stats[2])
+    assert abs(p - bs_call) <= 4 * se + 1e-4
+    # E[e^{-rT} S_T] = S0 (martingale check of the generator + reduction)
+    assert abs(stats[2][3] / stats[2][0] - 100.0) < 4 * 100.0 * 0.2 / math.sqrt(2 * n) + 1e-4
+    # sharding invariance: disjoint Philox path ranges add up to the single-device statistics
+    a, _, _ = ex.path_stats(lp, specs, 0.05, 1.0, n_base=n // 2 + 3, path_offset=0)
+    b, _, _ = ex.path_stats(lp, specs, 0.05, 1.0, n_base=n - (n // 2 + 3), path_offset=n // 2 + 3)
+    np.testing.assert_allclose((a + b)[:, :6], stats[:, :6], rtol=1e-9)
+
+
+def test_control_variate_on_path_payoff(op):
+    from optpricer_b200 import exotics as ex, processes as pr
+    meta = load_json("mc_paths.json")["heston_small_anti1"]
+    lp = _lazy(op, meta, None, rng="numpy")
+    ref_paths = _oracle_paths(meta, None)
+    pay = payoffs.asian_payoff(ref_paths, 100.0, "call")
+    want = payoffs.cv_estimator(payoffs.six_stats(pay, ref_paths[-1], 0.05, 1.0), 100.0)
+    got = op.asian_price(lp, 100.0, 0.05, 1.0, "call", control_variate=True)
+    assert rel(got[0], want[0]) <= 1e-11 and rel(got[1], want[1]) <= REL_SE
+    plain = op.asian_price(lp, 100.0, 0.05, 1.0, "call")
+    assert got[1] < plain[1]
+
+
+def test_argument_errors_match_reference_texts(op):
+    from optpricer_b200 import processes as pr
+    with pytest.raises(ValueError, match="n_steps and n_paths must be positive."):
+        pr.gbm_paths(100, 0.05, 0, 0.2, 1, 0, 10)
+    with pytest.raises(ValueError, match=r"rho must be in \[-1, 1\]."):
+        pr.heston_paths(100, 0.05, 0, 0.04, 2, 0.04, 0.3, -1.5, 1, 10, 10)
+    lp = pr.gbm_paths(100, 0.05, 0, 0.2, 1, 10, 10, seed=1)
+    with pytest.raises(ValueError, match="barrier_type must be one of"):
+        op.barrier_price(lp, 100, 0.05, 1, "call", 120, "sideways")
+    with pytest.raises(ValueError, match="kind must be 'call' or 'put'"):
+        op.barrier_price(lp, 100, 0.05, 1, "both", 120, "up-and-out")
+    with pytest.raises(ValueError, match="average_type must be 'arithmetic' or 'geometric'"):
+        op.asian_price(lp, 100, 0.05, 1, "call", "harmonic")
+    with pytest.raises(ValueError, match="strike_type must be 'fixed' or 'floating'"):
+        op.asian_price(lp, 100, 0.05, 1, "call", "arithmetic", "odd")
+    with pytest.raises(ValueError, match="strike_type must be 'floating' or 'fixed'"):
+        op.lookback_price(lp, 0.05, 1, "call", 0.0, "odd")
+    assert lp.shape == (11, 20) and np.asarray(lp).shape == (11, 20)
+    assert np.all(np.asarray(lp)[0] == 100.0)
