@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(256) path_fp32_kernel(PathArgs a) {
     k.h_c1 = (float)(1.0 - a.kappa * dt);
     k.h_kt = (float)(a.kappa * a.theta * dt);
     k.h_xs = (float)(a.xi * sdt);
-    k.m_c1 = (float)(1.0 + (a.r - a.q) * dt);
+    k.m_c1 = (float)((a.r - a.q) * dt - 0.5 * a.sigma * a.sigma * dt);
     k.m_ssdt = (float)(a.sigma * sdt);
     k.m_hs2dt = (float)(0.5 * a.sigma * a.sigma * dt);
     const float S0 = (float)a.S0;
@@ -339,12 +339,14 @@ __global__ void __launch_bounds__(256) path_fp32_kernel(PathArgs a) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j, ++t) {
                     if (t < n_steps) {
+                        // S' = S + S*g with g kept as a SMALL number: folding the 1 into a
+                        // rounded fp32 constant would bias every step by up to 6e-8
                         const float zs = k.m_ssdt * z[j];
-                        const float zq = fmaf(k.m_hs2dt * z[j], z[j], k.m_c1 - k.m_hs2dt);
-                        p.S = fmaxf(p.S * (zq + zs), 1e-10f);
+                        const float zq = fmaf(k.m_hs2dt * z[j], z[j], k.m_c1);
+                        p.S = fmaxf(fmaf(p.S, zq + zs, p.S), 1e-10f);
                         observe_lin<MASK>(p);
                         if (ANTI) {
-                            m.S = fmaxf(m.S * (zq - zs), 1e-10f);
+                            m.S = fmaxf(fmaf(m.S, zq - zs, m.S), 1e-10f);
                             observe_lin<MASK>(m);
                         }
                     }
@@ -393,7 +395,7 @@ __device__ __forceinline__ void lv_step(LinState& s, const float2* row, const Lv
         const float sig_dn = table_sigma32(row, pos + k.c_dn, k.pos_max);
         const float da = fmaf(sig_up, k.k_up, -(sig_dn * k.k_dn));
         const float av = sig * s.S;
-        s.S = fmaxf(fmaf(av, fmaf(da, zzh, zs), s.S * k.c1), 1e-10f);
+        s.S = fmaxf(fmaf(av, fmaf(da, zzh, zs), fmaf(s.S, k.c1, s.S)), 1e-10f);
     } else {  // LV_EULER, processes.py:253-256
         sig = fmaxf(sig, 0.f);
         const float ex = fmaf(sig * z, k.e_sdt2, fmaf(sig * sig, k.e_mhalf2, k.e_rq2));
@@ -425,7 +427,7 @@ __global__ void __launch_bounds__(kLvThreads) lv_fp32_kernel(PathArgs a, int row
     k.c_dn = (float)(log1p(-fmin(a.bump, 0.999999)) / a.h);
     k.k_up = (float)((1.0 + a.bump) / (2.0 * a.bump));
     k.k_dn = (float)((1.0 - a.bump) / (2.0 * a.bump));
-    k.c1 = (float)(1.0 + (a.r - a.q) * dt);
+    k.c1 = (float)((a.r - a.q) * dt);  // S*(1+c1) is evaluated as fma(S, c1, S)
     k.sdt = (float)sdt;
     k.hdt = (float)(0.5 * dt);
     k.e_sdt2 = (float)(sdt * L2E);
