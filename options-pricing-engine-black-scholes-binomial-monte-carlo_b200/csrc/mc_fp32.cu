@@ -233,8 +233,54 @@ struct StepConst {
     float m_c1, m_ssdt, m_hs2dt;
 };
 
+// one time step of a base path and its mirror, per process
+template <int MASK, bool ANTI>
+__device__ __forceinline__ void gbm_step(LogState& p, LogState& m, float z, const StepConst& k) {
+    // log2 S accumulates drift + vol*Z exactly like the reference's cumsum (processes.py:52-53)
+    p.x += fmaf(k.vol2, z, k.drift2);
+    observe_log<MASK>(p);
+    if (ANTI) {
+        m.x += fmaf(-k.vol2, z, k.drift2);
+        observe_log<MASK>(m);
+    }
+}
+
+template <int MASK, bool ANTI>
+__device__ __forceinline__ void heston_step(LogState& p, LogState& m, float& vp, float& vm, float z0,
+                                            float z1, const StepConst& k) {
+    // full-truncation Euler (processes.py:150-160); v >= 0 is re-established at the end of every
+    // step, so max(v,0) at the start of the next one is the identity.
+    const float zc = fmaf(k.rho, z0, k.rhoc * z1);
+    {
+        const float sq = mufu_sqrt(vp);
+        p.x = fmaf(sq * zc, k.h_sdt2, fmaf(vp, k.h_mhalf2, p.x + k.h_rq2));
+        vp = fmaxf(fmaf(sq * z0, k.h_xs, fmaf(vp, k.h_c1, k.h_kt)), 0.f);
+        observe_log<MASK>(p);
+    }
+    if (ANTI) {
+        const float sq = mufu_sqrt(vm);
+        m.x = fmaf(-(sq * zc), k.h_sdt2, fmaf(vm, k.h_mhalf2, m.x + k.h_rq2));
+        vm = fmaxf(fmaf(-(sq * z0), k.h_xs, fmaf(vm, k.h_c1, k.h_kt)), 0.f);
+        observe_log<MASK>(m);
+    }
+}
+
+template <int MASK, bool ANTI>
+__device__ __forceinline__ void gbmm_step(LinState& p, LinState& m, float z, const StepConst& k) {
+    // S' = S + S*g with g kept as a SMALL number (processes.py:296-303): folding the 1 into a
+    // rounded fp32 constant would bias every step by up to 6e-8
+    const float zs = k.m_ssdt * z;
+    const float zq = fmaf(k.m_hs2dt * z, z, k.m_c1);
+    p.S = fmaxf(fmaf(p.S, zq + zs, p.S), 1e-10f);
+    observe_lin<MASK>(p);
+    if (ANTI) {
+        m.S = fmaxf(fmaf(m.S, zq - zs, m.S), 1e-10f);
+        observe_lin<MASK>(m);
+    }
+}
+
 template <int PROC, int MASK, bool ANTI>
-__global__ void __launch_bounds__(256) path_fp32_kernel(PathArgs a) {
+__global__ void __launch_bounds__(256, 5) path_fp32_kernel(PathArgs a) {
     extern __shared__ double dyn[];
     __shared__ double blockvals[kMaxVals];
     double* acc = dyn;
@@ -263,94 +309,57 @@ __global__ void __launch_bounds__(256) path_fp32_kernel(PathArgs a) {
     const float df = (float)exp(-a.pay[0].r_disc * a.pay[0].T_disc);
     const unsigned long long n_eff = ANTI ? 2 * a.n_base : a.n_base;
     constexpr int kDims = (PROC == OPTP_PROC_HESTON_FTE) ? 2 : 1;
-    constexpr int kPerCall = 4 / kDims;
-    const unsigned int n_calls = (n_steps + kPerCall - 1) / kPerCall;
+    constexpr int kPerCall = 4 / kDims;  // steps served by one Philox call
+    const unsigned int n_full = n_steps / kPerCall, n_tail = n_steps % kPerCall;
 
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
          b < a.n_base; b += stride) {
         const unsigned long long gpath = a.path_offset + b;
         PathEnd ep, em;
+        float z[4];
         if (PROC == OPTP_PROC_GBM) {
-            // S_t = S0*2^(t*drift2 +- W_t), W_t = sum vol2*z  (processes.py:44-55)
             LogState p, m;
-            float w = 0.f;
-            unsigned int t = 0;
 #pragma unroll 1
-            for (unsigned int c = 0; c < n_calls; ++c) {
-                float z[4];
+            for (unsigned int c = 0; c < n_full; ++c) {
                 philox_normals4(a.seed, gpath, c, 0u, z);
 #pragma unroll
-                for (int j = 0; j < 4; ++j, ++t) {
-                    if (t < n_steps) {
-                        const float td = (float)(t + 1) * k.drift2;
-                        w = fmaf(k.vol2, z[j], w);
-                        p.x = td + w;
-                        observe_log<MASK>(p);
-                        if (ANTI) {
-                            m.x = td - w;
-                            observe_log<MASK>(m);
-                        }
-                    }
-                }
+                for (int j = 0; j < 4; ++j) gbm_step<MASK, ANTI>(p, m, z[j], k);
+            }
+            if (n_tail) {
+                philox_normals4(a.seed, gpath, n_full, 0u, z);
+                for (unsigned int j = 0; j < n_tail; ++j) gbm_step<MASK, ANTI>(p, m, z[j], k);
             }
             ep = finish_log<MASK>(p, S0, inv_n);
             if (ANTI) em = finish_log<MASK>(m, S0, inv_n);
         } else if (PROC == OPTP_PROC_HESTON_FTE) {
-            // full-truncation Euler (processes.py:150-160); v >= 0 is re-established at the end
-            // of every step, so max(v,0) at the start of the next one is the identity.
             LogState p, m;
             float vp = fmaxf((float)a.v0, 0.f), vm = vp;
-            unsigned int t = 0;
 #pragma unroll 1
-            for (unsigned int c = 0; c < n_calls; ++c) {
-                float z[4];
+            for (unsigned int c = 0; c < n_full; ++c) {
                 philox_normals4(a.seed, gpath, c, 0u, z);
-#pragma unroll
-                for (int j = 0; j < 2; ++j, ++t) {
-                    if (t < n_steps) {
-                        const float z0 = z[2 * j], zc = fmaf(k.rho, z0, k.rhoc * z[2 * j + 1]);
-                        {
-                            const float sq = mufu_sqrt(vp);
-                            p.x = fmaf(sq * zc, k.h_sdt2, fmaf(vp, k.h_mhalf2, p.x + k.h_rq2));
-                            vp = fmaxf(fmaf(sq * z0, k.h_xs, fmaf(vp, k.h_c1, k.h_kt)), 0.f);
-                            observe_log<MASK>(p);
-                        }
-                        if (ANTI) {
-                            const float sq = mufu_sqrt(vm);
-                            m.x = fmaf(-(sq * zc), k.h_sdt2, fmaf(vm, k.h_mhalf2, m.x + k.h_rq2));
-                            vm = fmaxf(fmaf(-(sq * z0), k.h_xs, fmaf(vm, k.h_c1, k.h_kt)), 0.f);
-                            observe_log<MASK>(m);
-                        }
-                    }
-                }
+                heston_step<MASK, ANTI>(p, m, vp, vm, z[0], z[1], k);
+                heston_step<MASK, ANTI>(p, m, vp, vm, z[2], z[3], k);
+            }
+            if (n_tail) {
+                philox_normals4(a.seed, gpath, n_full, 0u, z);
+                heston_step<MASK, ANTI>(p, m, vp, vm, z[0], z[1], k);
             }
             ep = finish_log<MASK>(p, S0, inv_n);
             if (ANTI) em = finish_log<MASK>(m, S0, inv_n);
-        } else {  // OPTP_PROC_GBM_MILSTEIN, processes.py:296-303
+        } else {  // OPTP_PROC_GBM_MILSTEIN
             LinState p, m;
             p.S = p.smax = p.smin = S0;
             m = p;
-            unsigned int t = 0;
 #pragma unroll 1
-            for (unsigned int c = 0; c < n_calls; ++c) {
-                float z[4];
+            for (unsigned int c = 0; c < n_full; ++c) {
                 philox_normals4(a.seed, gpath, c, 0u, z);
 #pragma unroll
-                for (int j = 0; j < 4; ++j, ++t) {
-                    if (t < n_steps) {
-                        // S' = S + S*g with g kept as a SMALL number: folding the 1 into a
-                        // rounded fp32 constant would bias every step by up to 6e-8
-                        const float zs = k.m_ssdt * z[j];
-                        const float zq = fmaf(k.m_hs2dt * z[j], z[j], k.m_c1);
-                        p.S = fmaxf(fmaf(p.S, zq + zs, p.S), 1e-10f);
-                        observe_lin<MASK>(p);
-                        if (ANTI) {
-                            m.S = fmaxf(fmaf(m.S, zq - zs, m.S), 1e-10f);
-                            observe_lin<MASK>(m);
-                        }
-                    }
-                }
+                for (int j = 0; j < 4; ++j) gbmm_step<MASK, ANTI>(p, m, z[j], k);
+            }
+            if (n_tail) {
+                philox_normals4(a.seed, gpath, n_full, 0u, z);
+                for (unsigned int j = 0; j < n_tail; ++j) gbmm_step<MASK, ANTI>(p, m, z[j], k);
             }
             ep = finish_lin<MASK>(p, inv_n);
             if (ANTI) em = finish_lin<MASK>(m, inv_n);

@@ -50,16 +50,30 @@ int require_ready();
 // the 128-bit counter is (base path index lo, hi, step block, stream), the 64-bit key is
 // the user's seed, so a draw depends only on (seed, path, step) -- never on the grid
 // shape or on how paths are sharded over GPUs.
+// 32x32 -> 64 multiply as ONE IMAD.WIDE.U32 (writing the product as a 64-bit C++ expression
+// makes nvcc add a dead "hi + 0" VIADD per multiply inside unrolled loops).
+__host__ __device__ __forceinline__ void mulhilo32(uint32_t a, uint32_t b, uint32_t& hi,
+                                                  uint32_t& lo) {
+#ifdef __CUDA_ARCH__
+    asm("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}"
+        : "=r"(lo), "=r"(hi)
+        : "r"(a), "r"(b));
+#else
+    const uint64_t p = (uint64_t)a * b;
+    hi = (uint32_t)(p >> 32);
+    lo = (uint32_t)p;
+#endif
+}
+
 __host__ __device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2,
                                                       uint32_t& c3, uint32_t k0, uint32_t k1) {
-    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
-    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
-    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
-    c1 = (uint32_t)p1;
-    c3 = (uint32_t)p0;
-    c0 = n0;
-    c2 = n2;
+    uint32_t h0, l0, h1, l1;
+    mulhilo32(0xD2511F53u, c0, h0, l0);
+    mulhilo32(0xCD9E8D57u, c2, h1, l1);
+    c0 = h1 ^ c1 ^ k0;
+    c2 = h0 ^ c3 ^ k1;
+    c1 = l1;
+    c3 = l0;
 }
 
 __host__ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
@@ -75,14 +89,11 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------ uniforms / normals
-// One 32-bit word -> u in (0,1]:  top 23 bits build a float in [1,2) with bit operations
-// (no I2F, which would share the 16-lane XU pipe with the MUFU ops); u = 2 - f.  The lowest
-// cell (0, 2^-23] is refined with the 9 spare bits so the radius reaches 6.7 sigma.
+// One 32-bit word -> u in (0,1]:  u = (w + 0.5) * 2^-32 as I2FP + FFMA (two issue slots; all 32
+// bits count at the low end, so the radius sqrt(-2 ln u) reaches 6.7 sigma; w = 2^32-1 rounds
+// to u = 1 -> radius 0, never a NaN).
 __device__ __forceinline__ float u01_open_low(uint32_t w) {
-    const float f = __uint_as_float(0x3f800000u | (w >> 9));
-    float u = 2.0f - f;
-    if ((w >> 9) == 0x7fffffu) u = ((float)(w & 511u) + 0.5f) * 2.3283064365386963e-10f;
-    return u;
+    return fmaf(__uint2float_rn(w), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
 }
 
 __device__ __forceinline__ float mufu_lg2(float x) {
@@ -116,9 +127,8 @@ __device__ __forceinline__ void box_muller(uint32_t w0, uint32_t w1, float& z0, 
     const float u = u01_open_low(w0);
     // r = sqrt(-2 ln u) = sqrt(-2 ln2 * lg2 u)
     const float r = mufu_sqrt(-1.3862943611198906f * mufu_lg2(u));
-    // angle = 2*pi*(f-1), f in [1,2)
-    const float f = __uint_as_float(0x3f800000u | (w1 >> 9));
-    const float a = fmaf(f, 6.283185307179586f, -6.283185307179586f);
+    // angle = 2*pi*w1/2^32 in [0, 2*pi]
+    const float a = __uint2float_rn(w1) * 1.4629180792671596e-9f;
     z0 = r * mufu_cos(a);
     z1 = r * mufu_sin(a);
 }
