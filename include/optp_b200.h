@@ -174,7 +174,9 @@ int optp_crr_batch_dev(const double* S0, const double* K, const double* T, const
 /* ---- roofline microbenchmarks (bench.py only) ---------------------------------
  * Measure the peaks MEASURED_PEAKS.json lacks, on the device, with CUDA events:
  *   which = 0 FP32 FFMA lane-ops/s, 1 MUFU.EX2 ops/s, 2 FP64 DFMA lane-ops/s,
- *           3 shared-memory bytes/s (LDS.64 conflict-free), 4 IMAD.WIDE lane-ops/s. */
+ *           3 shared-memory bytes/s (LDS.64 conflict-free), 4 IMAD.WIDE+LOP3 pairs/s,
+ *           5..14 single-opcode probes used to build the pipe model in profiles/ (IMAD.WIDE,
+ *           IMAD.HI, IMAD, LOP3, I2FP, MUFU.SIN, MUFU.LG2, MUFU.SQRT, FMNMX, FADD lane-ops/s). */
 int optp_microbench(int which, double* per_second_out, double* sm_clock_mhz_out);
 
 #ifdef __cplusplus

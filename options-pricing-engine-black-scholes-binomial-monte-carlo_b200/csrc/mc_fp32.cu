@@ -91,10 +91,13 @@ __global__ void __launch_bounds__(256) terminal_fp32_kernel(TermArgs a) {
     unsigned long long g = g_lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     while (g < g_hi) {
         float sx = 0, sxx = 0, sy = 0, syy = 0, sxy = 0;
+        uint4 w = philox_words(a.seed, g, 0u, kTermStream);
 #pragma unroll 1
         for (int it = 0; it < kFlush && g < g_hi; ++it, g += stride) {
             float z[4];
-            philox_normals4(a.seed, g, 0u, kTermStream, z);
+            const uint4 wn = philox_words(a.seed, g + stride, 0u, kTermStream);  // software pipeline
+            normals_from_words(w, z);
+            w = wn;
             const bool full = (g << 2) >= first && (g << 2) + 4 <= last;
             if (full) {
 #pragma unroll
@@ -320,14 +323,17 @@ __global__ void __launch_bounds__(256, 5) path_fp32_kernel(PathArgs a) {
         float z[4];
         if (PROC == OPTP_PROC_GBM) {
             LogState p, m;
+            uint4 w = philox_words(a.seed, gpath, 0u, 0u);
 #pragma unroll 1
             for (unsigned int c = 0; c < n_full; ++c) {
-                philox_normals4(a.seed, gpath, c, 0u, z);
+                const uint4 wn = philox_words(a.seed, gpath, c + 1, 0u);  // software pipeline
+                normals_from_words(w, z);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) gbm_step<MASK, ANTI>(p, m, z[j], k);
+                w = wn;
             }
             if (n_tail) {
-                philox_normals4(a.seed, gpath, n_full, 0u, z);
+                normals_from_words(w, z);
                 for (unsigned int j = 0; j < n_tail; ++j) gbm_step<MASK, ANTI>(p, m, z[j], k);
             }
             ep = finish_log<MASK>(p, S0, inv_n);
@@ -335,14 +341,17 @@ __global__ void __launch_bounds__(256, 5) path_fp32_kernel(PathArgs a) {
         } else if (PROC == OPTP_PROC_HESTON_FTE) {
             LogState p, m;
             float vp = fmaxf((float)a.v0, 0.f), vm = vp;
+            uint4 w = philox_words(a.seed, gpath, 0u, 0u);
 #pragma unroll 1
             for (unsigned int c = 0; c < n_full; ++c) {
-                philox_normals4(a.seed, gpath, c, 0u, z);
+                const uint4 wn = philox_words(a.seed, gpath, c + 1, 0u);
+                normals_from_words(w, z);
                 heston_step<MASK, ANTI>(p, m, vp, vm, z[0], z[1], k);
                 heston_step<MASK, ANTI>(p, m, vp, vm, z[2], z[3], k);
+                w = wn;
             }
             if (n_tail) {
-                philox_normals4(a.seed, gpath, n_full, 0u, z);
+                normals_from_words(w, z);
                 heston_step<MASK, ANTI>(p, m, vp, vm, z[0], z[1], k);
             }
             ep = finish_log<MASK>(p, S0, inv_n);
@@ -351,14 +360,17 @@ __global__ void __launch_bounds__(256, 5) path_fp32_kernel(PathArgs a) {
             LinState p, m;
             p.S = p.smax = p.smin = S0;
             m = p;
+            uint4 w = philox_words(a.seed, gpath, 0u, 0u);
 #pragma unroll 1
             for (unsigned int c = 0; c < n_full; ++c) {
-                philox_normals4(a.seed, gpath, c, 0u, z);
+                const uint4 wn = philox_words(a.seed, gpath, c + 1, 0u);
+                normals_from_words(w, z);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) gbmm_step<MASK, ANTI>(p, m, z[j], k);
+                w = wn;
             }
             if (n_tail) {
-                philox_normals4(a.seed, gpath, n_full, 0u, z);
+                normals_from_words(w, z);
                 for (unsigned int j = 0; j < n_tail; ++j) gbmm_step<MASK, ANTI>(p, m, z[j], k);
             }
             ep = finish_lin<MASK>(p, inv_n);
@@ -468,10 +480,13 @@ __global__ void __launch_bounds__(kLvThreads) lv_fp32_kernel(PathArgs a, int row
             }
             __syncthreads();
             if (active) {
+                uint4 w = philox_words(a.seed, gpath, t0 >> 2, 0u);
 #pragma unroll 1
                 for (unsigned int r = 0; r < nr; r += 4) {
                     float z[4];
-                    philox_normals4(a.seed, gpath, (t0 + r) >> 2, 0u, z);
+                    const uint4 wn = philox_words(a.seed, gpath, ((t0 + r) >> 2) + 1, 0u);
+                    normals_from_words(w, z);
+                    w = wn;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         if (r + j < nr) {

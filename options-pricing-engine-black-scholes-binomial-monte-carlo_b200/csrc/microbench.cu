@@ -85,6 +85,71 @@ peak_kernel(float* sink, long long* clocks, float seed_f, double seed_d, unsigne
 #pragma unroll
         for (int i = 0; i < kChains; ++i) t += s[i];
         if (t == 123.456) sink[0] = (float)t;
+    } else if (WHICH >= 5) {  // single-instruction probes (inline PTX pins the opcode)
+        unsigned int v[kChains];
+        float f[kChains];
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) {
+            v[i] = seed_u + threadIdx.x + i;
+            f[i] = seed_f * 0.5f + (float)i * 0.01f;
+        }
+#pragma unroll 1
+        for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int i = 0; i < kChains; ++i) {
+                    if (WHICH == 5) {  // IMAD.WIDE only: hi word feeds the next multiply
+                        unsigned int lo, hi;
+                        asm volatile("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}"
+                                     : "=r"(lo), "=r"(hi) : "r"(v[i]), "r"(0xD2511F53u));
+                        v[i] = hi;
+                    } else if (WHICH == 6) {  // IMAD.HI
+                        asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(v[i]) : "r"(v[i]), "r"(0xD2511F53u));
+                    } else if (WHICH == 7) {  // IMAD (low 32 bits)
+                        asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(v[i]) : "r"(v[i]), "r"(0xD2511F53u), "r"(seed_u));
+                    } else if (WHICH == 8) {  // LOP3
+                        asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(v[i]) : "r"(v[i]), "r"(seed_u), "r"(it));
+                    } else if (WHICH == 9) {  // I2FP
+                        asm volatile("cvt.rn.f32.u32 %0, %1;" : "=f"(f[i]) : "r"(v[i]));
+                        v[i] = __float_as_uint(f[i]);
+                    } else if (WHICH == 10) {  // MUFU.SIN (+ the range-reduction FMUL)
+                        asm volatile("sin.approx.ftz.f32 %0, %1;" : "=f"(f[i]) : "f"(f[i]));
+                    } else if (WHICH == 11) {  // MUFU.LG2
+                        asm volatile("lg2.approx.ftz.f32 %0, %1;" : "=f"(f[i]) : "f"(f[i]));
+                    } else if (WHICH == 12) {  // MUFU.SQRT
+                        asm volatile("sqrt.approx.ftz.f32 %0, %1;" : "=f"(f[i]) : "f"(f[i]));
+                    } else if (WHICH == 13) {  // FMNMX
+                        asm volatile("max.f32 %0, %1, %2;" : "=f"(f[i]) : "f"(f[i]), "f"(seed_f));
+                    } else if (WHICH == 14) {  // FADD
+                        asm volatile("add.f32 %0, %1, %2;" : "=f"(f[i]) : "f"(f[i]), "f"(seed_f));
+                    } else if (WHICH == 15 || WHICH == 16 || WHICH == 17) {
+                        // does IMAD.WIDE hold the issue port?  1 IMAD.WIDE + 3 FFMA (15), + 3 FMNMX (16),
+                        // + 1 MUFU.EX2 (17) per group; counted as one op per group
+                        unsigned int lo, hi;
+                        asm volatile("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}"
+                                     : "=r"(lo), "=r"(hi) : "r"(v[i]), "r"(0xD2511F53u));
+                        v[i] = hi;
+                        if (WHICH == 15) {
+                            asm volatile("fma.rn.f32 %0, %0, %1, %2;\n\tfma.rn.f32 %0, %0, %1, %2;\n\tfma.rn.f32 %0, %0, %1, %2;"
+                                         : "+f"(f[i]) : "f"(seed_f), "f"(0.25f));
+                        } else if (WHICH == 16) {
+                            asm volatile("max.f32 %0, %0, %1;\n\tmin.f32 %0, %0, %2;\n\tmax.f32 %0, %0, %1;"
+                                         : "+f"(f[i]) : "f"(seed_f), "f"(0.25f));
+                        } else {
+                            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(f[i]));
+                        }
+                    }
+                }
+        }
+        unsigned int sv = 0;
+        float sf = 0;
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) {
+            sv ^= v[i];
+            sf += f[i];
+        }
+        if (sv == 0x12345u && sf == 1.5f) sink[0] = sf;
     } else {  // IMAD.WIDE (32x32 -> 64), the Philox round multiplier
         unsigned int v[kChains];
 #pragma unroll
@@ -156,6 +221,19 @@ extern "C" int optp_microbench(int which, double* per_second_out, double* sm_clo
         case 2: return run_peak<2>(per_second_out, sm_clock_mhz_out);
         case 3: return run_peak<3>(per_second_out, sm_clock_mhz_out);
         case 4: return run_peak<4>(per_second_out, sm_clock_mhz_out);
+        case 5: return run_peak<5>(per_second_out, sm_clock_mhz_out);
+        case 6: return run_peak<6>(per_second_out, sm_clock_mhz_out);
+        case 7: return run_peak<7>(per_second_out, sm_clock_mhz_out);
+        case 8: return run_peak<8>(per_second_out, sm_clock_mhz_out);
+        case 9: return run_peak<9>(per_second_out, sm_clock_mhz_out);
+        case 10: return run_peak<10>(per_second_out, sm_clock_mhz_out);
+        case 11: return run_peak<11>(per_second_out, sm_clock_mhz_out);
+        case 12: return run_peak<12>(per_second_out, sm_clock_mhz_out);
+        case 13: return run_peak<13>(per_second_out, sm_clock_mhz_out);
+        case 14: return run_peak<14>(per_second_out, sm_clock_mhz_out);
+        case 15: return run_peak<15>(per_second_out, sm_clock_mhz_out);
+        case 16: return run_peak<16>(per_second_out, sm_clock_mhz_out);
+        case 17: return run_peak<17>(per_second_out, sm_clock_mhz_out);
         default: return set_error(OPTP_E_ARG, "unknown microbenchmark %d", which);
     }
 }

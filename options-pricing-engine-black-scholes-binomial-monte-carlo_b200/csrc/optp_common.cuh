@@ -133,13 +133,24 @@ __device__ __forceinline__ void box_muller(uint32_t w0, uint32_t w1, float& z0, 
     z1 = r * mufu_sin(a);
 }
 
-// Four normals of (seed, base path, block, stream).
-__device__ __forceinline__ void philox_normals4(uint64_t seed, uint64_t path, uint32_t block,
-                                                uint32_t stream, float z[4]) {
-    const uint4 w = philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), block, stream,
-                                  (uint32_t)seed, (uint32_t)(seed >> 32));
+// Four random words of (seed, base path, block, stream), and the four normals they map to.
+// The two halves are separate so a kernel can request the words of block c+1 before it turns
+// the words of block c into normals: the integer Philox chain (IMAD.WIDE / LOP3) then overlaps
+// the MUFU-bound Box-Muller of the previous block inside one warp's instruction stream.
+__device__ __forceinline__ uint4 philox_words(uint64_t seed, uint64_t path, uint32_t block,
+                                              uint32_t stream) {
+    return philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), block, stream, (uint32_t)seed,
+                         (uint32_t)(seed >> 32));
+}
+
+__device__ __forceinline__ void normals_from_words(const uint4& w, float z[4]) {
     box_muller(w.x, w.y, z[0], z[1]);
     box_muller(w.z, w.w, z[2], z[3]);
+}
+
+__device__ __forceinline__ void philox_normals4(uint64_t seed, uint64_t path, uint32_t block,
+                                                uint32_t stream, float z[4]) {
+    normals_from_words(philox_words(seed, path, block, stream), z);
 }
 
 // ------------------------------------------------------------------ fp64 reductions
