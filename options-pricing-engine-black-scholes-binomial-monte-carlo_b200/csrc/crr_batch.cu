@@ -80,8 +80,14 @@ __device__ __forceinline__ double pick_max(double c, double e) { return e > c ? 
 // Every L.R levels (and at the end) the registers are multiplied back by pd^m; L.R bounds
 // pd^-m by 2^+-200, so no contract can overflow.  Rounding differs from binomial.py:29 by
 // O(1 ulp) per level -- far inside the 1e-10 parity bar.
+// u^(2i), i < 32, as a two-level table: u^(2i) = hi[i >> 3] * lo[i & 7] (24 registers instead of
+// 64; the freed registers are what lets ptxas overlap the exercise DFMA -> DSETP -> FSEL chains).
+struct UTab {
+    double lo[8], hi[4];
+};
+
 template <int B, bool AMER>
-__device__ __forceinline__ void run_levels(double (&v)[32], const double (&U2)[32], double sb,
+__device__ __forceinline__ void run_levels(double (&v)[32], const UTab& U, double sb,
                                            const Lattice& L, int k_hi, int k_lo) {
     int k = k_hi;
     while (k >= k_lo) {
@@ -96,13 +102,39 @@ __device__ __forceinline__ void run_levels(double (&v)[32], const double (&U2)[3
             back *= L.pd;
             sb *= L.u;
             double nb_next = 0.0;
+            double sa[4];
+            if (AMER) {
 #pragma unroll
-            for (int i = 0; i < B; ++i) {
-                const double up = (i + 1 < B) ? v[i + 1] : nb;
-                double c = fma(L.rho, up, v[i]);
-                if (AMER) c = pick_max(c, fma(sbg, U2[i], sKg));
-                v[i] = c;
-                if (i == 0) nb_next = __shfl_down_sync(0xffffffffu, c, 1);
+                for (int a = 0; a < 4; ++a)
+                    if (8 * a < B) sa[a] = sbg * U.hi[a];
+            }
+            // groups of G nodes: all continuation DFMAs, all exercise DFMAs, all compares, all
+            // selects -- so the DFMA -> DSETP -> FSEL latencies of one node are covered by the
+            // other nodes of the group instead of being exposed per node
+            constexpr int G = (B >= 8) ? 8 : B;
+#pragma unroll
+            for (int g0 = 0; g0 < B; g0 += G) {
+                double c[G], e[G];
+#pragma unroll
+                for (int t = 0; t < G; ++t) {
+                    const int i = g0 + t;
+                    if (i < B) {
+                        const double up = (i + 1 < B) ? v[i + 1] : nb;
+                        c[t] = fma(L.rho, up, v[i]);
+                    }
+                }
+                if (AMER) {
+#pragma unroll
+                    for (int t = 0; t < G; ++t)
+                        if (g0 + t < B) e[t] = fma(sa[(g0 + t) >> 3], U.lo[(g0 + t) & 7], sKg);
+#pragma unroll
+                    for (int t = 0; t < G; ++t)
+                        if (g0 + t < B) c[t] = pick_max(c[t], e[t]);
+                }
+#pragma unroll
+                for (int t = 0; t < G; ++t)
+                    if (g0 + t < B) v[g0 + t] = c[t];
+                if (g0 == 0) nb_next = __shfl_down_sync(0xffffffffu, c[0], 1);
             }
             nb = nb_next;
         }
@@ -131,20 +163,20 @@ __device__ __forceinline__ void repack(double (&v)[32], double* tile, int lane) 
 // (BN = 0 ends the schedule).  `k` is the next output level.  Once the walk has started
 // every later stage runs, so the previous layout is always the previous schedule entry.
 template <int BPREV, int B, int BN, bool AMER>
-__device__ __forceinline__ void stage(double (&v)[32], const double (&U2)[32], const Lattice& L,
+__device__ __forceinline__ void stage(double (&v)[32], const UTab& U, const Lattice& L,
                                       int N, int& k, bool& started, double* tile, int lane) {
     if (!started) {
         // terminal payoff, binomial.py:20-25
         const double sbN = lane_base(L, lane, B, N);
 #pragma unroll
-        for (int i = 0; i < B; ++i) v[i] = pick_max(0.0, fma(sbN, U2[i], L.sK));
+        for (int i = 0; i < B; ++i) v[i] = pick_max(0.0, fma(sbN * U.hi[i >> 3], U.lo[i & 7], L.sK));
         started = true;
     } else {
         repack<BPREV, B>(v, tile, lane);
     }
     const int k_lo = (BN > 0) ? (32 * BN - 1) : 0;
     const double sb = AMER ? lane_base(L, lane, B, k + 1) : 0.0;
-    run_levels<B, AMER>(v, U2, sb, L, k, k_lo);
+    run_levels<B, AMER>(v, U, sb, L, k, k_lo);
     k = k_lo - 1;
 }
 
@@ -166,12 +198,17 @@ crr_warp_kernel(CrrArgs a) {
             }
             continue;
         }
-        double U2[32], v[32];
+        double v[32];
+        UTab U;
         {
             const double u2 = L.u * L.u;
-            U2[0] = 1.0;
+            U.lo[0] = 1.0;
 #pragma unroll
-            for (int i = 1; i < 32; ++i) U2[i] = U2[i - 1] * u2;
+            for (int i = 1; i < 8; ++i) U.lo[i] = U.lo[i - 1] * u2;
+            const double u16 = U.lo[7] * u2;
+            U.hi[0] = 1.0;
+#pragma unroll
+            for (int a = 1; a < 4; ++a) U.hi[a] = U.hi[a - 1] * u16;
         }
         int k = a.N - 1;
         bool started = false;
@@ -179,7 +216,7 @@ crr_warp_kernel(CrrArgs a) {
         // pick the first layout that holds the N+1 terminal nodes, then walk the schedule
 #define OPTP_STAGE(BP, B, BN)                                                         \
     if (started || N + 1 > 32 * (BN))                                                 \
-        stage<BP, B, BN, AMER>(v, U2, L, N, k, started, tile, lane);
+        stage<BP, B, BN, AMER>(v, U, L, N, k, started, tile, lane);
         OPTP_STAGE(32, 32, 28)
         OPTP_STAGE(32, 28, 24)
         OPTP_STAGE(28, 24, 20)

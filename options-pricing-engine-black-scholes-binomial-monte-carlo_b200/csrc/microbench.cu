@@ -85,6 +85,38 @@ peak_kernel(float* sink, long long* clocks, float seed_f, double seed_d, unsigne
 #pragma unroll
         for (int i = 0; i < kChains; ++i) t += s[i];
         if (t == 123.456) sink[0] = (float)t;
+    } else if (WHICH == 18 || WHICH == 19) {
+        // CRR node-update mix, 4 independent chains: DFMA, DFMA, DSETP, 2 FSEL (18, American) or one
+        // DFMA (19, European); counted as one op per node update (the caller halves kChains)
+        constexpr int NC = 4;
+        double v[NC], U[NC];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            v[i] = seed_d + (double)(threadIdx.x + i);
+            U[i] = seed_d * (1.0 + 0.01 * i);
+        }
+        const double rho = seed_d * 0.25 + 0.5;
+        double a = seed_d * 1e-3, kk = -seed_d;
+#pragma unroll 1
+        for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    double c = fma(rho, v[(i + 1) % NC], v[i]);
+                    if (WHICH == 18) {
+                        const double e = fma(a, U[i], kk);
+                        c = e > c ? e : c;
+                    }
+                    v[i] = c;
+                }
+                if (WHICH == 18) a = -a;  // keeps the exercise DFMA inside the loop (one FADD-class op per 4 nodes)
+            }
+        }
+        double t = 0;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) t += v[i];
+        if (t == 123.456) sink[0] = (float)t;
     } else if (WHICH >= 5) {  // single-instruction probes (inline PTX pins the opcode)
         unsigned int v[kChains];
         float f[kChains];
@@ -234,6 +266,8 @@ extern "C" int optp_microbench(int which, double* per_second_out, double* sm_clo
         case 15: return run_peak<15>(per_second_out, sm_clock_mhz_out);
         case 16: return run_peak<16>(per_second_out, sm_clock_mhz_out);
         case 17: return run_peak<17>(per_second_out, sm_clock_mhz_out);
+        case 18: return run_peak<18>(per_second_out, sm_clock_mhz_out);
+        case 19: return run_peak<19>(per_second_out, sm_clock_mhz_out);
         default: return set_error(OPTP_E_ARG, "unknown microbenchmark %d", which);
     }
 }

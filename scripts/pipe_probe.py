@@ -7,7 +7,8 @@ sys.path.insert(0, os.path.join(ROOT, "options-pricing-engine-black-scholes-bino
 from optpricer_b200 import _native as nv  # noqa: E402
 names = ["FFMA", "MUFU.EX2", "DFMA", "LDS.64 bytes", "IMAD.WIDE+LOP3", "IMAD.WIDE", "IMAD.HI", "IMAD", "LOP3", "I2FP",
          "sin.approx (FMUL+MUFU.SIN)", "MUFU.LG2", "MUFU.SQRT", "FMNMX", "FADD",
-         "group: IMAD.WIDE + 3 FFMA", "group: IMAD.WIDE + 3 FMNMX", "group: IMAD.WIDE + MUFU.EX2"]
+         "group: IMAD.WIDE + 3 FFMA", "group: IMAD.WIDE + 3 FMNMX", "group: IMAD.WIDE + MUFU.EX2",
+         "CRR node: DFMA,DFMA,DSETP,2 FSEL", "CRR node: DFMA"]
 nv.init(0)
 for i, n in enumerate(names):
     v, _ = nv.microbench(i)
