@@ -32,6 +32,7 @@ struct CrrArgs {
     int N;
     double* price;
     uint8_t* status;
+    int todo_only;  // full-width kernels: price only contracts the band kernel left at status 2
 };
 
 struct Lattice {
@@ -190,6 +191,7 @@ crr_warp_kernel(CrrArgs a) {
     const unsigned long long warp0 = (unsigned long long)blockIdx.x * kWarpsPerCta + wib;
     const unsigned long long nwarps = (unsigned long long)gridDim.x * kWarpsPerCta;
     for (unsigned long long o = warp0; o < a.n; o += nwarps) {
+        if (a.todo_only && a.status[o] != 2) continue;
         const Lattice L = make_lattice(a, o);
         if (!L.ok) {  // binomial.py:16-17 -> per-contract status instead of raising
             if (lane == 0) {
@@ -235,6 +237,274 @@ crr_warp_kernel(CrrArgs a) {
         }
     }
 }
+
+
+// ---------------------------------------------------------------- banded American put kernel
+// The N = 1000 lattice spans +-31 standard deviations of ln S_T; almost all of it is either
+// exactly worthless (every terminal descendant out of the money: V = 0 bit-for-bit), worthless
+// to 2^-90 K, or deep inside the early-exercise region where V = K - S is known in closed form.
+// This kernel walks only the band between the exercise boundary and the (numerically) zero
+// region, one option per warp, band in registers, in segments of <= 32 levels:
+//   * within a segment the window [w0, w0 + 32B) is fixed in index space; node j needs nodes j
+//     and j+1 of the next level only, so nothing BELOW the window is ever read, and the node
+//     just ABOVE the window top is 0 (lane 31's neighbour);
+//   * at a segment boundary the band [jlo, jhi) is measured from the registers (jlo = first
+//     node that did not choose exercise at the last level, jhi = 1 + last node worth more than
+//     2^-90 K), the next window [jlo - nlev - 2, min(jhi, k+1)) is laid out with the smallest
+//     B that holds it, and the level is re-packed through a shared-memory tile; nodes entering
+//     from below get the exercise value, nodes entering from above get 0.
+// Why the cut at the bottom is exact: if both children of a node are exercise nodes then
+// cont = disc*K - S*e^{-q dt} < K - S whenever K(1-disc) > S(1-e^{-q dt}), which r > q >= 0
+// guarantees for every S < K; so the exercise boundary index drops by at most one per level
+// and a margin of nlev + 2 nodes keeps the window bottom inside the exercise region for the
+// whole segment.  The cut at the top discards values below 2^-90 K (they can only shrink at a
+// fixed index going back in time); the induced error is < 1e-21 K.  Contracts that do not
+// qualify (calls, European, r <= q, band wider than 512 nodes) are left at status 2 and priced
+// by the full-width kernel in a second launch.
+constexpr int kBandWarps = 4;
+constexpr int kBandMaxB = 16;
+constexpr int kBandTile = 32 * kBandMaxB + 8;
+
+// one level for B nodes per lane; `nb` is the next lane's first node (0 above the window).
+// FLAGS: also return a bit mask of the nodes that chose exercise.
+template <int B, bool FLAGS>
+__device__ __forceinline__ unsigned int band_level(double (&v)[kBandMaxB], const UTab& U, double rho,
+                                                   double sbg, double sKg, double nb) {
+    double sa[2];
+    sa[0] = sbg;
+#pragma unroll
+    for (int a = 1; a < 2; ++a)
+        if (8 * a < B) sa[a] = sbg * U.hi[a];
+    unsigned int mask = 0;
+    constexpr int G = (B >= 8) ? 8 : B;
+#pragma unroll
+    for (int g0 = 0; g0 < B; g0 += G) {
+        double c[G], e[G];
+#pragma unroll
+        for (int t = 0; t < G; ++t) {
+            const int i = g0 + t;
+            if (i < B) {
+                const double up = (i + 1 < B) ? v[i + 1] : nb;
+                c[t] = fma(rho, up, v[i]);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < G; ++t)
+            if (g0 + t < B) e[t] = fma(sa[(g0 + t) >> 3], U.lo[(g0 + t) & 7], sKg);
+#pragma unroll
+        for (int t = 0; t < G; ++t) {
+            if (g0 + t < B) {
+                const bool ex = e[t] > c[t];
+                if (FLAGS) mask |= ex ? (1u << (g0 + t)) : 0u;
+                v[g0 + t] = ex ? e[t] : c[t];
+            }
+        }
+    }
+    return mask;
+}
+
+// nlev levels (the first one is level k_first) on window w0 in layout B; returns the exercise
+// mask of the last level.  nlev <= L.R, so the scaled recursion cannot overflow.
+template <int B>
+__device__ __forceinline__ unsigned int band_segment(double (&v)[kBandMaxB], const UTab& U,
+                                                     const Lattice& L, int lane, int w0, int k_first,
+                                                     int nlev) {
+    double sbg = L.sgn * L.S0 * pow(L.u, (double)(2 * (w0 + lane * B) - (k_first + 1)));
+    double sKg = L.sK, back = 1.0;
+    double nb = __shfl_down_sync(0xffffffffu, v[0], 1);
+    if (lane == 31) nb = 0.0;
+    unsigned int mask = 0;
+    for (int t = 0; t < nlev; ++t) {
+        sbg *= L.u_pd;
+        sKg *= L.inv_pd;
+        back *= L.pd;
+        if (t + 1 < nlev) {
+            band_level<B, false>(v, U, L.rho, sbg, sKg, nb);
+        } else {
+            mask = band_level<B, true>(v, U, L.rho, sbg, sKg, nb);
+        }
+        nb = __shfl_down_sync(0xffffffffu, v[0], 1);
+        if (lane == 31) nb = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < B; ++i) v[i] *= back;
+    return mask;
+}
+
+template <int B>
+__device__ __forceinline__ void band_store(const double (&v)[kBandMaxB], double* tile, int lane) {
+#pragma unroll
+    for (int i = 0; i < B; ++i) tile[i * 32 + lane] = v[i];  // conflict-free, slot-major
+}
+
+// lane-local scan of the registers at level k: first non-exercise slot, last slot above thr
+template <int B>
+__device__ __forceinline__ void band_scan(const double (&v)[kBandMaxB], unsigned int exmask, int j0,
+                                          int k, double thr, int& first_cont, int& last_live) {
+    const unsigned int full = (B >= 32) ? 0xffffffffu : ((1u << B) - 1u);
+    const unsigned int cont = ~exmask & full;
+    first_cont = cont ? (__ffs(cont) - 1) : B;
+    last_live = -1;
+#pragma unroll
+    for (int i = 0; i < B; ++i)
+        if (v[i] > thr && j0 + i <= k) last_live = i;
+}
+
+#define OPTP_BAND_SWITCH(Bv, CALL)        \
+    switch (Bv) {                         \
+        case 1: { constexpr int BB = 1; CALL; } break;   \
+        case 2: { constexpr int BB = 2; CALL; } break;   \
+        case 3: { constexpr int BB = 3; CALL; } break;   \
+        case 4: { constexpr int BB = 4; CALL; } break;   \
+        case 6: { constexpr int BB = 6; CALL; } break;   \
+        case 8: { constexpr int BB = 8; CALL; } break;   \
+        case 12: { constexpr int BB = 12; CALL; } break; \
+        default: { constexpr int BB = 16; CALL; } break; \
+    }
+
+__device__ __forceinline__ int band_pick_B(int width) {
+    const int need = (width + 31) >> 5;
+    if (need <= 4) return need < 1 ? 1 : need;
+    if (need <= 6) return 6;
+    if (need <= 8) return 8;
+    if (need <= 12) return 12;
+    return 16;
+}
+
+__global__ void __launch_bounds__(kBandWarps * 32, 3) crr_band_kernel(CrrArgs a) {
+    __shared__ double tiles[kBandWarps][kBandTile];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    double* tile = tiles[wib];
+    const int N = a.N;
+    const unsigned long long warp0 = (unsigned long long)blockIdx.x * kBandWarps + wib;
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * kBandWarps;
+    for (unsigned long long o = warp0; o < a.n; o += nwarps) {
+        const Lattice L = make_lattice(a, o);
+        if (!L.ok) {
+            if (lane == 0) {
+                a.price[o] = nan("");
+                a.status[o] = 1;
+            }
+            continue;
+        }
+        const double r = a.r[o], q = a.q[o], K = a.K[o];
+        const double dt = a.T[o] / (double)N;
+        const double one_m_disc = -expm1(-r * dt), one_m_dq = -expm1(-q * dt);
+        const bool eligible = (L.sgn < 0.0) && q >= 0.0 && one_m_disc > 1e-9 &&
+                              one_m_disc > one_m_dq * (1.0 + 1e-6);
+        if (!eligible) {
+            if (lane == 0) a.status[o] = 2;
+            continue;
+        }
+        UTab U;
+        {
+            const double u2 = L.u * L.u;
+            U.lo[0] = 1.0;
+#pragma unroll
+            for (int i = 1; i < 8; ++i) U.lo[i] = U.lo[i - 1] * u2;
+            const double u16 = U.lo[7] * u2;
+            U.hi[0] = 1.0;
+#pragma unroll
+            for (int i = 1; i < 4; ++i) U.hi[i] = U.hi[i - 1] * u16;
+        }
+        const double thr = K * 8.0779356694631609e-28;  // 2^-90 K
+        double v[kBandMaxB];
+        // ---- level N: every node is closed form, max(K - S, 0) (binomial.py:20-25) ----------
+        int B = 2, k = N;
+        // index of the first out-of-the-money terminal node, S0*u^(2j-N) >= K
+        const double jz = 0.5 * ((double)N + log(K / L.S0) / log(L.u));
+        int w0 = (int)fmin(fmax(jz - 31.0, 0.0), (double)max(0, N + 1 - 64));
+        unsigned int exmask = 0;
+        {
+            const double sb = L.sgn * L.S0 * pow(L.u, (double)(2 * (w0 + lane * 2) - N));
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const double e = fma(sb, U.lo[i], L.sK);
+                v[i] = e > 0.0 ? e : 0.0;
+                exmask |= (e > 0.0) ? (1u << i) : 0u;
+            }
+        }
+        bool fail = false;
+        double price = 0.0;
+        while (true) {
+            // ---- measure the band [jlo, jhi) of the level held in registers ------------------
+            int first_cont = 0, last_live = -1;
+            OPTP_BAND_SWITCH(B, band_scan<BB>(v, exmask, w0 + lane * BB, k, thr, first_cont, last_live));
+            const unsigned int has_cont = __ballot_sync(0xffffffffu, first_cont < B);
+            const unsigned int has_live = __ballot_sync(0xffffffffu, last_live >= 0);
+            int jlo, jhi;
+            if (has_cont) {
+                const int f = __ffs(has_cont) - 1;
+                jlo = w0 + f * B + __shfl_sync(0xffffffffu, first_cont, f);
+            } else {
+                jlo = w0 + 32 * B;
+            }
+            if (has_live) {
+                const int f = 31 - __clz(has_live);
+                jhi = w0 + f * B + __shfl_sync(0xffffffffu, last_live, f) + 1;
+            } else {
+                jhi = w0;
+            }
+            if (jhi < jlo) jhi = jlo;
+            // the window bottom must still be inside the exercise region (or be node 0)
+            if (w0 > 0 && jlo <= w0) fail = true;
+            if (k == 0 || fail) break;
+            // ---- next segment: levels k-1 ... k-nlev ------------------------------------------
+            int nlev = min(32, min(L.R, k));
+            int top = min(jhi, k + 1);           // exclusive; node `top` of level k is 0 (or dead)
+            int bot = max(0, jlo - nlev - 2);
+            if (top < bot + 1) top = bot + 1;
+            const int Bn = band_pick_B(top - bot);
+            if (top - bot > 32 * kBandMaxB) {
+                fail = true;
+                break;
+            }
+            int w0n = max(0, top - 32 * Bn);
+            // ---- re-pack level k from (w0, B) to (w0n, Bn) -------------------------------------
+            OPTP_BAND_SWITCH(B, band_store<BB>(v, tile, lane));
+            __syncwarp();
+            {
+                const int magic = (65536 + B - 1) / B;   // exact j / B for j < 2048
+                const double sb = L.sgn * L.S0 * pow(L.u, (double)(2 * (w0n + lane * Bn) - k));
+                const int width_old = 32 * B;
+#pragma unroll
+                for (int i = 0; i < kBandMaxB; ++i) {
+                    if (i < Bn) {
+                        const int j = w0n + lane * Bn + i;
+                        const int jr = j - w0;
+                        double val;
+                        if (jr < 0) {  // entering from below: exercise value, closed form
+                            val = fma(sb * U.hi[i >> 3], U.lo[i & 7], L.sK);
+                        } else if (jr >= width_old) {
+                            val = 0.0;
+                        } else {
+                            const int lo_ = (jr * magic) >> 16;
+                            val = tile[(jr - lo_ * B) * 32 + lo_];
+                        }
+                        v[i] = val;
+                    }
+                }
+            }
+            __syncwarp();
+            w0 = w0n;
+            B = Bn;
+            OPTP_BAND_SWITCH(B, exmask = band_segment<BB>(v, U, L, lane, w0, k - 1, nlev));
+            k -= nlev;
+        }
+        if (fail) {
+            if (lane == 0) a.status[o] = 2;
+            continue;
+        }
+        // level 0: node 0 is in the window (w0 == 0) or below it (then it is an exercise node)
+        price = (w0 == 0) ? __shfl_sync(0xffffffffu, v[0], 0) : (K - L.S0);
+        if (lane == 0) {
+            a.price[o] = price;
+            a.status[o] = 0;
+        }
+    }
+}
+#undef OPTP_BAND_SWITCH
 
 // ---------------------------------------------------------------- generic N: one option per CTA
 template <bool AMER>
@@ -283,26 +553,50 @@ __global__ void __launch_bounds__(256) crr_cta_kernel(CrrArgs a) {
     }
 }
 
-static int launch_crr(const CrrArgs& a, int american, cudaStream_t st) {
+static int launch_full_warp(const CrrArgs& a, int american, cudaStream_t st) {
     Context& c = ctx();
+    const unsigned long long want = (a.n + kWarpsPerCta - 1) / kWarpsPerCta;
+    int per_sm = 0;
+    if (american)
+        OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, crr_warp_kernel<true>,
+                                                                kWarpsPerCta * 32, 0));
+    else
+        OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, crr_warp_kernel<false>,
+                                                                kWarpsPerCta * 32, 0));
+    if (per_sm < 1) per_sm = 1;
+    // persistent warps: exactly one resident wave, options strided over warps
+    const unsigned long long cap = (unsigned long long)c.n_sm * per_sm;
+    const unsigned int grid = (unsigned int)(want < cap ? want : cap);
+    if (american)
+        crr_warp_kernel<true><<<grid, kWarpsPerCta * 32, 0, st>>>(a);
+    else
+        crr_warp_kernel<false><<<grid, kWarpsPerCta * 32, 0, st>>>(a);
+    c.launches++;
+    OPTP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st) {
+    Context& c = ctx();
+    CrrArgs a = a_in;
+    a.todo_only = 0;
     if (a.n == 0) return 0;
     if (a.N <= 1023) {
-        const unsigned long long want = (a.n + kWarpsPerCta - 1) / kWarpsPerCta;
-        int per_sm = 0;
-        if (american)
-            OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, crr_warp_kernel<true>,
-                                                                    kWarpsPerCta * 32, 0));
-        else
-            OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, crr_warp_kernel<false>,
-                                                                    kWarpsPerCta * 32, 0));
-        if (per_sm < 1) per_sm = 1;
-        // persistent warps: exactly one resident wave, options strided over warps
-        const unsigned long long cap = (unsigned long long)c.n_sm * per_sm;
-        const unsigned int grid = (unsigned int)(want < cap ? want : cap);
-        if (american)
-            crr_warp_kernel<true><<<grid, kWarpsPerCta * 32, 0, st>>>(a);
-        else
-            crr_warp_kernel<false><<<grid, kWarpsPerCta * 32, 0, st>>>(a);
+        if (american && !c.crr_no_band) {
+            // pass 1: banded kernel (American puts with r > q); pass 2: whatever it left at status 2
+            int per_sm = 0;
+            OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, crr_band_kernel,
+                                                                    kBandWarps * 32, 0));
+            if (per_sm < 1) per_sm = 1;
+            const unsigned long long want = (a.n + kBandWarps - 1) / kBandWarps;
+            const unsigned long long cap = (unsigned long long)c.n_sm * per_sm;
+            crr_band_kernel<<<(unsigned int)(want < cap ? want : cap), kBandWarps * 32, 0, st>>>(a);
+            c.launches++;
+            OPTP_CUDA(cudaGetLastError());
+            a.todo_only = 1;
+            if (c.crr_band_only) return 0;  // diagnostics: leave the status-2 contracts unpriced
+        }
+        return launch_full_warp(a, american, st);
     } else {
         const size_t smem = sizeof(double) * 3 * (size_t)(a.N + 2);
         if (smem > 227 * 1024)
@@ -337,7 +631,7 @@ extern "C" int optp_crr_batch_dev(const double* S0, const double* K, const doubl
     if (N == 0 || N > (1u << 24)) return set_error(OPTP_E_ARG, "N must be positive.");
     if (n && (!S0 || !K || !T || !r || !q || !sigma || !is_call || !price_out || !status_out))
         return set_error(OPTP_E_ARG, "null pointer argument");
-    CrrArgs a{S0, K, T, r, q, sigma, is_call, (unsigned long long)n, (int)N, price_out, status_out};
+    CrrArgs a{S0, K, T, r, q, sigma, is_call, (unsigned long long)n, (int)N, price_out, status_out, 0};
     return launch_crr(a, american, (cudaStream_t)stream);
 }
 
@@ -373,7 +667,8 @@ extern "C" int optp_crr_batch(const double* S0, const double* K, const double* T
               (unsigned long long)n,
               (int)N,
               (double*)out,
-              (uint8_t*)(out + colp)};
+              (uint8_t*)(out + colp),
+              0};
     if (int e = launch_crr(a, american, c.stream)) return e;
     OPTP_CUDA(cudaMemcpyAsync(price_out, out, col, cudaMemcpyDeviceToHost, c.stream));
     OPTP_CUDA(cudaMemcpyAsync(status_out, out + colp, n, cudaMemcpyDeviceToHost, c.stream));

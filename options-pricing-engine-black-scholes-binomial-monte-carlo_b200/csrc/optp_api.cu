@@ -1,5 +1,6 @@
 // Context, error reporting and memory helpers of the C ABI (include/optp_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include "optp_common.cuh"
 
@@ -92,6 +93,12 @@ int optp_init(int device) {
     OPTP_CUDA(cudaHostAlloc(&c.stats_host, sizeof(double) * kMaxPayoffs * OPTP_NSTATS,
                             cudaHostAllocDefault));
     c.launches = 0;
+    {
+        const char* nb = getenv("OPTP_CRR_NO_BAND");
+        c.crr_no_band = nb && nb[0] == '1';
+        const char* bo = getenv("OPTP_CRR_BAND_ONLY");
+        c.crr_band_only = bo && bo[0] == '1';
+    }
     c.ready = true;
     return 0;
 }

@@ -27,6 +27,8 @@ struct Context {
     Arena in0, in1, out0, out1, table_f32, table_f64;
     uint32_t table_steps = 0, table_nodes = 0;
     uint64_t launches = 0;
+    bool crr_band_only = false;  // OPTP_CRR_BAND_ONLY=1: skip the fallback pass (diagnostics)
+    bool crr_no_band = false;  // OPTP_CRR_NO_BAND=1: full-width CRR kernels only (A/B testing)
 };
 
 constexpr int kMaxPayoffs = 16;

@@ -14,7 +14,7 @@ import torch  # noqa: E402
 from optpricer_b200 import _native as nv  # noqa: E402
 from bench import cfg2_contracts  # noqa: E402
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 18
+n = min(int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 18, 1_000_000)
 lib = nv.init(0)
 cols = [a[:n] for a in cfg2_contracts(1_000_000)]  # the fixture's first 64 come from the 1M-draw stream
 dev = torch.device("cuda", 0)
@@ -40,4 +40,5 @@ for american in (1, 0):
         ref = np.array(json.load(open(os.path.join(ROOT, "tests/golden/crr.json")))["cfg2_first64_american_put_N1000"])
         got = price[:64].cpu().numpy()
         msg += f"  max rel err vs reference (64 contracts) {np.max(np.abs(got - ref) / ref):.2e}"
+        msg += f"  status counts {np.bincount(status.cpu().numpy(), minlength=3).tolist()}"
     print(msg)
