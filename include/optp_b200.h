@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OPTP_ABI_VERSION 3
+#define OPTP_ABI_VERSION 4
 
 /* argument errors */
 #define OPTP_E_ARG 1        /* bad scalar argument / null pointer            */
@@ -98,6 +98,13 @@ const char* optp_last_error(void);
 int optp_device_count(void);
 /* Number of kernels this library has launched since optp_init (bench.py "gpu_launches"). */
 uint64_t optp_launch_count(void);
+/* Tuning / diagnostics switches (all default to the production setting):
+ *   "crr_band"      1 = American puts with r > q go through the banded kernel (default), 0 = every
+ *                   contract through the full-width kernels (A/B checks of the band cuts)
+ *   "crr_band_only" 1 = skip the full-width fallback pass; contracts the banded kernel declined
+ *                   keep status 2 (diagnostics only)
+ * Returns OPTP_E_ARG for an unknown key. */
+int optp_set_option(const char* key, long value);
 /* Pinned host staging memory for callers that want DMA-able buffers. */
 int optp_host_alloc(void** p, uint64_t bytes);
 int optp_host_free(void* p);

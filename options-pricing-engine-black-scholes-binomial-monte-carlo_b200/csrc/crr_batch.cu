@@ -242,7 +242,7 @@ crr_warp_kernel(CrrArgs a) {
 // ---------------------------------------------------------------- banded American put kernel
 // The N = 1000 lattice spans +-31 standard deviations of ln S_T; almost all of it is either
 // exactly worthless (every terminal descendant out of the money: V = 0 bit-for-bit), worthless
-// to 2^-90 K, or deep inside the early-exercise region where V = K - S is known in closed form.
+// to 2^-80 K, or deep inside the early-exercise region where V = K - S is known in closed form.
 // This kernel walks only the band between the exercise boundary and the (numerically) zero
 // region, one option per warp, band in registers, in segments of <= 32 levels:
 //   * within a segment the window [w0, w0 + 32B) is fixed in index space; node j needs nodes j
@@ -250,26 +250,30 @@ crr_warp_kernel(CrrArgs a) {
 //     just ABOVE the window top is 0 (lane 31's neighbour);
 //   * at a segment boundary the band [jlo, jhi) is measured from the registers (jlo = first
 //     node that did not choose exercise at the last level, jhi = 1 + last node worth more than
-//     2^-90 K), the next window [jlo - nlev - 2, min(jhi, k+1)) is laid out with the smallest
+//     2^-80 K), the next window [jlo - nlev - 2, min(jhi, k+1)) is laid out with the smallest
 //     B that holds it, and the level is re-packed through a shared-memory tile; nodes entering
 //     from below get the exercise value, nodes entering from above get 0.
 // Why the cut at the bottom is exact: if both children of a node are exercise nodes then
 // cont = disc*K - S*e^{-q dt} < K - S whenever K(1-disc) > S(1-e^{-q dt}), which r > q >= 0
 // guarantees for every S < K; so the exercise boundary index drops by at most one per level
 // and a margin of nlev + 2 nodes keeps the window bottom inside the exercise region for the
-// whole segment.  The cut at the top discards values below 2^-90 K (they can only shrink at a
+// whole segment.  The cut at the top discards values below 2^-80 K (they can only shrink at a
 // fixed index going back in time); the induced error is < 1e-21 K.  Contracts that do not
 // qualify (calls, European, r <= q, band wider than 512 nodes) are left at status 2 and priced
 // by the full-width kernel in a second launch.
 constexpr int kBandWarps = 4;
 constexpr int kBandMaxB = 16;
 constexpr int kBandTile = 32 * kBandMaxB + 8;
+#ifndef OPTP_BAND_SEG
+#define OPTP_BAND_SEG 64
+#endif
+constexpr int kBandSeg = OPTP_BAND_SEG;  // levels per segment
 
 // one level for B nodes per lane; `nb` is the next lane's first node (0 above the window).
 // FLAGS: also return a bit mask of the nodes that chose exercise.
 template <int B, bool FLAGS>
 __device__ __forceinline__ unsigned int band_level(double (&v)[kBandMaxB], const UTab& U, double rho,
-                                                   double sbg, double sKg, double nb) {
+                                                   double sbg, double sKg, double nb, bool& ex0) {
     double sa[2];
     sa[0] = sbg;
 #pragma unroll
@@ -295,6 +299,7 @@ __device__ __forceinline__ unsigned int band_level(double (&v)[kBandMaxB], const
         for (int t = 0; t < G; ++t) {
             if (g0 + t < B) {
                 const bool ex = e[t] > c[t];
+                if (g0 + t == 0) ex0 = ex;
                 if (FLAGS) mask |= ex ? (1u << (g0 + t)) : 0u;
                 v[g0 + t] = ex ? e[t] : c[t];
             }
@@ -307,25 +312,36 @@ __device__ __forceinline__ unsigned int band_level(double (&v)[kBandMaxB], const
 // mask of the last level.  nlev <= L.R, so the scaled recursion cannot overflow.
 template <int B>
 __device__ __forceinline__ unsigned int band_segment(double (&v)[kBandMaxB], const UTab& U,
-                                                     const Lattice& L, int lane, int w0, int k_first,
-                                                     int nlev) {
-    double sbg = L.sgn * L.S0 * pow(L.u, (double)(2 * (w0 + lane * B) - (k_first + 1)));
+                                                     const Lattice& L, int lane, double sb, int nlev,
+                                                     bool& bottom_always_exercise) {
+    // sb = sgn*S0*u^(2*(w0 + lane*B) - k): this lane's first node one level above the segment
+    double sbg = sb;
     double sKg = L.sK, back = 1.0;
     double nb = __shfl_down_sync(0xffffffffu, v[0], 1);
     if (lane == 31) nb = 0.0;
     unsigned int mask = 0;
-    for (int t = 0; t < nlev; ++t) {
+    bool ex0 = true;
+    // the last level is peeled: it is the only one that records the full exercise mask
+#pragma unroll 1
+    for (int t = 0; t < nlev - 1; ++t) {
         sbg *= L.u_pd;
         sKg *= L.inv_pd;
         back *= L.pd;
-        if (t + 1 < nlev) {
-            band_level<B, false>(v, U, L.rho, sbg, sKg, nb);
-        } else {
-            mask = band_level<B, true>(v, U, L.rho, sbg, sKg, nb);
-        }
+        bool e0;
+        band_level<B, false>(v, U, L.rho, sbg, sKg, nb, e0);
+        ex0 = ex0 && e0;
         nb = __shfl_down_sync(0xffffffffu, v[0], 1);
         if (lane == 31) nb = 0.0;
     }
+    {
+        sbg *= L.u_pd;
+        sKg *= L.inv_pd;
+        back *= L.pd;
+        bool e0;
+        mask = band_level<B, true>(v, U, L.rho, sbg, sKg, nb, e0);
+        ex0 = ex0 && e0;
+    }
+    bottom_always_exercise = ex0;  // meaningful in lane 0: the window's bottom node, every level
 #pragma unroll
     for (int i = 0; i < B; ++i) v[i] *= back;
     return mask;
@@ -371,7 +387,7 @@ __device__ __forceinline__ int band_pick_B(int width) {
     return 16;
 }
 
-__global__ void __launch_bounds__(kBandWarps * 32, 3) crr_band_kernel(CrrArgs a) {
+__global__ void __launch_bounds__(kBandWarps * 32, 5) crr_band_kernel(CrrArgs a) {
     __shared__ double tiles[kBandWarps][kBandTile];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -408,16 +424,17 @@ __global__ void __launch_bounds__(kBandWarps * 32, 3) crr_band_kernel(CrrArgs a)
 #pragma unroll
             for (int i = 1; i < 4; ++i) U.hi[i] = U.hi[i - 1] * u16;
         }
-        const double thr = K * 8.0779356694631609e-28;  // 2^-90 K
+        const double thr = K * 8.2718061255302767e-25;  // 2^-80 K
+        const double ln_u = log(L.u);
         double v[kBandMaxB];
         // ---- level N: every node is closed form, max(K - S, 0) (binomial.py:20-25) ----------
         int B = 2, k = N;
         // index of the first out-of-the-money terminal node, S0*u^(2j-N) >= K
-        const double jz = 0.5 * ((double)N + log(K / L.S0) / log(L.u));
+        const double jz = 0.5 * ((double)N + log(K / L.S0) / ln_u);
         int w0 = (int)fmin(fmax(jz - 31.0, 0.0), (double)max(0, N + 1 - 64));
         unsigned int exmask = 0;
         {
-            const double sb = L.sgn * L.S0 * pow(L.u, (double)(2 * (w0 + lane * 2) - N));
+            const double sb = L.sgn * L.S0 * exp(ln_u * (double)(2 * (w0 + lane * 2) - N));
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const double e = fma(sb, U.lo[i], L.sK);
@@ -427,6 +444,7 @@ __global__ void __launch_bounds__(kBandWarps * 32, 3) crr_band_kernel(CrrArgs a)
         }
         bool fail = false;
         double price = 0.0;
+        int prev_drop = 0, prev_nlev = 0, jlo_seg_start = -1;
         while (true) {
             // ---- measure the band [jlo, jhi) of the level held in registers ------------------
             int first_cont = 0, last_live = -1;
@@ -447,13 +465,20 @@ __global__ void __launch_bounds__(kBandWarps * 32, 3) crr_band_kernel(CrrArgs a)
                 jhi = w0;
             }
             if (jhi < jlo) jhi = jlo;
+            if (jlo_seg_start >= 0) prev_drop = max(0, jlo_seg_start - jlo);
             // the window bottom must still be inside the exercise region (or be node 0)
             if (w0 > 0 && jlo <= w0) fail = true;
             if (k == 0 || fail) break;
             // ---- next segment: levels k-1 ... k-nlev ------------------------------------------
-            int nlev = min(32, min(L.R, k));
+            int nlev = min(kBandSeg, min(L.R, k));
             int top = min(jhi, k + 1);           // exclusive; node `top` of level k is 0 (or dead)
-            int bot = max(0, jlo - nlev - 2);
+            // margin below the boundary: rigorous (one node per level) for the first segment; later
+            // the boundary falls no faster than it did over the previous segment (it decelerates
+            // like sqrt(tau)), and the per-level bottom check catches any violation
+            int margin = nlev + 2;
+            if (prev_nlev > 0) margin = min(margin, (prev_drop * nlev + prev_nlev - 1) / prev_nlev + 6);
+            jlo_seg_start = jlo;
+            int bot = max(0, jlo - margin);
             if (top < bot + 1) top = bot + 1;
             const int Bn = band_pick_B(top - bot);
             if (top - bot > 32 * kBandMaxB) {
@@ -464,9 +489,10 @@ __global__ void __launch_bounds__(kBandWarps * 32, 3) crr_band_kernel(CrrArgs a)
             // ---- re-pack level k from (w0, B) to (w0n, Bn) -------------------------------------
             OPTP_BAND_SWITCH(B, band_store<BB>(v, tile, lane));
             __syncwarp();
+            // this lane's first node of the new layout at level k: sgn*S0*u^(2j - k), via exp()
+            const double sb = L.sgn * L.S0 * exp(ln_u * (double)(2 * (w0n + lane * Bn) - k));
             {
                 const int magic = (65536 + B - 1) / B;   // exact j / B for j < 2048
-                const double sb = L.sgn * L.S0 * pow(L.u, (double)(2 * (w0n + lane * Bn) - k));
                 const int width_old = 32 * B;
 #pragma unroll
                 for (int i = 0; i < kBandMaxB; ++i) {
@@ -489,8 +515,13 @@ __global__ void __launch_bounds__(kBandWarps * 32, 3) crr_band_kernel(CrrArgs a)
             __syncwarp();
             w0 = w0n;
             B = Bn;
-            OPTP_BAND_SWITCH(B, exmask = band_segment<BB>(v, U, L, lane, w0, k - 1, nlev));
+            bool bot_ok = true;
+            OPTP_BAND_SWITCH(B, exmask = band_segment<BB>(v, U, L, lane, sb, nlev, bot_ok));
+            // everything below the window is an exercise node only while the window's bottom node
+            // chose exercise at EVERY level (then the node below it has two exercise children)
+            if (w0 > 0 && !__shfl_sync(0xffffffffu, (int)bot_ok, 0)) fail = true;
             k -= nlev;
+            prev_nlev = nlev;
         }
         if (fail) {
             if (lane == 0) a.status[o] = 2;

@@ -125,6 +125,19 @@ int optp_shutdown(void) {
 
 uint64_t optp_launch_count(void) { return g_ctx.launches; }
 
+int optp_set_option(const char* key, long value) {
+    if (!key) return set_error(OPTP_E_ARG, "null option key");
+    if (!strcmp(key, "crr_band")) {
+        g_ctx.crr_no_band = (value == 0);
+        return 0;
+    }
+    if (!strcmp(key, "crr_band_only")) {
+        g_ctx.crr_band_only = (value != 0);
+        return 0;
+    }
+    return set_error(OPTP_E_ARG, "unknown option '%s'", key);
+}
+
 int optp_host_alloc(void** p, uint64_t bytes) {
     if (!p) return set_error(OPTP_E_ARG, "null pointer");
     OPTP_CUDA(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault));

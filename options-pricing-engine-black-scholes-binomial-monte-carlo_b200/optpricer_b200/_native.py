@@ -13,7 +13,7 @@ import threading
 import numpy as np
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "liboptp_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 NSTATS = 8
 MAX_PAYOFFS = 16
 
@@ -25,7 +25,7 @@ MODE_FP32_PHILOX, MODE_FP64_PHILOX, MODE_FP64_HOSTZ = 0, 1, 2
 
 EXPORTS = (
     "optp_abi_version", "optp_init", "optp_shutdown", "optp_last_error", "optp_device_count",
-    "optp_launch_count", "optp_host_alloc", "optp_host_free",
+    "optp_launch_count", "optp_set_option", "optp_host_alloc", "optp_host_free",
     "optp_mc_terminal", "optp_mc_terminal_dev", "optp_mc_path", "optp_mc_path_dev",
     "optp_sigma_table_upload", "optp_paths", "optp_payoff_from_paths",
     "optp_crr_batch", "optp_crr_batch_dev", "optp_microbench",
@@ -66,6 +66,7 @@ def _declare(lib):
     lib.optp_init.argtypes = [i]
     lib.optp_last_error.restype = C.c_char_p
     lib.optp_launch_count.restype = u64
+    lib.optp_set_option.argtypes = [C.c_char_p, C.c_long]
     lib.optp_host_alloc.argtypes = [C.POINTER(vp), u64]
     lib.optp_host_free.argtypes = [vp]
     term = [d, d, d, d, d, d, i, u64, i, i, i, u64, u64, vp, vp]
@@ -139,6 +140,10 @@ def shutdown():
     if _lib is not None:
         _lib.optp_shutdown()
     _device = None
+
+
+def set_option(key, value):
+    check(load().optp_set_option(key.encode(), int(value)), "optp_set_option")
 
 
 def launch_count():

@@ -182,6 +182,36 @@ def test_crr_ragged_sizes_against_oracle(op, N):
         assert np.all(np.isnan(got[~ok]))
 
 
+def test_crr_banded_kernel_equals_full_width_kernel(op):
+    """The banded American-put kernel (exercise-region / zero-region cuts) against the full-width
+    kernel on the same contracts, including the corners of parameter space: deep in / out of the
+    money, tiny and long maturities, low and high volatility, q > 0, r <= q (declined -> fallback)."""
+    from optpricer_b200 import _native as nv
+    g = np.random.default_rng(99)
+    n = 30_000
+    S0 = g.uniform(20, 300, n); K = S0 * np.exp(g.uniform(-1.2, 1.2, n)); T = np.exp(g.uniform(np.log(0.01), np.log(5.0), n))
+    sig = g.uniform(0.05, 0.9, n); r = g.uniform(0.0005, 0.12, n); q = np.where(g.random(n) < 0.5, 0.0, g.uniform(0.0, 0.1, n))
+    is_call = (g.random(n) < 0.2).astype(np.uint8)
+    for N in (1000, 257, 64, 5):
+        banded, st_b = op.crr_batch(S0, K, T, r, q, sig, is_call, N, american=True, return_status=True)
+        nv.set_option("crr_band", 0)
+        try:
+            full, st_f = op.crr_batch(S0, K, T, r, q, sig, is_call, N, american=True, return_status=True)
+        finally:
+            nv.set_option("crr_band", 1)
+        np.testing.assert_array_equal(st_b, st_f)
+        ok = st_f == 0
+        np.testing.assert_allclose(banded[ok], full[ok], rtol=REL_CRR, atol=REL_CRR)
+    # how much of a typical book the banded kernel actually takes (config-2 contracts: all of it)
+    S0, K, T, r, q, sig, is_call = crr_tree.cfg2_contracts(20_000)
+    nv.set_option("crr_band_only", 1)
+    try:
+        _, st = op.crr_batch(S0, K, T, r, q, sig, is_call, 1000, american=True, return_status=True)
+    finally:
+        nv.set_option("crr_band_only", 0)
+    assert np.count_nonzero(st == 2) == 0
+
+
 def test_crr_batch_flags_bad_contracts_without_aborting(op):
     S0 = np.array([100.0, 100.0, 100.0]); K = np.array([100.0, 100.0, 90.0])
     T = np.array([1.0, 2.0, 1.0]); r = np.array([0.05, 0.30, 0.05]); q = np.zeros(3)
