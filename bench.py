@@ -452,6 +452,25 @@ def main():
                           "value": rate, "unit": "path-steps/s/GPU", "ms": ms,
                           "fp32_pipe_frac": rate * OPS_PER_PATH_STEP["terminal"] / peaks["fp32_ffma_lane_ops"],
                           "price": pt[0], "stderr": pt[1]})
+        # cfg 5: 10k-contract book (1/3 European, 1/3 barrier, 1/3 arithmetic Asian) through price_book;
+        # bounded to 2^18 base paths per contract here (BASELINE: 1e7); paths shard over the ranks
+        from optpricer_b200 import book as bk
+        n_rows, book_paths = 10_000, 1 << 18
+        rows = bk.synthetic_book(n_rows, n_paths=book_paths)
+        bk.price_book(rows[:200], mc_paths=book_paths)
+        barrier()
+        t0 = time.perf_counter()
+        priced = bk.price_book(rows, mc_paths=book_paths)
+        barrier()
+        book_s = max_over_ranks(time.perf_counter() - t0)
+        steps_of = lambda r: 1 if r["method"] == "mc" else r["n_steps"]  # noqa: E731
+        book_path_steps = sum(2.0 * book_paths * steps_of(r) for r in rows)
+        workloads.append({"workload": "cfg5 book: 10k contracts (European / barrier / arithmetic Asian), price_book(), "
+                                      f"{2 * book_paths} effective paths each, 252 steps, sharded by paths over the ranks",
+                          "value": book_path_steps / book_s, "unit": "path-steps/s (all GPUs, end to end)",
+                          "contracts_per_s": n_rows / book_s, "seconds": book_s,
+                          "priced": sum(1 for r in priced if r.get("price") is not None),
+                          "checksum": float(sum(r["price"] for r in priced[:100]))})
         # cfg 1 as is: latency of one euro_price_mc call (200k paths) through the public API
         opt = __import__("optpricer_b200").OptionSpec(100.0, 110.0, 1.0, 0.03, 0.2)
         mc.euro_price_mc(opt, "call", n_paths=200_000, seed=1)

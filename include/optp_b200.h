@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OPTP_ABI_VERSION 4
+#define OPTP_ABI_VERSION 5
 
 /* argument errors */
 #define OPTP_E_ARG 1        /* bad scalar argument / null pointer            */
@@ -163,6 +163,28 @@ int optp_paths(const optp_process* proc, uint32_t n_steps, uint64_t n_base, int 
 int optp_payoff_from_paths(const double* paths, uint64_t n_rows, uint64_t n_cols,
                            const optp_payoff* payoff, double* payoff_out,
                            double stats_out[OPTP_NSTATS]);
+
+/* ---- book of Monte Carlo items ----------------------------------------------
+ * Replaces the serial row loop of scripts/price_book.py:139-145 for its "mc" and "exotic" rows
+ * (price_book.py:78-114): every item is one euro_price_mc call (terminal_only) or one
+ * <generator> + <payoff(s)> pair; all items are launched back to back on the context's stream
+ * and the statistics blocks come back in ONE device-to-host copy.
+ *   stats_out: for every item, in order, n_payoffs blocks of OPTP_NSTATS doubles
+ *   (terminal_only items: one block).  Local-vol processes are not accepted here (one sigma
+ *   table per context).  path_offset shards the base paths of an item across GPUs. */
+typedef struct optp_book_item {
+    int32_t terminal_only;  /* 1: optp_mc_terminal semantics, uses proc.{S0,r,q,T,sigma}, K, is_call */
+    int32_t n_payoffs;      /* payoffs[first_payoff .. first_payoff + n_payoffs), ignored if terminal_only */
+    uint32_t first_payoff;
+    uint32_t n_steps;
+    uint64_t n_base, seed, path_offset;
+    int32_t antithetic, mode;
+    int32_t is_call, reserved;
+    double K;
+    optp_process proc;
+} optp_book_item;
+int optp_mc_book(const optp_book_item* items, uint64_t n_items, const optp_payoff* payoffs,
+                 uint64_t n_payoffs_total, double* stats_out);
 
 /* ---- batched CRR binomial ---------------------------------------------------
  * Replaces crr (binomial.py:7-38) looped over a heterogeneous contract batch, and

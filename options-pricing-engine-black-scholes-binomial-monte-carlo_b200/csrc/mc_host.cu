@@ -242,6 +242,63 @@ int optp_mc_path(const optp_process* proc, const optp_payoff* payoffs, uint32_t 
     return 0;
 }
 
+// ------------------------------------------------------------------ book of items
+int optp_mc_book(const optp_book_item* items, uint64_t n_items, const optp_payoff* payoffs,
+                 uint64_t n_payoffs_total, double* stats_out) {
+    if (int e = require_ready()) return e;
+    if (n_items == 0) return 0;
+    if (!items || !stats_out) return set_error(OPTP_E_ARG, "null pointer argument");
+    Context& c = ctx();
+    OPTP_CUDA(cudaSetDevice(c.device));
+    // validate everything before the first launch, and size the statistics buffer
+    uint64_t n_blocks = 0;
+    for (uint64_t i = 0; i < n_items; ++i) {
+        const optp_book_item& it = items[i];
+        if (it.terminal_only) {
+            if (it.n_base == 0) return set_error(OPTP_E_ARG, "item %llu: n_base must be positive",
+                                                 (unsigned long long)i);
+            if (it.mode == OPTP_MODE_FP64_HOSTZ)
+                return set_error(OPTP_E_ARG, "item %llu: a book has no host normals", (unsigned long long)i);
+            n_blocks += 1;
+        } else {
+            if (is_lv(it.proc.kind))
+                return set_error(OPTP_E_KIND, "item %llu: local-vol processes are not accepted in a book",
+                                 (unsigned long long)i);
+            if (it.mode == OPTP_MODE_FP64_HOSTZ)
+                return set_error(OPTP_E_ARG, "item %llu: a book has no host normals", (unsigned long long)i);
+            if (int e = check_process(&it.proc, it.n_steps, it.n_base)) return e;
+            if (!payoffs || (uint64_t)it.first_payoff + (uint64_t)it.n_payoffs > n_payoffs_total)
+                return set_error(OPTP_E_ARG, "item %llu: payoff range out of bounds", (unsigned long long)i);
+            if (int e = check_payoffs(payoffs + it.first_payoff, (uint32_t)it.n_payoffs)) return e;
+            n_blocks += (uint64_t)it.n_payoffs;
+        }
+    }
+    const size_t bytes = sizeof(double) * OPTP_NSTATS * n_blocks;
+    if (int e = arena_reserve(c.out1, bytes)) return e;
+    double* stats_dev = (double*)c.out1.p;
+    uint64_t blk = 0;
+    for (uint64_t i = 0; i < n_items; ++i) {
+        const optp_book_item& it = items[i];
+        double* dst = stats_dev + blk * OPTP_NSTATS;
+        if (it.terminal_only) {
+            if (int e = optp_mc_terminal_dev(it.proc.S0, it.K, it.proc.T, it.proc.r, it.proc.q,
+                                             it.proc.sigma, it.is_call, it.n_base, it.antithetic, it.mode,
+                                             0, it.seed, it.path_offset, nullptr, dst, c.stream))
+                return e;
+            blk += 1;
+        } else {
+            if (int e = optp_mc_path_dev(&it.proc, payoffs + it.first_payoff, (uint32_t)it.n_payoffs,
+                                         it.n_steps, it.n_base, it.antithetic, it.mode, it.seed,
+                                         it.path_offset, nullptr, nullptr, nullptr, dst, c.stream))
+                return e;
+            blk += (uint64_t)it.n_payoffs;
+        }
+    }
+    OPTP_CUDA(cudaMemcpyAsync(stats_out, stats_dev, bytes, cudaMemcpyDeviceToHost, c.stream));
+    OPTP_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
 // ------------------------------------------------------------------ materialised paths
 int optp_paths(const optp_process* proc, uint32_t n_steps, uint64_t n_base, int antithetic, int mode,
                uint64_t seed, uint64_t path_offset, const double* z, double* paths_out,

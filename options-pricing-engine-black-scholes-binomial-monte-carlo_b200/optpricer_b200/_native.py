@@ -13,7 +13,7 @@ import threading
 import numpy as np
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "liboptp_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 NSTATS = 8
 MAX_PAYOFFS = 16
 
@@ -26,7 +26,7 @@ MODE_FP32_PHILOX, MODE_FP64_PHILOX, MODE_FP64_HOSTZ = 0, 1, 2
 EXPORTS = (
     "optp_abi_version", "optp_init", "optp_shutdown", "optp_last_error", "optp_device_count",
     "optp_launch_count", "optp_set_option", "optp_host_alloc", "optp_host_free",
-    "optp_mc_terminal", "optp_mc_terminal_dev", "optp_mc_path", "optp_mc_path_dev",
+    "optp_mc_terminal", "optp_mc_terminal_dev", "optp_mc_path", "optp_mc_path_dev", "optp_mc_book",
     "optp_sigma_table_upload", "optp_paths", "optp_payoff_from_paths",
     "optp_crr_batch", "optp_crr_batch_dev", "optp_microbench",
 )
@@ -52,6 +52,15 @@ class OptpPayoff(C.Structure):
                 ("payout", C.c_double), ("r_disc", C.c_double), ("T_disc", C.c_double)]
 
 
+class OptpBookItem(C.Structure):
+    _fields_ = [("terminal_only", C.c_int32), ("n_payoffs", C.c_int32),
+                ("first_payoff", C.c_uint32), ("n_steps", C.c_uint32),
+                ("n_base", C.c_uint64), ("seed", C.c_uint64), ("path_offset", C.c_uint64),
+                ("antithetic", C.c_int32), ("mode", C.c_int32),
+                ("is_call", C.c_int32), ("reserved", C.c_int32),
+                ("K", C.c_double), ("proc", OptpProcess)]
+
+
 _lock = threading.Lock()
 _lib = None
 _device = None
@@ -75,6 +84,7 @@ def _declare(lib):
     path = [C.POINTER(OptpProcess), C.POINTER(OptpPayoff), u32, u32, u64, i, i, u64, u64, vp, vp, vp, vp]
     lib.optp_mc_path.argtypes = path
     lib.optp_mc_path_dev.argtypes = path + [vp]
+    lib.optp_mc_book.argtypes = [C.POINTER(OptpBookItem), u64, C.POINTER(OptpPayoff), u64, vp]
     lib.optp_sigma_table_upload.argtypes = [vp, u32, u32]
     lib.optp_paths.argtypes = [C.POINTER(OptpProcess), u32, u64, i, i, u64, u64, vp, vp, vp]
     lib.optp_payoff_from_paths.argtypes = [vp, u64, u64, C.POINTER(OptpPayoff), vp, vp]

@@ -1,0 +1,230 @@
+"""Book pricing on the B200: the batched replacement of the serial row loop of the reference's
+scripts/price_book.py (:45-118 `_price_row`, :139-145 the loop).
+
+Rows use the reference's CSV schema (price_book.py:9-18): id,S0,K,T,r,sigma,q,kind,method and, for
+exotics, exotic_type,barrier,barrier_type,rebate,average_type,strike_type,payout,n_steps,n_paths,
+american.  Methods on the hot path:
+  binomial  all rows of one `american` flag become ONE optp_crr_batch call (reference: crr, N=500)
+  mc        euro_price_mc (reference: n_paths=100_000, seed=1)          -> one terminal-kernel item
+  exotic    gbm_paths(..., antithetic=True, seed=1) + one payoff pricer -> one fused path-kernel
+            item; rows that share (S0, r, q, sigma, T, n_steps, n_paths) -- the script seeds every
+            row with seed=1, i.e. common random numbers -- share ONE simulated path set and are
+            evaluated as several payoffs of the same launch (up to 16 per launch)
+All Monte Carlo items of the book are launched back to back by optp_mc_book and their statistics
+return in one device-to-host copy; with a torch.distributed process group the base paths of every
+item are sharded over the ranks and ONE all-reduce sums the whole book's statistics.
+`method == "bs"` rows are closed-form Black-Scholes (not a hot path; priced on the host so a mixed
+book still comes back complete).  As in the reference, a failing row yields
+{"id", "price": None, "error": str} and does not abort the book.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _native as nv
+from . import exotics as ex
+from . import monte_carlo as mc
+from .binomial import _check_lattice
+from .core import OptionSpec
+
+
+def _f(row, key, default=None):
+    v = row.get(key, default)
+    if v is None or (isinstance(v, str) and v.strip() == ""):
+        if default is None:
+            raise KeyError(key)
+        v = default
+    return float(v)
+
+
+def _s(row, key, default=""):
+    v = row.get(key, default)
+    return (default if v is None else str(v)).strip().lower()
+
+
+def _bs_price(S0, K, T, r, q, sigma, kind):
+    """Closed-form Black-Scholes with continuous yield (reference black_scholes_vec.py:37-60)."""
+    d1 = (math.log(S0 / K) + (r - q + 0.5 * sigma * sigma) * T) / (sigma * math.sqrt(T))
+    d2 = d1 - sigma * math.sqrt(T)
+    N = lambda x: 0.5 * math.erfc(-x / math.sqrt(2.0))  # noqa: E731
+    if kind == "call":
+        return S0 * math.exp(-q * T) * N(d1) - K * math.exp(-r * T) * N(d2)
+    if kind == "put":
+        return K * math.exp(-r * T) * N(-d2) - S0 * math.exp(-q * T) * N(-d1)
+    raise ValueError("kind must be 'call' or 'put'")
+
+
+def _exotic_spec(row, K, kind):
+    et = _s(row, "exotic_type")
+    if et == "barrier":
+        return ex.barrier_spec(K, kind, _f(row, "barrier"), _s(row, "barrier_type"), _f(row, "rebate", 0.0))
+    if et == "asian":
+        return ex.asian_spec(K, kind, _s(row, "average_type", "arithmetic"), _s(row, "strike_type", "fixed"))
+    if et == "digital":
+        return ex.digital_spec(K, kind, _f(row, "payout", 1.0))
+    if et == "lookback":
+        return ex.lookback_spec(kind, K, _s(row, "strike_type", "floating"))
+    raise ValueError(f"Unknown exotic_type: {et!r}")
+
+
+def plan_book(rows, *, tree_steps=500, mc_paths=100_000, exotic_steps=500, exotic_paths=100_000, seed=1):
+    """Parse rows into device work.  Returns (results, crr_groups, items) where `results` already
+    holds the host-priced / failed rows and the rest are filled in by price_book."""
+    results = [None] * len(rows)
+    crr_groups = {}      # american flag -> list of (row index, S0, K, T, r, q, sigma, is_call)
+    items = []           # dicts: kind "terminal" | "path", rows [(row index, payoff spec)], params
+    path_groups = {}     # (S0, r, q, sigma, T, n_steps, n_paths) -> item (<= 16 payoffs each)
+    for i, row in enumerate(rows):
+        rid = row.get("id", "")
+        try:
+            S0, K, T, r, sigma = (_f(row, k) for k in ("S0", "K", "T", "r", "sigma"))
+            q = _f(row, "q", 0.0)
+            kind, method = _s(row, "kind"), _s(row, "method")
+            if method == "bs":
+                results[i] = {"id": rid, "price": _bs_price(S0, K, T, r, q, sigma, kind), "stderr": None}
+            elif method == "binomial":
+                OptionSpec(S0=S0, K=K, T=T, r=r, sigma=sigma, q=q)
+                _check_lattice(T, r, q, sigma, tree_steps)
+                american = _s(row, "american", "false") == "true"
+                crr_groups.setdefault(american, []).append((i, S0, K, T, r, q, sigma, 1 if kind == "call" else 0))
+            elif method == "mc":
+                OptionSpec(S0=S0, K=K, T=T, r=r, sigma=sigma, q=q)
+                items.append(dict(kind="terminal", rows=[(i, None)], S0=S0, K=K, T=T, r=r, q=q, sigma=sigma,
+                                  is_call=mc._kind_flag(kind), n_base=int(mc_paths), seed=seed))
+            elif method == "exotic":
+                n_steps = int(_f(row, "n_steps", exotic_steps))
+                n_paths = int(_f(row, "n_paths", exotic_paths))
+                if n_steps <= 0 or n_paths <= 0:
+                    raise ValueError("n_steps and n_paths must be positive.")
+                spec = _exotic_spec(row, K, kind)
+                key = (S0, r, q, sigma, T, n_steps, n_paths)
+                it = path_groups.get(key)
+                if it is None or len(it["rows"]) >= nv.MAX_PAYOFFS:
+                    it = dict(kind="path", rows=[], S0=S0, r=r, q=q, sigma=sigma, T=T, n_steps=n_steps,
+                              n_base=n_paths, seed=seed)
+                    path_groups[key] = it
+                    items.append(it)
+                it["rows"].append((i, spec))
+            else:
+                raise ValueError(f"Unknown method: {method!r}")
+        except Exception as e:  # per-row failure, as scripts/price_book.py:139-145
+            results[i] = {"id": rid, "price": None, "error": str(e)}
+    return results, crr_groups, items
+
+
+def book_stats(items, *, mode="fp32", rank=0, world=1):
+    """Run all Monte Carlo items through optp_mc_book for this rank's share of the base paths.
+    Returns the (n_blocks, 8) statistics array (item order, payoff order inside an item)."""
+    from .distributed import shard_range
+    n_blocks = sum(len(it["rows"]) for it in items)
+    stats = np.zeros((n_blocks, nv.NSTATS), dtype=np.float64)
+    if not items:
+        return stats
+    lib = nv.init()
+    arr = (nv.OptpBookItem * len(items))()
+    specs = []
+    live = 0
+    for it in items:
+        lo, hi = shard_range(it["n_base"], rank, world)
+        a = arr[live]
+        if hi == lo:
+            it["_skip"] = True   # this rank has no paths of the item; its blocks stay zero
+            continue
+        it["_skip"] = False
+        live += 1
+        a.terminal_only = 1 if it["kind"] == "terminal" else 0
+        a.n_base, a.seed, a.path_offset = hi - lo, mc._seed64(it["seed"]), lo
+        a.antithetic, a.mode = 1, mc._MODES[mode]
+        a.proc.kind = nv.PROC_GBM
+        a.proc.S0, a.proc.r, a.proc.q, a.proc.T, a.proc.sigma = it["S0"], it["r"], it["q"], it["T"], it["sigma"]
+        if it["kind"] == "terminal":
+            a.K, a.is_call, a.n_steps, a.n_payoffs, a.first_payoff = it["K"], it["is_call"], 1, 1, 0
+        else:
+            a.n_steps, a.n_payoffs, a.first_payoff = it["n_steps"], len(it["rows"]), len(specs)
+            specs.extend((s, it["r"], it["T"]) for _, s in it["rows"])
+    pay = (nv.OptpPayoff * max(1, len(specs)))()
+    for j, (s, r, T) in enumerate(specs):
+        one = ex._native_payoffs([s], r, T)[0]
+        C.memmove(C.byref(pay[j]), C.byref(one), C.sizeof(nv.OptpPayoff))
+    live_blocks = sum(len(it["rows"]) for it in items if not it["_skip"])
+    out = np.zeros((live_blocks, nv.NSTATS), dtype=np.float64)
+    if live:
+        nv.check(lib.optp_mc_book(arr, live, pay, len(specs), nv.ptr(out)), "optp_mc_book")
+    src = dst = 0
+    for it in items:
+        n = len(it["rows"])
+        if not it["_skip"]:
+            stats[dst:dst + n] = out[src:src + n]
+            src += n
+        dst += n
+    return stats
+
+
+def price_book(rows, *, tree_steps=500, mc_paths=100_000, exotic_steps=500, exotic_paths=100_000, seed=1,
+               mode="fp32", control_variate=True, sharded=None):
+    """Price a portfolio (list of dict rows).  Returns one result dict per row, in row order:
+    {"id", "price", "stderr"} or {"id", "price": None, "error"}.
+
+    `sharded`: None = shard over the default torch.distributed process group when one is initialised.
+    `control_variate` applies to the "mc" rows only (euro_price_mc's default, monte_carlo.py:84)."""
+    from . import distributed as dd
+    from .binomial import crr_batch
+    results, crr_groups, items = plan_book(rows, tree_steps=tree_steps, mc_paths=mc_paths,
+                                           exotic_steps=exotic_steps, exotic_paths=exotic_paths, seed=seed)
+    rank, world = dd.world() if sharded in (None, True) else (0, 1)
+    # --- trees: one batch per american flag -----------------------------------------------------
+    for american, group in crr_groups.items():
+        cols = [np.array([g[c] for g in group], dtype=np.float64) for c in range(1, 8)]
+        if world > 1:
+            prices = dd.crr_batch(*cols, tree_steps, american=american)
+        else:
+            prices = crr_batch(*cols, tree_steps, american=american)
+        for g, p in zip(group, prices):
+            results[g[0]] = {"id": rows[g[0]].get("id", ""), "price": float(p), "stderr": None}
+    # --- Monte Carlo: every item in one optp_mc_book call, one all-reduce for the whole book -----
+    if items:
+        stats = book_stats(items, mode=mode, rank=rank, world=world)
+        if world > 1:
+            stats = dd.allreduce_sum(stats)
+        blk = 0
+        for it in items:
+            for (i, spec) in it["rows"]:
+                s = stats[blk]
+                blk += 1
+                if it["kind"] == "terminal":
+                    price, se = mc.estimator((int(s[0]), *s[1:6]), S0=it["S0"], q=it["q"], T=it["T"],
+                                             control_variate=control_variate)
+                else:
+                    price, se = ex.estimate(s)
+                results[i] = {"id": rows[i].get("id", ""), "price": price, "stderr": se}
+    return results
+
+
+def synthetic_book(n_rows, seed=5, *, exotic_steps=252, n_paths=5_000_000):
+    """BASELINE config 5: S0=100, K~U(80,120), T in {.25,.5,1,2}, r=.03, q=0,
+    sigma~U(.15,.45), call/put 50/50, one third European ("mc"), one third barrier (up-and-out /
+    down-and-out at B = S0*(1 +- U(.1,.4))), one third arithmetic Asian; n_paths base paths each."""
+    g = np.random.default_rng(seed)
+    rows = []
+    for i in range(n_rows):
+        K = float(g.uniform(80.0, 120.0))
+        T = float(g.choice([0.25, 0.5, 1.0, 2.0]))
+        sigma = float(g.uniform(0.15, 0.45))
+        kind = "call" if g.random() < 0.5 else "put"
+        typ = int(g.integers(0, 3))
+        row = dict(id=i, S0=100.0, K=K, T=T, r=0.03, sigma=sigma, q=0.0, kind=kind)
+        if typ == 0:
+            row.update(method="mc")
+        elif typ == 1:
+            up = g.random() < 0.5
+            B = 100.0 * (1.0 + float(g.uniform(0.1, 0.4))) if up else 100.0 * (1.0 - float(g.uniform(0.1, 0.4)))
+            row.update(method="exotic", exotic_type="barrier", barrier=B,
+                       barrier_type="up-and-out" if up else "down-and-out", n_steps=exotic_steps, n_paths=n_paths)
+        else:
+            row.update(method="exotic", exotic_type="asian", average_type="arithmetic", strike_type="fixed",
+                       n_steps=exotic_steps, n_paths=n_paths)
+        rows.append(row)
+    return rows

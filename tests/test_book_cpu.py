@@ -1,0 +1,65 @@
+"""Host-side logic of the book pricer (optpricer_b200.book): row parsing in the reference's CSV
+schema (scripts/price_book.py:9-18), grouping into device work, per-row failures."""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "options-pricing-engine-black-scholes-binomial-monte-carlo_b200"))
+
+from optpricer_b200 import book  # noqa: E402
+
+
+ROWS = [
+    dict(id="1", S0="100", K="110", T="0.5", r="0.05", sigma="0.20", q="0.0", kind="call", method="bs"),
+    dict(id="2", S0="100", K="95", T="1.0", r="0.05", sigma="0.25", q="0.01", kind="put", method="mc"),
+    dict(id="3", S0="100", K="105", T="0.5", r="0.05", sigma="0.20", q="0.0", kind="call", method="binomial"),
+    dict(id="4", S0="100", K="100", T="1.0", r="0.05", sigma="0.20", q="0.0", kind="call", method="exotic",
+         exotic_type="barrier", barrier="120", barrier_type="up-and-out"),
+    dict(id="5", S0="100", K="100", T="1.0", r="0.05", sigma="0.20", q="0.0", kind="put", method="exotic",
+         exotic_type="asian"),
+    dict(id="6", S0="100", K="100", T="1.0", r="0.05", sigma="0.20", q="0.0", kind="put", method="binomial",
+         american="true"),
+    dict(id="7", S0="100", K="100", T="1.0", r="0.05", sigma="0.20", kind="call", method="fem"),
+    dict(id="8", S0="-1", K="100", T="1.0", r="0.05", sigma="0.20", kind="call", method="mc"),
+    dict(id="9", S0="100", K="100", T="1.0", r="0.05", sigma="0.20", kind="call", method="exotic",
+         exotic_type="barrier", barrier="120", barrier_type="sideways"),
+    dict(id="10", S0="100", K="100", T="1.0", r="0.05", sigma="0.30", q="0.0", kind="call", method="exotic",
+         exotic_type="lookback", n_steps="50", n_paths="1000"),
+]
+
+
+def test_plan_groups_rows_and_keeps_failures():
+    results, crr_groups, items = book.plan_book(ROWS)
+    # closed-form row priced on the host (BS call 100/110/0.5/0.05/0.2 = 2.9057...)
+    assert results[0]["price"] == pytest.approx(2.9057, abs=2e-3)
+    # failures carry the reference's messages and do not abort the book
+    assert results[6] == {"id": "7", "price": None, "error": "Unknown method: 'fem'"}
+    assert results[7]["error"] == "S0 must be positive, got -1.0"
+    assert "barrier_type must be one of" in results[8]["error"]
+    assert sorted(crr_groups) == [False, True] and len(crr_groups[False]) == 1 and crr_groups[True][0][0] == 5
+    kinds = [(it["kind"], [r for r, _ in it["rows"]]) for it in items]
+    # rows 4 and 5 share (S0, r, q, sigma, T, n_steps, n_paths) -> ONE simulated path set, two payoffs
+    assert kinds == [("terminal", [1]), ("path", [3, 4]), ("path", [9])]
+    assert items[1]["n_steps"] == 500 and items[1]["n_base"] == 100_000 and items[2]["n_steps"] == 50
+    assert all(results[i] is None for i in (1, 2, 3, 4, 5, 9))
+
+
+def test_more_than_sixteen_payoffs_split_into_launches():
+    rows = [dict(id=i, S0=100, K=90 + i, T=1.0, r=0.05, sigma=0.2, kind="call", method="exotic", exotic_type="digital")
+            for i in range(40)]
+    _, _, items = book.plan_book(rows)
+    assert [len(it["rows"]) for it in items] == [16, 16, 8]
+
+
+def test_synthetic_book_composition():
+    rows = book.synthetic_book(3000, n_paths=1000)
+    methods = [r["method"] for r in rows]
+    assert 800 < methods.count("mc") < 1200
+    ex = [r for r in rows if r["method"] == "exotic"]
+    assert {r["exotic_type"] for r in ex} == {"barrier", "asian"}
+    for r in ex:
+        if r["exotic_type"] == "barrier":
+            assert (r["barrier"] > 100) == (r["barrier_type"] == "up-and-out")
+    assert rows == book.synthetic_book(3000, n_paths=1000)

@@ -478,3 +478,52 @@ def test_argument_errors_match_reference_texts(op):
         op.lookback_price(lp, 0.05, 1, "call", 0.0, "odd")
     assert lp.shape == (11, 20) and np.asarray(lp).shape == (11, 20)
     assert np.all(np.asarray(lp)[0] == 100.0)
+
+
+# ------------------------------------------------------------------------------ book pricing
+def test_price_book_equals_row_by_row_api(op):
+    """optp_mc_book (all items back to back, one copy) against the single-call public API on the same
+    Philox keys: identical statistics, hence identical prices; per-row failures do not abort."""
+    from optpricer_b200 import book, processes as pr
+    rows = [
+        dict(id="a", S0=100, K=110, T=0.5, r=0.05, sigma=0.20, q=0.0, kind="call", method="bs"),
+        dict(id="b", S0=100, K=95, T=1.0, r=0.05, sigma=0.25, q=0.01, kind="put", method="mc"),
+        dict(id="c", S0=100, K=105, T=0.5, r=0.05, sigma=0.20, q=0.0, kind="call", method="binomial"),
+        dict(id="d", S0=100, K=100, T=1.0, r=0.05, sigma=0.20, q=0.0, kind="call", method="exotic",
+             exotic_type="barrier", barrier=120, barrier_type="up-and-out", n_steps=100, n_paths=50_000),
+        dict(id="e", S0=100, K=100, T=1.0, r=0.05, sigma=0.20, q=0.0, kind="put", method="exotic",
+             exotic_type="asian", n_steps=100, n_paths=50_000),
+        dict(id="f", S0=100, K=100, T=1.0, r=0.05, sigma=0.20, q=0.0, kind="put", method="binomial", american="true"),
+        dict(id="g", S0=100, K=100, T=1.0, r=0.05, sigma=0.20, kind="call", method="fem"),
+        dict(id="h", S0=100, K=100, T=2.0, r=0.03, sigma=0.30, q=0.0, kind="call", method="exotic",
+             exotic_type="lookback", strike_type="fixed", n_steps=50, n_paths=20_000),
+        dict(id="i", S0=100, K=100, T=2.0, r=0.03, sigma=0.30, q=0.0, kind="call", method="exotic",
+             exotic_type="digital", payout=10.0, n_steps=50, n_paths=20_000),
+    ]
+    out = book.price_book(rows, mc_paths=200_000)
+    assert [r["id"] for r in out] == list("abcdefghi")
+    assert out[6]["price"] is None and "Unknown method" in out[6]["error"]
+    assert out[0]["price"] == pytest.approx(2.9057, abs=2e-3)
+    want_b = op.euro_price_mc(op.OptionSpec(100, 95, 1.0, 0.05, 0.25, 0.01), "put", n_paths=200_000, seed=1)
+    assert out[1]["price"] == pytest.approx(want_b[0], rel=1e-12) and out[1]["stderr"] == pytest.approx(want_b[1], rel=1e-9)
+    assert out[2]["price"] == pytest.approx(op.crr(op.OptionSpec(100, 105, 0.5, 0.05, 0.2), "call", 500), rel=1e-12)
+    assert out[5]["price"] == pytest.approx(op.crr(op.OptionSpec(100, 100, 1.0, 0.05, 0.2), "put", 500, american=True),
+                                            rel=1e-12)
+    lp = pr.gbm_paths(100, 0.05, 0.0, 0.2, 1.0, 100, 50_000, seed=1)
+    assert out[3]["price"] == pytest.approx(op.barrier_price(lp, 100, 0.05, 1.0, "call", 120, "up-and-out")[0], rel=1e-12)
+    assert out[4]["price"] == pytest.approx(op.asian_price(lp, 100, 0.05, 1.0, "put")[0], rel=1e-12)
+    lp2 = pr.gbm_paths(100, 0.03, 0.0, 0.3, 2.0, 50, 20_000, seed=1)
+    assert out[7]["price"] == pytest.approx(op.lookback_price(lp2, 0.03, 2.0, "call", 100, "fixed")[0], rel=1e-12)
+    assert out[8]["price"] == pytest.approx(op.digital_price(lp2, 100, 0.03, 2.0, "call", 10.0)[0], rel=1e-12)
+    assert out[8]["stderr"] == pytest.approx(op.digital_price(lp2, 100, 0.03, 2.0, "call", 10.0)[1], rel=1e-9)
+
+
+def test_synthetic_book_prices_are_sane(op):
+    from optpricer_b200 import book
+    rows = book.synthetic_book(300, n_paths=20_000, exotic_steps=64)
+    out = book.price_book(rows, mc_paths=20_000)
+    assert all(r["price"] is not None and r["price"] >= 0.0 for r in out)
+    for row, res in zip(rows, out):
+        if row["method"] == "mc":
+            bs = book._bs_price(row["S0"], row["K"], row["T"], row["r"], row["q"], row["sigma"], row["kind"])
+            assert abs(res["price"] - bs) <= 5 * res["stderr"] + 1e-3

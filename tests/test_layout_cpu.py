@@ -31,11 +31,11 @@ def header_symbols():
 def test_library_exports_every_declared_symbol(native):
     lib = native.load()
     declared = header_symbols()
-    assert len(declared) >= 18
+    assert len(declared) >= 20
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/optp_b200.h but not exported"
     assert sorted(native.EXPORTS) == declared
-    assert lib.optp_abi_version() == native.ABI_VERSION == 4
+    assert lib.optp_abi_version() == native.ABI_VERSION == 5
 
 
 def test_struct_layout_matches_header(native, tmp_path):
