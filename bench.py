@@ -422,6 +422,16 @@ def main():
                           "n_paths_effective": 2 * nb, "value": rate, "unit": "path-steps/s/GPU", "ms": ms,
                           "fp32_pipe_frac": rate * OPS_PER_PATH_STEP["heston_asian"] / peaks["fp32_ffma_lane_ops"],
                           "price": pcv[0], "stderr": pcv[1]})
+        # cfg 4, QE variant (no reference code -- parity unpinned, checked against oracle/heston_qe):
+        # the scheme is meant for coarse grids, 32 steps here
+        hq = nv.OptpProcess()
+        C.memmove(C.byref(hq), C.byref(hp), C.sizeof(nv.OptpProcess))
+        hq.kind = nv.PROC_HESTON_QE
+        rate, ms, s = path_rate(hq, [ex.asian_spec(100.0, "call")], 32, nb, 0.05, 1.0)
+        pq = ex.estimate(s[0], control_variate=True, expected_y=100.0)
+        workloads.append({"workload": "cfg4 variant: Heston QE (Andersen 2008) 32 steps, arithmetic Asian call, antithetic+CV",
+                          "n_paths_effective": 2 * nb, "value": rate, "unit": "path-steps/s/GPU", "ms": ms,
+                          "price": pq[0], "stderr": pq[1], "parity": "unpinned (no reference implementation)"})
         # cfg 3: LV Milstein on the Dupire table, 252 steps, up-and-out barrier call
         tab_file = os.path.join(ROOT, "tests", "golden", "dupire_table_252x256.npz")
         if os.path.exists(tab_file):

@@ -40,7 +40,7 @@ extern "C" {
 #define OPTP_PROC_LV_EULER 3     /* local_vol_paths           processes.py:223-258 */
 #define OPTP_PROC_GBM_MILSTEIN 4 /* gbm_milstein_paths        processes.py:264-305 */
 #define OPTP_PROC_SABR 5         /* sabr_paths                processes.py:168-217 */
-#define OPTP_PROC_HESTON_QE 6    /* Andersen QE -- no reference code, parity unpinned */
+#define OPTP_PROC_HESTON_QE 6    /* Andersen (2008) QE -- no reference code, parity unpinned */
 
 /* ---- payoff kinds (reference exotics.py) ---------------------------------- */
 #define OPTP_PAY_VANILLA 0   /* vanilla leg of barrier_price  exotics.py:83-88   */

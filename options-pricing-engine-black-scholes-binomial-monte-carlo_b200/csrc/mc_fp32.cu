@@ -234,6 +234,8 @@ struct StepConst {
     float rho, rhoc, h_sdt2, h_mhalf2, h_rq2, h_c1, h_kt, h_xs;
     // GBM Milstein (linear)
     float m_c1, m_ssdt, m_hs2dt;
+    // Heston QE (Andersen 2008); x in log2 units
+    float q_theta, q_E, q_c1, q_c2, q_K0, q_K1, q_K2, q_K3;
 };
 
 // one time step of a base path and its mirror, per process
@@ -266,6 +268,37 @@ __device__ __forceinline__ void heston_step(LogState& p, LogState& m, float& vp,
         vm = fmaxf(fmaf(-(sq * z0), k.h_xs, fmaf(vm, k.h_c1, k.h_kt)), 0.f);
         observe_log<MASK>(m);
     }
+}
+
+// Heston quadratic-exponential step of ONE path (no reference code: Andersen 2008, see
+// oracle/path_schemes.py:heston_qe).  psi <= 1.5  <=>  tt = 2 m^2 / s^2 >= 4/3.
+template <int MASK>
+__device__ __forceinline__ void heston_qe_one(LogState& s, float& v, float z0, float z1,
+                                              const StepConst& k) {
+    const float m = fmaf(v - k.q_theta, k.q_E, k.q_theta);
+    const float s2 = fmaf(v, k.q_c1, k.q_c2);
+    float inv_s2;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_s2) : "f"(s2));
+    const float m2 = m * m;
+    const float tt = (m2 + m2) * inv_s2;
+    float vn;
+    if (tt >= 1.3333334f) {
+        const float r1 = mufu_sqrt(fmaf(tt, tt, -tt));
+        const float b2 = (tt - 1.0f) + r1;
+        float inv_1b2;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_1b2) : "f"(1.0f + b2));
+        const float bz = mufu_sqrt(b2) + z0;
+        vn = (m * inv_1b2) * (bz * bz);
+    } else {  // exponential branch (small variance): rare, full-precision library calls
+        const float psi = 2.0f / tt;
+        const float p = (psi - 1.0f) / (psi + 1.0f);
+        const float u = normcdff(z0), omu = normcdff(-z0);
+        vn = (u <= p) ? 0.0f : logf((1.0f - p) / omu) * m / (1.0f - p);
+    }
+    const float vol = mufu_sqrt(fmaxf(k.q_K3 * (v + vn), 0.0f));
+    s.x = fmaf(vol, z1, fmaf(k.q_K2, vn, fmaf(k.q_K1, v, s.x + k.q_K0)));
+    v = vn;
+    observe_log<MASK>(s);
 }
 
 template <int MASK, bool ANTI>
@@ -304,6 +337,17 @@ __global__ void __launch_bounds__(256, 5) path_fp32_kernel(PathArgs a) {
     k.h_c1 = (float)(1.0 - a.kappa * dt);
     k.h_kt = (float)(a.kappa * a.theta * dt);
     k.h_xs = (float)(a.xi * sdt);
+    if (PROC == OPTP_PROC_HESTON_QE) {
+        const double E = exp(-a.kappa * dt);
+        k.q_theta = (float)a.theta;
+        k.q_E = (float)E;
+        k.q_c1 = (float)(a.xi * a.xi * E * (1.0 - E) / a.kappa);
+        k.q_c2 = (float)(a.theta * a.xi * a.xi * (1.0 - E) * (1.0 - E) / (2.0 * a.kappa));
+        k.q_K0 = (float)(((a.r - a.q) * dt - a.rho * a.kappa * a.theta * dt / a.xi) * L2E);
+        k.q_K1 = (float)((0.5 * dt * (a.kappa * a.rho / a.xi - 0.5) - a.rho / a.xi) * L2E);
+        k.q_K2 = (float)((0.5 * dt * (a.kappa * a.rho / a.xi - 0.5) + a.rho / a.xi) * L2E);
+        k.q_K3 = (float)(0.5 * dt * (1.0 - a.rho * a.rho) * L2E * L2E);
+    }
     k.m_c1 = (float)((a.r - a.q) * dt - 0.5 * a.sigma * a.sigma * dt);
     k.m_ssdt = (float)(a.sigma * sdt);
     k.m_hs2dt = (float)(0.5 * a.sigma * a.sigma * dt);
@@ -311,7 +355,7 @@ __global__ void __launch_bounds__(256, 5) path_fp32_kernel(PathArgs a) {
     const float inv_n = (float)(1.0 / (double)n_steps);
     const float df = (float)exp(-a.pay[0].r_disc * a.pay[0].T_disc);
     const unsigned long long n_eff = ANTI ? 2 * a.n_base : a.n_base;
-    constexpr int kDims = (PROC == OPTP_PROC_HESTON_FTE) ? 2 : 1;
+    constexpr int kDims = (PROC == OPTP_PROC_HESTON_FTE || PROC == OPTP_PROC_HESTON_QE) ? 2 : 1;
     constexpr int kPerCall = 4 / kDims;  // steps served by one Philox call
     const unsigned int n_full = n_steps / kPerCall, n_tail = n_steps % kPerCall;
 
@@ -353,6 +397,28 @@ __global__ void __launch_bounds__(256, 5) path_fp32_kernel(PathArgs a) {
             if (n_tail) {
                 normals_from_words(w, z);
                 heston_step<MASK, ANTI>(p, m, vp, vm, z[0], z[1], k);
+            }
+            ep = finish_log<MASK>(p, S0, inv_n);
+            if (ANTI) em = finish_log<MASK>(m, S0, inv_n);
+        } else if (PROC == OPTP_PROC_HESTON_QE) {
+            LogState p, m;
+            float vp = fmaxf((float)a.v0, 0.f), vm = vp;
+            uint4 w = philox_words(a.seed, gpath, 0u, 0u);
+#pragma unroll 1
+            for (unsigned int c = 0; c < n_full; ++c) {
+                const uint4 wn = philox_words(a.seed, gpath, c + 1, 0u);
+                normals_from_words(w, z);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    heston_qe_one<MASK>(p, vp, z[2 * j], z[2 * j + 1], k);
+                    if (ANTI) heston_qe_one<MASK>(m, vm, -z[2 * j], -z[2 * j + 1], k);
+                }
+                w = wn;
+            }
+            if (n_tail) {
+                normals_from_words(w, z);
+                heston_qe_one<MASK>(p, vp, z[0], z[1], k);
+                if (ANTI) heston_qe_one<MASK>(m, vm, -z[0], -z[1], k);
             }
             ep = finish_log<MASK>(p, S0, inv_n);
             if (ANTI) em = finish_log<MASK>(m, S0, inv_n);
@@ -536,6 +602,7 @@ int launch_table_convert(const double* t64, float2* t32, unsigned int n_steps, i
 // ------------------------------------------------------------------ dispatch
 bool path_fp32_supported(int proc) {
     return proc == OPTP_PROC_GBM || proc == OPTP_PROC_HESTON_FTE || proc == OPTP_PROC_GBM_MILSTEIN ||
+           proc == OPTP_PROC_HESTON_QE ||
            proc == OPTP_PROC_LV_MILSTEIN || proc == OPTP_PROC_LV_EULER;
 }
 
@@ -619,6 +686,7 @@ int launch_path_fp32(const PathArgs& a, cudaStream_t st) {
     switch (a.proc) {
         case OPTP_PROC_GBM: return launch_mask<OPTP_PROC_GBM>(a, mask, st);
         case OPTP_PROC_HESTON_FTE: return launch_mask<OPTP_PROC_HESTON_FTE>(a, mask, st);
+        case OPTP_PROC_HESTON_QE: return launch_mask<OPTP_PROC_HESTON_QE>(a, mask, st);
         case OPTP_PROC_GBM_MILSTEIN: return launch_mask<OPTP_PROC_GBM_MILSTEIN>(a, mask, st);
         case OPTP_PROC_LV_MILSTEIN: return launch_mask<OPTP_PROC_LV_MILSTEIN>(a, mask, st);
         case OPTP_PROC_LV_EULER: return launch_mask<OPTP_PROC_LV_EULER>(a, mask, st);

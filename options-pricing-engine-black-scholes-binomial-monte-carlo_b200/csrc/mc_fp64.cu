@@ -119,7 +119,8 @@ __global__ void __launch_bounds__(128) path_fp64_kernel(PathArgs a) {
     double* acc = dyn;
     acc_zero(acc, n_vals);
 
-    constexpr int kDims = (PROC == OPTP_PROC_HESTON_FTE || PROC == OPTP_PROC_SABR) ? 2 : 1;
+    constexpr int kDims =
+        (PROC == OPTP_PROC_HESTON_FTE || PROC == OPTP_PROC_SABR || PROC == OPTP_PROC_HESTON_QE) ? 2 : 1;
     constexpr int kPerCall = 4 / kDims;
     const unsigned long long n_eff = a.anti ? 2 * a.n_base : a.n_base;
     const unsigned int n_steps = a.n_steps;
@@ -135,6 +136,14 @@ __global__ void __launch_bounds__(128) path_fp64_kernel(PathArgs a) {
     const double rhoc = sqrt(fmax(0.0, 1.0 - a.rho * a.rho));
     const double inv_h = 1.0 / a.h;
     const double rq = a.r - a.q;
+    // Heston QE constants (Andersen 2008, central discretisation gamma1 = gamma2 = 1/2)
+    const double qe_E = exp(-a.kappa * dt);
+    const double qe_c1 = a.xi * a.xi * qe_E * (1.0 - qe_E) / a.kappa;
+    const double qe_c2 = a.theta * a.xi * a.xi * ((1.0 - qe_E) * (1.0 - qe_E)) / (2.0 * a.kappa);
+    const double qe_K0 = -a.rho * a.kappa * a.theta * dt / a.xi;
+    const double qe_K1 = 0.5 * dt * (a.kappa * a.rho / a.xi - 0.5) - a.rho / a.xi;
+    const double qe_K2 = 0.5 * dt * (a.kappa * a.rho / a.xi - 0.5) + a.rho / a.xi;
+    const double qe_K3 = 0.5 * dt * (1.0 - a.rho * a.rho);
 
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c < n_eff;
@@ -144,7 +153,8 @@ __global__ void __launch_bounds__(128) path_fp64_kernel(PathArgs a) {
         const unsigned long long gpath = a.path_offset + b;
         double S = a.S0, logs = 0.0, clamps = 0.0;
         double v = 0.0;
-        if (PROC == OPTP_PROC_HESTON_FTE) v = fmax(a.v0, 0.0);  // processes.py:150
+        if (PROC == OPTP_PROC_HESTON_FTE || PROC == OPTP_PROC_HESTON_QE) v = fmax(a.v0, 0.0);  // processes.py:150
+        if (PROC == OPTP_PROC_HESTON_QE) logs = log(a.S0);
         if (PROC == OPTP_PROC_SABR) v = a.v0;                   // alpha0, processes.py:199
         double smax = S, smin = S, sumS = 0.0, sumLog = 0.0;
         if (a.paths_out) a.paths_out[c] = S;
@@ -172,6 +182,28 @@ __global__ void __launch_bounds__(128) path_fp64_kernel(PathArgs a) {
                 S = S * exp((rq - 0.5 * vp) * dt + sq * sdt * zc);
                 v = v + a.kappa * (a.theta - vp) * dt + a.xi * sq * sdt * z0;
                 v = fmax(v, 0.0);
+            } else if (PROC == OPTP_PROC_HESTON_QE) {
+                // Andersen (2008) QE, same expression order as oracle/path_schemes.py:heston_qe
+                const double m = a.theta + (v - a.theta) * qe_E;
+                const double s2 = v * qe_c1 + qe_c2;
+                const double psi = s2 / (m * m);
+                double vn;
+                if (psi <= 1.5) {
+                    const double tt = 2.0 / psi;
+                    const double b2 = fmax(tt - 1.0 + sqrt(tt) * sqrt(fmax(tt - 1.0, 0.0)), 0.0);
+                    const double aa = m / (1.0 + b2);
+                    const double bz = sqrt(b2) + z0;
+                    vn = aa * (bz * bz);
+                } else {
+                    const double p = (psi - 1.0) / (psi + 1.0);
+                    const double beta = (1.0 - p) / m;
+                    const double u = 0.5 * erfc(-z0 * 0.7071067811865476);
+                    const double omu = 0.5 * erfc(z0 * 0.7071067811865476);
+                    vn = (u <= p) ? 0.0 : log((1.0 - p) / omu) / beta;
+                }
+                logs = logs + rq * dt + qe_K0 + qe_K1 * v + qe_K2 * vn + sqrt(fmax(qe_K3 * (v + vn), 0.0)) * z1;
+                v = vn;
+                S = exp(logs);
             } else if (PROC == OPTP_PROC_LV_MILSTEIN) {
                 const double* row = a.table64 + (size_t)t * a.n_nodes;
                 double sig = table_sigma64(row, a.n_nodes, a.x0, inv_h, S, clamps);
@@ -256,6 +288,7 @@ int launch_path_fp64(const PathArgs& a, cudaStream_t st) {
     switch (a.proc) {
         case OPTP_PROC_GBM: return launch_one64<OPTP_PROC_GBM>(a, st);
         case OPTP_PROC_HESTON_FTE: return launch_one64<OPTP_PROC_HESTON_FTE>(a, st);
+        case OPTP_PROC_HESTON_QE: return launch_one64<OPTP_PROC_HESTON_QE>(a, st);
         case OPTP_PROC_LV_MILSTEIN: return launch_one64<OPTP_PROC_LV_MILSTEIN>(a, st);
         case OPTP_PROC_LV_EULER: return launch_one64<OPTP_PROC_LV_EULER>(a, st);
         case OPTP_PROC_GBM_MILSTEIN: return launch_one64<OPTP_PROC_GBM_MILSTEIN>(a, st);

@@ -30,6 +30,8 @@ static int check_process(const optp_process* pr, uint32_t n_steps, uint64_t n_ba
          pr->kind == OPTP_PROC_HESTON_QE) &&
         !(pr->rho >= -1.0 && pr->rho <= 1.0))
         return set_error(OPTP_E_ARG, "rho must be in [-1, 1].");
+    if (pr->kind == OPTP_PROC_HESTON_QE && !(pr->xi > 0.0 && pr->kappa > 0.0 && pr->theta > 0.0))
+        return set_error(OPTP_E_ARG, "the QE scheme needs xi > 0, kappa > 0 and theta > 0");
     if (pr->kind == OPTP_PROC_LV_MILSTEIN || pr->kind == OPTP_PROC_LV_EULER) {
         if (pr->n_nodes < 2 || !(pr->h > 0.0))
             return set_error(OPTP_E_ARG, "sigma table needs n_nodes >= 2 and h > 0");

@@ -165,12 +165,20 @@ def gbm_milstein_paths(S0, r, q, sigma, T, n_steps, n_paths, *, antithetic=True,
 
 
 def heston_paths(S0, r, q, v0, kappa, theta, xi, rho, T, n_steps, n_paths, *, antithetic=True,
-                 seed=None, return_variance=False, rng="philox", mode="fp32"):
-    """Heston, full-truncation Euler (processes.py:117-162).  return_variance=True materialises."""
+                 seed=None, return_variance=False, rng="philox", mode="fp32", scheme="fte"):
+    """Heston paths (processes.py:117-162).  return_variance=True materialises.
+    scheme="fte": the reference's full-truncation Euler (default, drop-in).
+    scheme="qe":  Andersen's quadratic-exponential scheme -- NEW, the reference has no such code
+                  (parity unpinned; checked against oracle/path_schemes.py:heston_qe)."""
     _check_sizes(n_steps, n_paths)
     if not (-1.0 <= rho <= 1.0):
         raise ValueError("rho must be in [-1, 1].")
-    proc = dict(kind=nv.PROC_HESTON_FTE, S0=S0, r=r, q=q, T=T, v0=v0, kappa=kappa, theta=theta, xi=xi, rho=rho)
+    if scheme not in ("fte", "qe"):
+        raise ValueError("scheme must be 'fte' or 'qe'")
+    if scheme == "qe" and not (xi > 0 and kappa > 0 and theta > 0):
+        raise ValueError("the QE scheme needs xi > 0, kappa > 0 and theta > 0")
+    kind = nv.PROC_HESTON_FTE if scheme == "fte" else nv.PROC_HESTON_QE
+    proc = dict(kind=kind, S0=S0, r=r, q=q, T=T, v0=v0, kappa=kappa, theta=theta, xi=xi, rho=rho)
     lp = LazyPaths(proc, n_steps, n_paths, antithetic, seed, rng, mode)
     if return_variance:
         return lp.materialize(return_variance=True)

@@ -527,3 +527,47 @@ def test_synthetic_book_prices_are_sane(op):
         if row["method"] == "mc":
             bs = book._bs_price(row["S0"], row["K"], row["T"], row["r"], row["q"], row["sigma"], row["kind"])
             assert abs(res["price"] - bs) <= 5 * res["stderr"] + 1e-3
+
+
+# ------------------------------------------------------------------------------ Heston QE (unpinned scheme)
+QE_CASES = [dict(S0=100.0, r=0.05, q=0.0, v0=0.04, kappa=2.0, theta=0.04, xi=0.3, rho=-0.7, T=1.0),
+            dict(S0=100.0, r=0.02, q=0.01, v0=0.09, kappa=1.5, theta=0.04, xi=0.9, rho=-0.5, T=0.5)]
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_heston_qe_check_mode_matches_oracle(op, case):
+    """No reference code exists for QE; the fp64 kernel is checked against the numpy restatement of
+    Andersen (2008) on the same normals (case 1 violates Feller: the exponential branch is active)."""
+    from optpricer_b200 import exotics as ex, processes as pr
+    c = QE_CASES[case]
+    lp = pr.heston_paths(n_steps=24, n_paths=4000, seed=5, rng="numpy", scheme="qe", **c)
+    z2, zp = path_schemes.draw_normals(5, 24, 4000, 2)
+    ref, ref_v = path_schemes.heston_qe(z2, zp, return_variance=True, **c)
+    got, got_v = lp.materialize(return_variance=True)
+    np.testing.assert_allclose(got, ref, rtol=1e-11)
+    np.testing.assert_allclose(got_v, ref_v, rtol=1e-9, atol=1e-14)
+    if case == 1:
+        assert (ref_v == 0.0).any()          # the exponential branch produced exact zeros
+    specs = [ex.asian_spec(100.0, "call"), ex.barrier_spec(100.0, "put", 85.0, "down-and-in"), ex.vanilla_spec(100.0, "call")]
+    stats, pay, _ = ex.path_stats(lp, specs, c["r"], c["T"], want_payoffs=True)
+    np.testing.assert_allclose(pay[0], payoffs.asian_payoff(ref, 100.0, "call"), rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(pay[1], payoffs.barrier_payoff(ref, 100.0, "put", 85.0, "down-and-in"), rtol=1e-10, atol=1e-10)
+    want = payoffs.discounted_mean_se(payoffs.vanilla_payoff(ref, 100.0, "call"), c["r"], c["T"])
+    assert rel(ex.estimate(stats[2])[0], want[0]) <= 1e-11
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_heston_qe_production_kernel(op, case):
+    """fp32 QE kernel: tracks the fp64 kernel on the same Philox draws, and prices a vanilla call
+    within 4 SE (+ the scheme's discretisation bias allowance) of the semi-analytic Heston price."""
+    from optpricer_b200 import exotics as ex, processes as pr
+    from test_oracle_cpu import heston_call_semi_analytic
+    c = QE_CASES[case]
+    specs = [ex.vanilla_spec(100.0, "call"), ex.asian_spec(100.0, "call"), ex.lookback_spec("put")]
+    a = ex.price_payoffs(pr.heston_paths(n_steps=32, n_paths=400_000, seed=3, scheme="qe", mode="fp32", **c), specs, c["r"], c["T"])
+    b = ex.price_payoffs(pr.heston_paths(n_steps=32, n_paths=400_000, seed=3, scheme="qe", mode="fp64", **c), specs, c["r"], c["T"])
+    for (pa, sa), (pb, sb) in zip(a, b):
+        assert abs(pa - pb) <= 0.1 * sb, (pa, pb, sb)
+    exact = heston_call_semi_analytic(c["S0"], 100.0, c["T"], c["r"], c["q"], c["v0"], c["kappa"], c["theta"], c["xi"], c["rho"])
+    big = ex.price_payoffs(pr.heston_paths(n_steps=32, n_paths=4_000_000, seed=8, scheme="qe", **c), specs[:1], c["r"], c["T"])[0]
+    assert abs(big[0] - exact) <= 4.0 * big[1] + 0.02, (big, exact)

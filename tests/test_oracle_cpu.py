@@ -159,3 +159,44 @@ def test_cv_estimator_matches_terminal_estimator():
     a = payoffs.cv_estimator(st, 100.0)
     b = terminal_mc.estimator(st, S0=100.0, q=0.0, T=1.0, control_variate=True)
     assert a == pytest.approx(b, rel=1e-15)
+
+
+def heston_call_semi_analytic(S0, K, T, r, q, v0, kappa, theta, xi, rho):
+    """Heston (1993) call by numerical inversion of the characteristic function (Albrecher et al.
+    'little trap' form).  Independent yardstick for the QE oracle, which has no reference code."""
+    u = np.linspace(1e-8, 200.0, 200_001)
+    x = np.log(S0)
+
+    def cf(phi):
+        d = np.sqrt((rho * xi * 1j * phi - kappa) ** 2 + xi * xi * (1j * phi + phi * phi))
+        g = (kappa - rho * xi * 1j * phi - d) / (kappa - rho * xi * 1j * phi + d)
+        C = (r - q) * 1j * phi * T + kappa * theta / (xi * xi) * (
+            (kappa - rho * xi * 1j * phi - d) * T - 2.0 * np.log((1.0 - g * np.exp(-d * T)) / (1.0 - g)))
+        D = (kappa - rho * xi * 1j * phi - d) / (xi * xi) * (1.0 - np.exp(-d * T)) / (1.0 - g * np.exp(-d * T))
+        return np.exp(C + D * v0 + 1j * phi * x)
+
+    k = np.log(K)
+    f1 = np.real(np.exp(-1j * u * k) * cf(u - 1j) / (1j * u * cf(-1j)))
+    f2 = np.real(np.exp(-1j * u * k) * cf(u) / (1j * u))
+    P1 = 0.5 + np.trapezoid(f1, u) / np.pi
+    P2 = 0.5 + np.trapezoid(f2, u) / np.pi
+    return S0 * np.exp(-q * T) * P1 - K * np.exp(-r * T) * P2
+
+
+def test_heston_qe_oracle_against_semi_analytic_price():
+    """QE is 'parity unpinned' (no reference code); pin the restatement to the Heston closed form."""
+    cases = [dict(S0=100.0, r=0.05, q=0.0, v0=0.04, kappa=2.0, theta=0.04, xi=0.3, rho=-0.7, T=1.0),
+             dict(S0=100.0, r=0.02, q=0.01, v0=0.09, kappa=1.5, theta=0.04, xi=0.9, rho=-0.5, T=0.5)]
+    for c, n_steps in zip(cases, (16, 16)):
+        exact = heston_call_semi_analytic(c["S0"], 100.0, c["T"], c["r"], c["q"], c["v0"], c["kappa"], c["theta"],
+                                          c["xi"], c["rho"])
+        z2, zp = path_schemes.draw_normals(11, n_steps, 200_000, 2)
+        paths = path_schemes.heston_qe(z2, zp, **c)
+        price, se = payoffs.discounted_mean_se(payoffs.vanilla_payoff(paths, 100.0, "call"), c["r"], c["T"])
+        assert abs(price - exact) <= 4.0 * se + 0.02, (c, price, exact, se)
+        # discounted terminal price is a martingale up to the scheme's (small) drift bias
+        fwd = c["S0"] * np.exp((c["r"] - c["q"]) * c["T"])
+        assert abs(paths[-1].mean() - fwd) <= 4.0 * paths[-1].std() / np.sqrt(paths.shape[1]) + 0.05
+    # Black-Scholes limit of the closed form itself (xi -> 0): 10.4506 (reference tests/test_black_scholes.py:4-7)
+    bs = heston_call_semi_analytic(100.0, 100.0, 1.0, 0.05, 0.0, 0.04, 1.0, 0.04, 1e-4, 0.0)
+    assert abs(bs - 10.4506) < 2e-3
