@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OPTP_ABI_VERSION 5
+#define OPTP_ABI_VERSION 6
 
 /* argument errors */
 #define OPTP_E_ARG 1        /* bad scalar argument / null pointer            */
@@ -41,6 +41,7 @@ extern "C" {
 #define OPTP_PROC_GBM_MILSTEIN 4 /* gbm_milstein_paths        processes.py:264-305 */
 #define OPTP_PROC_SABR 5         /* sabr_paths                processes.py:168-217 */
 #define OPTP_PROC_HESTON_QE 6    /* Andersen (2008) QE -- no reference code, parity unpinned */
+#define OPTP_PROC_MERTON 7       /* merton_jump_paths         processes.py:62-111  */
 
 /* ---- payoff kinds (reference exotics.py) ---------------------------------- */
 #define OPTP_PAY_VANILLA 0   /* vanilla leg of barrier_price  exotics.py:83-88   */
@@ -67,7 +68,8 @@ typedef struct optp_process {
     int32_t n_nodes;   /* sigma table: nodes per row (LV_* only)                  */
     double S0, r, q, T;
     double sigma;                      /* GBM, GBM_MILSTEIN                          */
-    double v0, kappa, theta, xi, rho;  /* HESTON_*; SABR: v0=alpha0, xi=nu, kappa=beta */
+    double v0, kappa, theta, xi, rho;  /* HESTON_*; SABR: v0=alpha0, xi=nu, kappa=beta;
+                                          MERTON: v0=lam, kappa=mJ, theta=sJ           */
     double dS_bump;                    /* LV_MILSTEIN (processes.py:320)             */
     /* sigma(S,t) table, row i = step time i*T/n_steps (i < n_steps), n_nodes log-uniform
        nodes ln S = x0 + h*j; linear interpolation in ln S, flat outside.  The table is
@@ -131,7 +133,8 @@ int optp_mc_terminal_dev(double S0, double K, double T, double r, double q, doub
  *   n_payoffs payoffs are evaluated on the SAME simulated path set (price_book.py:80,92-93
  *   seeds every row alike, i.e. common random numbers); stats_out holds n_payoffs blocks.
  *   z (HOSTZ mode): n_streams consecutive (n_steps, n_base) C-order blocks, in the
- *   reference's draw order (GBM/LV: Z; Heston/SABR: Z2 then Zp -- processes.py:138-139).
+ *   reference's draw order (GBM/LV: Z; Heston/SABR: Z2 then Zp -- processes.py:138-139;
+ *   Merton: Z, then the Poisson counts K as doubles, then ZJ -- processes.py:89-93).
  *   payoff_out (optional, may be NULL): n_payoffs x n_eff undiscounted per-path payoffs,
  *   columns [0,n_base) base paths, [n_base,2n_base) antithetic mirrors (processes.py:49-50).
  *   terminal_out (optional): n_eff terminal prices S_T. */

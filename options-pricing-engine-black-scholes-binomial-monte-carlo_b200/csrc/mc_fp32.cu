@@ -236,6 +236,8 @@ struct StepConst {
     float m_c1, m_ssdt, m_hs2dt;
     // Heston QE (Andersen 2008); x in log2 units
     float q_theta, q_E, q_c1, q_c2, q_K0, q_K1, q_K2, q_K3;
+    // Merton jumps (log2 units): drift incl. compensator, mJ, sJ, mu = lam*dt, exp(-mu)
+    float j_drift2, j_m2, j_s2, j_mu, j_p0;
 };
 
 // one time step of a base path and its mirror, per process
@@ -348,6 +350,14 @@ __global__ void __launch_bounds__(256, 5) path_fp32_kernel(PathArgs a) {
         k.q_K2 = (float)((0.5 * dt * (a.kappa * a.rho / a.xi - 0.5) + a.rho / a.xi) * L2E);
         k.q_K3 = (float)(0.5 * dt * (1.0 - a.rho * a.rho) * L2E * L2E);
     }
+    if (PROC == OPTP_PROC_MERTON) {
+        const double kj = exp(a.kappa + 0.5 * a.theta * a.theta) - 1.0;
+        k.j_drift2 = (float)((a.r - a.q - 0.5 * a.sigma * a.sigma - a.v0 * kj) * dt * L2E);
+        k.j_m2 = (float)(a.kappa * L2E);
+        k.j_s2 = (float)(a.theta * L2E);
+        k.j_mu = (float)(a.v0 * dt);
+        k.j_p0 = (float)exp(-a.v0 * dt);
+    }
     k.m_c1 = (float)((a.r - a.q) * dt - 0.5 * a.sigma * a.sigma * dt);
     k.m_ssdt = (float)(a.sigma * sdt);
     k.m_hs2dt = (float)(0.5 * a.sigma * a.sigma * dt);
@@ -397,6 +407,33 @@ __global__ void __launch_bounds__(256, 5) path_fp32_kernel(PathArgs a) {
             if (n_tail) {
                 normals_from_words(w, z);
                 heston_step<MASK, ANTI>(p, m, vp, vm, z[0], z[1], k);
+            }
+            ep = finish_log<MASK>(p, S0, inv_n);
+            if (ANTI) em = finish_log<MASK>(m, S0, inv_n);
+        } else if (PROC == OPTP_PROC_MERTON) {
+            // one Philox call per step: (Z, ZJ) from one Box-Muller pair, the Poisson count from the
+            // third word; the mirror negates Z and ZJ and shares the count (processes.py:95-99)
+            LogState p, m;
+            uint4 w = philox_words(a.seed, gpath, 0u, 0u);
+#pragma unroll 1
+            for (unsigned int t = 0; t < n_steps; ++t) {
+                const uint4 wn = philox_words(a.seed, gpath, t + 1, 0u);
+                float z0, zj;
+                box_muller(w.x, w.y, z0, zj);
+                const float kj = poisson_inv(w.z, k.j_mu, k.j_p0);
+                const float dif = k.vol2 * z0;
+                float jm = 0.f, js = 0.f;
+                if (kj > 0.f) {
+                    jm = k.j_m2 * kj;
+                    js = k.j_s2 * mufu_sqrt(kj) * zj;
+                }
+                p.x += (k.j_drift2 + jm) + (dif + js);
+                observe_log<MASK>(p);
+                if (ANTI) {
+                    m.x += (k.j_drift2 + jm) - (dif + js);
+                    observe_log<MASK>(m);
+                }
+                w = wn;
             }
             ep = finish_log<MASK>(p, S0, inv_n);
             if (ANTI) em = finish_log<MASK>(m, S0, inv_n);
@@ -681,7 +718,7 @@ int launch_table_convert(const double* t64, float2* t32, unsigned int n_steps, i
 // ------------------------------------------------------------------ dispatch
 bool path_fp32_supported(int proc) {
     return proc == OPTP_PROC_GBM || proc == OPTP_PROC_HESTON_FTE || proc == OPTP_PROC_GBM_MILSTEIN ||
-           proc == OPTP_PROC_HESTON_QE ||
+           proc == OPTP_PROC_HESTON_QE || proc == OPTP_PROC_MERTON ||
            proc == OPTP_PROC_LV_MILSTEIN || proc == OPTP_PROC_LV_EULER;
 }
 
@@ -767,6 +804,7 @@ int launch_path_fp32(const PathArgs& a, cudaStream_t st) {
         case OPTP_PROC_GBM: return launch_mask<OPTP_PROC_GBM>(a, mask, st);
         case OPTP_PROC_HESTON_FTE: return launch_mask<OPTP_PROC_HESTON_FTE>(a, mask, st);
         case OPTP_PROC_HESTON_QE: return launch_mask<OPTP_PROC_HESTON_QE>(a, mask, st);
+        case OPTP_PROC_MERTON: return launch_mask<OPTP_PROC_MERTON>(a, mask, st);
         case OPTP_PROC_GBM_MILSTEIN: return launch_mask<OPTP_PROC_GBM_MILSTEIN>(a, mask, st);
         case OPTP_PROC_LV_MILSTEIN: return launch_mask<OPTP_PROC_LV_MILSTEIN>(a, mask, st);
         case OPTP_PROC_LV_EULER: return launch_mask<OPTP_PROC_LV_EULER>(a, mask, st);

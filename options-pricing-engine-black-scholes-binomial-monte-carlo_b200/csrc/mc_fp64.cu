@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(128) path_fp64_kernel(PathArgs a) {
 
     constexpr int kDims =
         (PROC == OPTP_PROC_HESTON_FTE || PROC == OPTP_PROC_SABR || PROC == OPTP_PROC_HESTON_QE) ? 2 : 1;
-    constexpr int kPerCall = 4 / kDims;
+    constexpr int kPerCall = (PROC == OPTP_PROC_MERTON) ? 1 : 4 / kDims;  // Merton: one call per step
     const unsigned long long n_eff = a.anti ? 2 * a.n_base : a.n_base;
     const unsigned int n_steps = a.n_steps;
     const double dt = a.T / (double)n_steps;
@@ -133,6 +133,9 @@ __global__ void __launch_bounds__(128) path_fp64_kernel(PathArgs a) {
     // per-process constants, same expression order as the reference
     const double gbm_drift = (a.r - a.q - 0.5 * a.sigma * a.sigma) * dt;
     const double gbm_vol = a.sigma * sdt;
+    // Merton: v0 = lam, kappa = mJ, theta = sJ; compensator kappa_J = exp(mJ + sJ^2/2) - 1 (processes.py:84-85)
+    const double mer_kj = exp(a.kappa + 0.5 * a.theta * a.theta) - 1.0;
+    const double mer_drift = (a.r - a.q - 0.5 * a.sigma * a.sigma - a.v0 * mer_kj) * dt;
     const double rhoc = sqrt(fmax(0.0, 1.0 - a.rho * a.rho));
     const double inv_h = 1.0 / a.h;
     const double rq = a.r - a.q;
@@ -161,8 +164,23 @@ __global__ void __launch_bounds__(128) path_fp64_kernel(PathArgs a) {
         if (a.var_out) a.var_out[c] = v;
         float zz[4] = {0.f, 0.f, 0.f, 0.f};
         for (unsigned int t = 0; t < n_steps; ++t) {
-            double z0, z1 = 0.0;
-            if (a.use_philox) {
+            double z0, z1 = 0.0, kj = 0.0;
+            if (PROC == OPTP_PROC_MERTON) {
+                // Z (mirrored), Poisson count (shared by the pair), ZJ (mirrored): processes.py:89-99
+                if (a.use_philox) {
+                    const uint4 w = philox_words(a.seed, gpath, t, 0u);
+                    float n0, n1;
+                    box_muller(w.x, w.y, n0, n1);
+                    z0 = sgn * (double)n0;
+                    z1 = sgn * (double)n1;
+                    kj = (double)poisson_inv(w.z, (float)(a.v0 * dt), (float)exp(-a.v0 * dt));
+                } else {
+                    const size_t o = (size_t)t * a.n_base + b;
+                    z0 = sgn * a.z[o];
+                    kj = a.z[zstream + o];
+                    z1 = sgn * a.z[2 * zstream + o];
+                }
+            } else if (a.use_philox) {
                 const unsigned int j = t % kPerCall;
                 if (j == 0) philox_normals4(a.seed, gpath, t / kPerCall, 0u, zz);
                 z0 = sgn * (double)zz[j * kDims];
@@ -172,7 +190,12 @@ __global__ void __launch_bounds__(128) path_fp64_kernel(PathArgs a) {
                 z0 = sgn * a.z[o];
                 if (kDims == 2) z1 = sgn * a.z[zstream + o];
             }
-            if (PROC == OPTP_PROC_GBM) {
+            if (PROC == OPTP_PROC_MERTON) {
+                // log increment = drift + vol*Z + (mJ*K + sJ*sqrt(K)*ZJ), processes.py:102-106
+                const double ysum = a.kappa * kj + a.theta * sqrt(kj) * z1;
+                logs += mer_drift + gbm_vol * z0 + ysum;
+                S = a.S0 * exp(logs);
+            } else if (PROC == OPTP_PROC_GBM) {
                 logs += gbm_drift + gbm_vol * z0;  // cumsum, processes.py:53
                 S = a.S0 * exp(logs);
             } else if (PROC == OPTP_PROC_HESTON_FTE) {
@@ -293,6 +316,7 @@ int launch_path_fp64(const PathArgs& a, cudaStream_t st) {
         case OPTP_PROC_LV_EULER: return launch_one64<OPTP_PROC_LV_EULER>(a, st);
         case OPTP_PROC_GBM_MILSTEIN: return launch_one64<OPTP_PROC_GBM_MILSTEIN>(a, st);
         case OPTP_PROC_SABR: return launch_one64<OPTP_PROC_SABR>(a, st);
+        case OPTP_PROC_MERTON: return launch_one64<OPTP_PROC_MERTON>(a, st);
         default: return set_error(OPTP_E_KIND, "process kind %d has no fp64 kernel", a.proc);
     }
 }

@@ -24,12 +24,14 @@ static int check_process(const optp_process* pr, uint32_t n_steps, uint64_t n_ba
     if (!pr) return set_error(OPTP_E_ARG, "null process");
     if (n_steps == 0 || n_base == 0)
         return set_error(OPTP_E_ARG, "n_steps and n_paths must be positive.");
-    if (pr->kind < OPTP_PROC_GBM || pr->kind > OPTP_PROC_HESTON_QE)
+    if (pr->kind < OPTP_PROC_GBM || pr->kind > OPTP_PROC_MERTON)
         return set_error(OPTP_E_KIND, "unknown process kind %d", pr->kind);
     if ((pr->kind == OPTP_PROC_HESTON_FTE || pr->kind == OPTP_PROC_SABR ||
          pr->kind == OPTP_PROC_HESTON_QE) &&
         !(pr->rho >= -1.0 && pr->rho <= 1.0))
         return set_error(OPTP_E_ARG, "rho must be in [-1, 1].");
+    if (pr->kind == OPTP_PROC_MERTON && (pr->v0 < 0.0 || pr->theta < 0.0))
+        return set_error(OPTP_E_ARG, "lam and sJ must be non-negative.");
     if (pr->kind == OPTP_PROC_HESTON_QE && !(pr->xi > 0.0 && pr->kappa > 0.0 && pr->theta > 0.0))
         return set_error(OPTP_E_ARG, "the QE scheme needs xi > 0, kappa > 0 and theta > 0");
     if (pr->kind == OPTP_PROC_LV_MILSTEIN || pr->kind == OPTP_PROC_LV_EULER) {

@@ -66,6 +66,7 @@ __host__ __device__ inline int observer_mask(const optp_payoff* p, int n) {
 }
 
 __host__ __device__ inline int n_streams_of(int proc) {
+    if (proc == OPTP_PROC_MERTON) return 3;
     return (proc == OPTP_PROC_HESTON_FTE || proc == OPTP_PROC_SABR || proc == OPTP_PROC_HESTON_QE) ? 2
                                                                                                   : 1;
 }

@@ -155,6 +155,19 @@ __device__ __forceinline__ void philox_normals4(uint64_t seed, uint64_t path, ui
     normals_from_words(philox_words(seed, path, block, stream), z);
 }
 
+// Poisson(mu) count by CDF inversion from one 32-bit word (mu = lambda*dt is small: the loop
+// almost always stops at k = 0).  p0 = exp(-mu).
+__device__ __forceinline__ float poisson_inv(uint32_t w, float mu, float p0) {
+    const float u = fmaf(__uint2float_rn(w), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    float k = 0.f, p = p0, c = p0;
+    while (u > c && k < 64.f) {
+        k += 1.f;
+        p *= mu / k;
+        c += p;
+    }
+    return k;
+}
+
 // ------------------------------------------------------------------ fp64 reductions
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -11,7 +11,7 @@ from .monte_carlo import euro_price_mc
 from .binomial import crr, crr_vec, crr_batch
 from .exotics import barrier_price, asian_price, digital_price, lookback_price, price_payoffs
 from .processes import (gbm_paths, heston_paths, milstein_local_vol_paths, local_vol_paths,
-                        gbm_milstein_paths, sabr_paths, SigmaTable, LazyPaths)
+                        gbm_milstein_paths, sabr_paths, merton_jump_paths, SigmaTable, LazyPaths)
 from ._native import NativeUnavailable
 
 __version__ = "0.1.0"
@@ -20,5 +20,5 @@ __all__ = [
     "OptionSpec", "CALL", "PUT", "euro_price_mc", "crr", "crr_vec", "crr_batch",
     "barrier_price", "asian_price", "digital_price", "lookback_price", "price_payoffs",
     "gbm_paths", "heston_paths", "milstein_local_vol_paths", "local_vol_paths",
-    "gbm_milstein_paths", "sabr_paths", "SigmaTable", "LazyPaths", "NativeUnavailable",
+    "gbm_milstein_paths", "sabr_paths", "merton_jump_paths", "SigmaTable", "LazyPaths", "NativeUnavailable",
 ]

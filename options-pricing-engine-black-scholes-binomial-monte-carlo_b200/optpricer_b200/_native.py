@@ -13,12 +13,13 @@ import threading
 import numpy as np
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "liboptp_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 NSTATS = 8
 MAX_PAYOFFS = 16
 
 # process kinds / payoff kinds / flags / modes -- mirror include/optp_b200.h
-PROC_GBM, PROC_HESTON_FTE, PROC_LV_MILSTEIN, PROC_LV_EULER, PROC_GBM_MILSTEIN, PROC_SABR, PROC_HESTON_QE = range(7)
+(PROC_GBM, PROC_HESTON_FTE, PROC_LV_MILSTEIN, PROC_LV_EULER, PROC_GBM_MILSTEIN, PROC_SABR, PROC_HESTON_QE,
+ PROC_MERTON) = range(8)
 PAY_VANILLA, PAY_DIGITAL, PAY_BARRIER, PAY_ASIAN, PAY_LOOKBACK = range(5)
 F_CALL, F_UP, F_IN, F_GEOMETRIC, F_FLOATING = 1, 2, 4, 8, 16
 MODE_FP32_PHILOX, MODE_FP64_PHILOX, MODE_FP64_HOSTZ = 0, 1, 2

@@ -13,6 +13,7 @@ use materialises the array through the fp64 kernel, so small-size code keeps wor
   local_vol_paths           <- processes.py:223-258
   gbm_milstein_paths        <- processes.py:264-305
   sabr_paths                <- processes.py:168-217   (fp64 kernels only)
+  merton_jump_paths         <- processes.py:62-111
 
 New optional keywords (defaults keep every call a drop-in):
   rng  = "philox"  counter-based Philox4x32-10 on the device (draw = f(seed, path, step))
@@ -95,6 +96,8 @@ class LazyPaths:
 
     # -- native descriptors ----------------------------------------------------------------
     def n_streams(self):
+        if self.proc["kind"] == nv.PROC_MERTON:
+            return 3
         return 2 if self.proc["kind"] in (nv.PROC_HESTON_FTE, nv.PROC_SABR, nv.PROC_HESTON_QE) else 1
 
     def native_process(self):
@@ -110,6 +113,12 @@ class LazyPaths:
     def host_normals(self):
         """The reference's draws: n_streams consecutive (n_steps, n_paths) blocks (Appendix B.3)."""
         g = np.random.default_rng(self.seed_arg)
+        if self.proc["kind"] == nv.PROC_MERTON:   # Z, Poisson counts, ZJ (processes.py:89-93)
+            shape = (self.n_steps, self.n_paths)
+            z = g.standard_normal(shape)
+            k = g.poisson(self.proc["v0"] * self.proc["T"] / self.n_steps, size=shape).astype(np.float64)
+            zj = g.standard_normal(size=shape)
+            return np.ascontiguousarray(np.stack([z, k, zj], axis=0))
         blocks = [g.standard_normal((self.n_steps, self.n_paths)) for _ in range(self.n_streams())]
         return np.ascontiguousarray(np.stack(blocks, axis=0))
 
@@ -197,6 +206,17 @@ def sabr_paths(S0, r, q, alpha0, beta, nu, rho, T, n_steps, n_paths, *, antithet
         raise ValueError("rho must be in [-1, 1].")
     proc = dict(kind=nv.PROC_SABR, S0=S0, r=r, q=q, T=T, v0=alpha0, kappa=beta, xi=nu, rho=rho)
     return LazyPaths(proc, n_steps, n_paths, antithetic, seed, rng, "fp64")
+
+
+def merton_jump_paths(S0, r, q, sigma, T, n_steps, n_paths, *, lam, mJ, sJ, antithetic=True, seed=None,
+                      rng="philox", mode="fp32"):
+    """Merton jump diffusion: exact GBM step + compound Poisson jump in log space (processes.py:62-111).
+    The antithetic mirror negates Z and ZJ and re-uses the Poisson counts, as the reference does."""
+    _check_sizes(n_steps, n_paths)
+    if lam < 0 or sJ < 0:
+        raise ValueError("lam and sJ must be non-negative.")
+    proc = dict(kind=nv.PROC_MERTON, S0=S0, r=r, q=q, T=T, sigma=sigma, v0=lam, kappa=mJ, theta=sJ)
+    return LazyPaths(proc, n_steps, n_paths, antithetic, seed, rng, mode)
 
 
 def _table_for(sigma_loc, S0, T, n_steps, sigma_grid):

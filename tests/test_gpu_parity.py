@@ -278,6 +278,8 @@ def _lazy(op, meta, npz, rng, mode="fp64", seed=None, n_mult=1):
     if gen == "sabr":
         kw["mode"] = "fp64"
         return pr.sabr_paths(**a, **kw)
+    if gen == "merton":
+        return pr.merton_jump_paths(**a, **kw)
     tab = pr.SigmaTable(*_table(meta, npz))
     if gen == "lv_milstein":
         return pr.milstein_local_vol_paths(sigma_loc=tab, dS_bump=meta.get("dS_bump", 0.01), **a, **kw)
@@ -297,6 +299,9 @@ def _oracle_paths(meta, npz):
     if gen == "sabr":
         z2, zp = path_schemes.draw_normals(seed, n_steps, n_paths, 2)
         return path_schemes.sabr_lognormal_vol(z2, zp, antithetic=anti, **a)
+    if gen == "merton":
+        z, k, zj = path_schemes.merton_draws(seed, n_steps, n_paths, a["lam"], a["T"])
+        return path_schemes.merton_jumps(z, k, zj, antithetic=anti, **a)
     (z,) = path_schemes.draw_normals(seed, n_steps, n_paths)
     if gen == "gbm_milstein":
         return path_schemes.gbm_milstein(z, antithetic=anti, **a)
@@ -308,7 +313,7 @@ def _oracle_paths(meta, npz):
 
 SMALL = ["gbm_small_anti1", "gbm_small_anti0", "heston_small_anti1", "heston_small_anti0", "heston_trunc",
          "lvm_const", "lvm_table_anti1", "lvm_table_anti0", "lvm_table_bump3", "lv_euler_table",
-         "gbm_milstein", "sabr_beta1.0", "sabr_beta0.5"]
+         "gbm_milstein", "sabr_beta1.0", "sabr_beta0.5", "merton"]
 
 
 @pytest.mark.parametrize("tag", SMALL)
@@ -369,7 +374,7 @@ def test_check_mode_reference_test_fixtures(op, tag):
 
 
 @pytest.mark.parametrize("tag", BIG + ["gbm_small_anti0", "heston_small_anti0", "lvm_table_anti0", "lv_euler_table",
-                                       "gbm_milstein"])
+                                       "gbm_milstein", "merton"])
 @pytest.mark.parametrize("mode", ["fp32", "fp64"])
 def test_philox_within_three_reference_se(op, tag, mode):
     from optpricer_b200 import exotics as ex
@@ -391,7 +396,7 @@ def test_philox_within_three_reference_se(op, tag, mode):
                 assert 0.85 < 4.0 * se / ref_se < 1.18, (tag, k, se, ref_se)
 
 
-@pytest.mark.parametrize("gen", ["gbm", "heston", "lvm", "lve", "gbmm"])
+@pytest.mark.parametrize("gen", ["gbm", "heston", "lvm", "lve", "gbmm", "merton"])
 def test_fp32_tracks_fp64_on_same_philox_draws(op, gen):
     """Production fp32 arithmetic vs the reference operation order in fp64, SAME device normals:
     the price difference must be a small fraction of the standard error."""
@@ -408,6 +413,8 @@ def test_fp32_tracks_fp64_on_same_philox_draws(op, gen):
             return pr.milstein_local_vol_paths(100.0, 0.05, 0.02, 1.0, 252, n, table, seed=11, mode=mode)
         if gen == "lve":
             return pr.local_vol_paths(100.0, 0.05, 0.02, 1.0, 252, n, table, seed=11, mode=mode)
+        if gen == "merton":
+            return pr.merton_jump_paths(100.0, 0.05, 0.0, 0.2, 1.0, 100, n, lam=0.8, mJ=-0.1, sJ=0.15, seed=11, mode=mode)
         return pr.gbm_milstein_paths(100.0, 0.05, 0.0, 0.2, 1.0, 252, n, seed=11, mode=mode)
 
     specs = [ex.barrier_spec(100.0, "call", 130.0, "up-and-out"), ex.barrier_spec(100.0, "put", 85.0, "down-and-in"),
