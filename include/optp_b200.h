@@ -103,6 +103,8 @@ uint64_t optp_launch_count(void);
 /* Tuning / diagnostics switches (all default to the production setting):
  *   "crr_band"      1 = American puts with r > q go through the banded kernel (default), 0 = every
  *                   contract through the full-width kernels (A/B checks of the band cuts)
+ *   "lv_window"     1 = LV Milstein uses the one-load window table when the bump is smaller than a
+ *                   grid cell (default), 0 = always the three-lookup (value, slope) path
  *   "crr_band_only" 1 = skip the full-width fallback pass; contracts the banded kernel declined
  *                   keep status 2 (diagnostics only)
  * Returns OPTP_E_ARG for an unknown key. */

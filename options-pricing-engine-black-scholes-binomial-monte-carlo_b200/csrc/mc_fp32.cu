@@ -16,6 +16,8 @@
 // The Philox counter layout (path, step block, stream) is the same one mc_fp64.cu uses in
 // FP64_PHILOX mode, so both modes see the same normals and differ only in arithmetic.
 #include <math.h>
+#include <stdlib.h>
+#include <type_traits>
 #include "mc_kernels.cuh"
 
 namespace optp {
@@ -528,9 +530,42 @@ __device__ __forceinline__ void lv_step(LinState& s, const float2* row, const Lv
     observe_lin<MASK>(s);
 }
 
+// Milstein step with the "window" table: node j holds (v_j, s_j, s_{j+1}, s_{j-1}) with
+// s_j = v_{j+1} - v_j, so ONE LDS.128 serves sigma(S), sigma(S(1+b)) and sigma(S(1-b)) as long as
+// the bump is smaller than a cell (|c_up|, |c_dn| < 1): the bumped points are in the same cell or in
+// the neighbouring one.  Rows carry two replicated nodes on each side (flat extrapolation), pos is
+// clamped to [-1, n]; that reproduces the per-lookup clamping of the (value, slope) path exactly.
+template <int MASK, bool LDG = false>
+__device__ __forceinline__ void lvm_step_win(LinState& s, const float4* row, const LvConst& k, float zs,
+                                             float zzh, unsigned int& clamps) {
+    // Issue-cost model of sm_100a (profiles/r1_pipe_model.md): FFMA/FADD/FMNMX cost one issue
+    // cycle, FSETP/IADD/LOP3/LEA two.  The piecewise-linear evaluations are therefore written with
+    // min/max instead of compare + select, and the clamp counter costs one compare.
+    const float pos = fmaf(mufu_lg2(s.S), k.inv_h2, k.c0);
+    const float pc0 = fminf(fmaxf(pos, 0.0f), k.pos_max);
+    clamps += (pc0 != pos) ? 1u : 0u;                      // lookups outside the tabulated range
+    const float pc = fminf(fmaxf(pos, -1.0f), k.pos_max + 1.0f);
+    const float t = __fadd_rd(pc, 12582912.0f);           // floor(pc) + 1.5*2^23, one FADD.RM
+    const int j = __float_as_int(t) - 0x4B400000;         // floor(pc) in [-1, n]
+    const float f = pc - (t - 12582912.0f);               // fraction in [0, 1)
+    const float4 e = LDG ? __ldg(row + j + 2) : row[j + 2];
+    float sig = fmaf(f, e.y, e.x);
+    // sigma at x + c_up (c_up in (0,1)):  v_j + min(tu,1) s_j + max(tu-1,0) s_{j+1}
+    const float tu = f + k.c_up;
+    const float sig_up = fmaf(fmaxf(tu - 1.0f, 0.0f), e.z, fmaf(fminf(tu, 1.0f), e.y, e.x));
+    // sigma at x + c_dn (c_dn in (-1,0)): v_j + max(td,0) s_j + min(td,0) s_{j-1}
+    const float td = f + k.c_dn;
+    const float sig_dn = fmaf(fminf(td, 0.0f), e.w, fmaf(fmaxf(td, 0.0f), e.y, e.x));
+    sig = fminf(fmaxf(sig, 1e-8f), 10.0f);
+    const float da = fmaf(sig_up, k.k_up, -(sig_dn * k.k_dn));
+    const float av = sig * s.S;
+    s.S = fmaxf(fmaf(av, fmaf(da, zzh, zs), fmaf(s.S, k.c1, s.S)), 1e-10f);
+    observe_lin<MASK>(s);
+}
+
 constexpr int kLvThreads = 256;
 #ifndef OPTP_LV_TMA
-#define OPTP_LV_TMA 0
+#define OPTP_LV_TMA 1
 #endif
 
 // ---- TMA bulk copy (cp.async.bulk -> SASS UBLKCP) + mbarrier helpers --------------------------
@@ -565,13 +600,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-template <int PROC, int MASK, bool ANTI>
-__global__ void __launch_bounds__(kLvThreads) lv_fp32_kernel(PathArgs a, int rows_per_chunk) {
+template <int PROC, int MASK, bool ANTI, bool WIN>
+__global__ void __launch_bounds__(kLvThreads, 4) lv_fp32_kernel(PathArgs a, int rows_per_chunk) {
+    using Node = typename std::conditional<WIN, float4, float2>::type;
     extern __shared__ double dyn[];
     __shared__ double blockvals[kMaxVals];
     const int n_vals = 3 + 3 * a.n_pay;
     double* acc = dyn;
-    float2* rows = reinterpret_cast<float2*>(dyn + (size_t)n_vals * kLvThreads);
+    Node* rows = reinterpret_cast<Node*>(dyn + (size_t)n_vals * kLvThreads);
+    const Node* table = WIN ? reinterpret_cast<const Node*>(a.table4) : reinterpret_cast<const Node*>(a.table32);
     acc_zero(acc, n_vals);
 
     const unsigned int n_steps = a.n_steps;
@@ -596,7 +633,8 @@ __global__ void __launch_bounds__(kLvThreads) lv_fp32_kernel(PathArgs a, int row
     const float inv_n = (float)(1.0 / (double)n_steps);
     const float df = (float)exp(-a.pay[0].r_disc * a.pay[0].T_disc);
     const unsigned long long n_eff = ANTI ? 2 * a.n_base : a.n_base;
-    const int n_ld = (a.n_nodes + 1) & ~1;  // padded row length of the fp32 table
+    // row length: (value, slope) table padded to an even node count; window table n + 4 nodes
+    const int n_ld = WIN ? a.n_nodes + 4 : ((a.n_nodes + 1) & ~1);
 
     // Staging of the table rows, selectable at compile time:
     //   OPTP_LV_TMA=0 (default; measured 8 % faster on B200, 448 vs 412 G path-steps/s on config 3):
@@ -607,7 +645,7 @@ __global__ void __launch_bounds__(kLvThreads) lv_fp32_kernel(PathArgs a, int row
     //     is (use count of b) & 1.
     __shared__ __align__(8) uint64_t full_bar[2];
     const unsigned int n_chunks = (n_steps + rows_per_chunk - 1) / rows_per_chunk;
-    const unsigned int row_bytes = (unsigned int)n_ld * (unsigned int)sizeof(float2);
+    const unsigned int row_bytes = (unsigned int)n_ld * (unsigned int)sizeof(Node);
     const unsigned int buf_elems = (unsigned int)rows_per_chunk * (unsigned int)n_ld;
     const unsigned long long n_slabs = (a.n_base + kLvThreads - 1) / kLvThreads;
     const unsigned long long my_slabs =
@@ -619,7 +657,7 @@ __global__ void __launch_bounds__(kLvThreads) lv_fp32_kernel(PathArgs a, int row
         const unsigned int nr = min((unsigned int)rows_per_chunk, n_steps - t0);
         uint64_t* bar = &full_bar[gc & 1];
         mbar_expect_tx(bar, nr * row_bytes);
-        bulk_g2s(rows + (size_t)(gc & 1) * buf_elems, a.table32 + (size_t)t0 * n_ld, nr * row_bytes, bar);
+        bulk_g2s(rows + (size_t)(gc & 1) * buf_elems, table + (size_t)t0 * n_ld, nr * row_bytes, bar);
     };
     if (OPTP_LV_TMA) {
         if (threadIdx.x == 0) {
@@ -647,14 +685,14 @@ __global__ void __launch_bounds__(kLvThreads) lv_fp32_kernel(PathArgs a, int row
         uint4 w = philox_words(a.seed, gpath, 0u, 0u);
         for (unsigned int t0 = 0; t0 < n_steps; t0 += rows_per_chunk, ++g) {
             const unsigned int nr = min((unsigned int)rows_per_chunk, n_steps - t0);
-            const float2* buf = rows + (OPTP_LV_TMA ? (size_t)(g & 1) * buf_elems : 0);
+            const Node* buf = rows + (OPTP_LV_TMA ? (size_t)(g & 1) * buf_elems : 0);
             if (OPTP_LV_TMA) {
                 mbar_wait(&full_bar[g & 1], (uint32_t)((g >> 1) & 1));
             } else {
                 __syncthreads();  // everyone is done with the previous chunk
-                const float4* src = reinterpret_cast<const float4*>(a.table32 + (size_t)t0 * n_ld);
+                const float4* src = reinterpret_cast<const float4*>(table + (size_t)t0 * n_ld);
                 float4* dst = reinterpret_cast<float4*>(rows);
-                const unsigned int n4 = nr * (unsigned int)n_ld / 2;
+                const unsigned int n4 = nr * row_bytes / 16u;
                 for (unsigned int i = threadIdx.x; i < n4; i += kLvThreads) dst[i] = __ldg(src + i);
                 __syncthreads();
             }
@@ -668,11 +706,16 @@ __global__ void __launch_bounds__(kLvThreads) lv_fp32_kernel(PathArgs a, int row
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         if (r + j < nr) {
-                            const float2* row = buf + (size_t)(r + j) * n_ld;
+                            const Node* row = buf + (size_t)(r + j) * n_ld;
                             const float zs = k.sdt * z[j];
                             const float zzh = k.hdt * fmaf(z[j], z[j], -1.0f);
-                            lv_step<PROC, MASK>(p, row, k, zs, zzh, z[j], clamps);
-                            if (ANTI) lv_step<PROC, MASK>(m, row, k, -zs, zzh, -z[j], clamps);
+                            if constexpr (WIN) {
+                                lvm_step_win<MASK>(p, row, k, zs, zzh, clamps);
+                                if (ANTI) lvm_step_win<MASK>(m, row, k, -zs, zzh, clamps);
+                            } else {
+                                lv_step<PROC, MASK>(p, row, k, zs, zzh, z[j], clamps);
+                                if (ANTI) lv_step<PROC, MASK>(m, row, k, -zs, zzh, -z[j], clamps);
+                            }
                         }
                     }
                 }
@@ -691,6 +734,97 @@ __global__ void __launch_bounds__(kLvThreads) lv_fp32_kernel(PathArgs a, int row
     reduce_and_emit(acc, blockvals, a.n_pay, (double)n_eff, a.partials, a.ticket, a.stats);
 }
 
+// Same Milstein step, but the window nodes are gathered straight from global memory through L1
+// (ld.global.nc): no shared-memory staging, hence no CTA-wide barrier every chunk and no chunk
+// copy on the critical path.  The rows in flight (all warps of an SM are within a few steps of each
+// other) are a few tens of KB and stay L1-resident; the 1 MB table stays L2-resident.
+template <int MASK, bool ANTI>
+__global__ void __launch_bounds__(256, 4) lvm_direct_kernel(PathArgs a) {
+    extern __shared__ double dyn[];
+    __shared__ double blockvals[kMaxVals];
+    double* acc = dyn;
+    acc_zero(acc, 3 + 3 * a.n_pay);
+    const unsigned int n_steps = a.n_steps;
+    const double dt = a.T / (double)n_steps;
+    constexpr double LN2 = 0.6931471805599453;
+    LvConst k;
+    k.inv_h2 = (float)(LN2 / a.h);
+    k.c0 = (float)(-a.x0 / a.h);
+    k.pos_max = (float)(a.n_nodes - 1);
+    k.c_up = (float)(log1p(a.bump) / a.h);
+    k.c_dn = (float)(log1p(-fmin(a.bump, 0.999999)) / a.h);
+    k.k_up = (float)((1.0 + a.bump) / (2.0 * a.bump));
+    k.k_dn = (float)((1.0 - a.bump) / (2.0 * a.bump));
+    k.c1 = (float)((a.r - a.q) * dt);
+    k.sdt = (float)sqrt(dt);
+    k.hdt = (float)(0.5 * dt);
+    const float S0 = (float)a.S0;
+    const float inv_n = (float)(1.0 / (double)n_steps);
+    const float df = (float)exp(-a.pay[0].r_disc * a.pay[0].T_disc);
+    const unsigned long long n_eff = ANTI ? 2 * a.n_base : a.n_base;
+    const int n_ld = a.n_nodes + 4;
+    const unsigned int n_full = n_steps >> 2, n_tail = n_steps & 3;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < a.n_base;
+         b += stride) {
+        const unsigned long long gpath = a.path_offset + b;
+        LinState p, m;
+        p.S = p.smax = p.smin = S0;
+        m = p;
+        unsigned int clamps = 0;
+        float z[4];
+        uint4 w = philox_words(a.seed, gpath, 0u, 0u);
+        const float4* row = a.table4;
+#pragma unroll 1
+        for (unsigned int c = 0; c < n_full; ++c) {
+            const uint4 wn = philox_words(a.seed, gpath, c + 1, 0u);
+            normals_from_words(w, z);
+            w = wn;
+#pragma unroll
+            for (int j = 0; j < 4; ++j, row += n_ld) {
+                const float zs = k.sdt * z[j];
+                const float zzh = k.hdt * fmaf(z[j], z[j], -1.0f);
+                lvm_step_win<MASK, true>(p, row, k, zs, zzh, clamps);
+                if (ANTI) lvm_step_win<MASK, true>(m, row, k, -zs, zzh, clamps);
+            }
+        }
+        if (n_tail) {
+            normals_from_words(w, z);
+            for (unsigned int j = 0; j < n_tail; ++j, row += n_ld) {
+                const float zs = k.sdt * z[j];
+                const float zzh = k.hdt * fmaf(z[j], z[j], -1.0f);
+                lvm_step_win<MASK, true>(p, row, k, zs, zzh, clamps);
+                if (ANTI) lvm_step_win<MASK, true>(m, row, k, -zs, zzh, clamps);
+            }
+        }
+        acc_add(acc, 2, (double)clamps);
+        path_epilogue(a, finish_lin<MASK>(p, inv_n), df, b, n_eff, acc);
+        if (ANTI) path_epilogue(a, finish_lin<MASK>(m, inv_n), df, a.n_base + b, n_eff, acc);
+    }
+    reduce_and_emit(acc, blockvals, a.n_pay, (double)n_eff, a.partials, a.ticket, a.stats);
+}
+
+template <int MASK, bool ANTI>
+static int launch_lvm_direct(const PathArgs& a, cudaStream_t st) {
+    const int threads = 256;
+    const size_t smem = sizeof(double) * (3 + 3 * a.n_pay) * threads;
+    auto kern = lvm_direct_kernel<MASK, ANTI>;
+    if (smem > 48 * 1024)
+        OPTP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+    if (per_sm < 1) per_sm = 1;
+    unsigned long long blocks = (a.n_base + threads - 1) / threads;
+    unsigned long long cap = (unsigned long long)ctx().n_sm * per_sm;
+    if (cap > kMaxBlocks) cap = kMaxBlocks;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    kern<<<(unsigned int)blocks, threads, smem, st>>>(a);
+    ctx().launches++;
+    OPTP_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // fp64 table -> (value, slope) fp32 pairs, rows padded to an even node count (16-byte rows)
 __global__ void table_convert_kernel(const double* t64, float2* t32, unsigned int n_steps,
                                      int n_nodes) {
@@ -707,10 +841,25 @@ __global__ void table_convert_kernel(const double* t64, float2* t32, unsigned in
     }
 }
 
-int launch_table_convert(const double* t64, float2* t32, unsigned int n_steps, int n_nodes,
+// fp64 table -> window nodes (v_j, s_j, s_{j+1}, s_{j-1}), j = -2 .. n+1 (edges replicated)
+__global__ void table_window_kernel(const double* t64, float4* t4, unsigned int n_steps, int n_nodes) {
+    const int n_ld = n_nodes + 4;
+    const size_t n = (size_t)n_steps * n_ld;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(i % n_ld) - 2;
+        const double* row = t64 + (i / n_ld) * (size_t)n_nodes;
+        auto V = [&](int q) { return row[min(max(q, 0), n_nodes - 1)]; };
+        t4[i] = make_float4((float)V(j), (float)(V(j + 1) - V(j)), (float)(V(j + 2) - V(j + 1)),
+                            (float)(V(j) - V(j - 1)));
+    }
+}
+
+int launch_table_convert(const double* t64, float2* t32, float4* t4, unsigned int n_steps, int n_nodes,
                          cudaStream_t st) {
     table_convert_kernel<<<64, 256, 0, st>>>(t64, t32, n_steps, n_nodes);
-    ctx().launches++;
+    table_window_kernel<<<64, 256, 0, st>>>(t64, t4, n_steps, n_nodes);
+    ctx().launches += 2;
     OPTP_CUDA(cudaGetLastError());
     return 0;
 }
@@ -744,13 +893,15 @@ static int launch_generic(const PathArgs& a, cudaStream_t st) {
     return 0;
 }
 
-template <int PROC, int MASK, bool ANTI>
-static int launch_lv(const PathArgs& a, cudaStream_t st) {
+template <int PROC, int MASK, bool ANTI, bool WIN>
+static int launch_lv_impl(const PathArgs& a, cudaStream_t st) {
     const size_t acc_bytes = sizeof(double) * (3 + 3 * a.n_pay) * kLvThreads;
-    const size_t row_bytes = sizeof(float2) * (size_t)((a.n_nodes + 1) & ~1);
-    // chunk of rows: a multiple of 4 (one Philox call = 4 steps): one 32 KB buffer, or two 16 KB
+    const size_t row_bytes = WIN ? sizeof(float4) * (size_t)(a.n_nodes + 4)
+                                 : sizeof(float2) * (size_t)((a.n_nodes + 1) & ~1);
+    // chunk of rows: a multiple of 4 (one Philox call = 4 steps): one ~32 KB buffer, or two ~16 KB
     // buffers when the TMA double-buffered staging is compiled in
-    int rows = (int)(((OPTP_LV_TMA ? 16 : 32) * 1024) / row_bytes) & ~3;
+    static const int chunk_kb = getenv("OPTP_LV_CHUNK_KB") ? atoi(getenv("OPTP_LV_CHUNK_KB")) : 36;  // per buffer
+    int rows = (int)((chunk_kb * 1024) / row_bytes) & ~3;
     if (rows < 4) rows = 4;
     const int max_rows = (int)((a.n_steps + 3) & ~3u);
     if (rows > max_rows) rows = max_rows;
@@ -758,22 +909,37 @@ static int launch_lv(const PathArgs& a, cudaStream_t st) {
     if (smem > 200 * 1024)
         return set_error(OPTP_E_TOO_LARGE, "sigma table rows of %d nodes do not fit shared memory",
                          a.n_nodes);
+    auto kern = lv_fp32_kernel<PROC, MASK, ANTI, WIN>;
     if (smem > 48 * 1024)
-        OPTP_CUDA(cudaFuncSetAttribute(lv_fp32_kernel<PROC, MASK, ANTI>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OPTP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &per_sm, lv_fp32_kernel<PROC, MASK, ANTI>, kLvThreads, smem));
+    OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kLvThreads, smem));
     if (per_sm < 1) per_sm = 1;
     unsigned long long blocks = (a.n_base + kLvThreads - 1) / kLvThreads;
     unsigned long long cap = (unsigned long long)ctx().n_sm * per_sm;
     if (cap > kMaxBlocks) cap = kMaxBlocks;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    lv_fp32_kernel<PROC, MASK, ANTI><<<(unsigned int)blocks, kLvThreads, smem, st>>>(a, rows);
+    kern<<<(unsigned int)blocks, kLvThreads, smem, st>>>(a, rows);
     ctx().launches++;
     OPTP_CUDA(cudaGetLastError());
     return 0;
+}
+
+template <int MASK, bool ANTI>
+static int launch_lvm_direct(const PathArgs& a, cudaStream_t st);
+
+template <int PROC, int MASK, bool ANTI>
+static int launch_lv(const PathArgs& a, cudaStream_t st) {
+    if constexpr (PROC == OPTP_PROC_LV_MILSTEIN) {
+        // one-load window lookup when the bump S(1 +- b) stays within one cell of ln S
+        const double cu = log1p(a.bump) / a.h, cd = -log1p(-fmin(a.bump, 0.999999)) / a.h;
+        if (cu < 1.0 && cd < 1.0 && !ctx().lv_no_window) {
+            if (ctx().lv_direct) return launch_lvm_direct<MASK, ANTI>(a, st);
+            return launch_lv_impl<PROC, MASK, ANTI, true>(a, st);
+        }
+    }
+    return launch_lv_impl<PROC, MASK, ANTI, false>(a, st);
 }
 
 template <int PROC, int MASK>

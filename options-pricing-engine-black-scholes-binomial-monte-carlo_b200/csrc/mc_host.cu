@@ -56,6 +56,7 @@ static void fill_args(PathArgs& a, const optp_process* pr, const optp_payoff* pa
     a.v0 = pr->v0; a.kappa = pr->kappa; a.theta = pr->theta; a.xi = pr->xi; a.rho = pr->rho;
     a.bump = pr->dS_bump; a.x0 = pr->x0; a.h = pr->h;
     a.table32 = (const float2*)c.table_f32.p;
+    a.table4 = (const float4*)c.table_f4.p;
     a.table64 = (const double*)c.table_f64.p;
     a.n_steps = n_steps;
     a.n_base = n_base;
@@ -77,9 +78,11 @@ static int upload_table(const double* table, uint32_t n_steps, uint32_t n_nodes)
     const size_t n_ld = (n_nodes + 1) & ~1u;
     if (int e = arena_reserve(c.table_f64, n * sizeof(double))) return e;
     if (int e = arena_reserve(c.table_f32, (size_t)n_steps * n_ld * sizeof(float2))) return e;
+    if (int e = arena_reserve(c.table_f4, (size_t)n_steps * (n_nodes + 4) * sizeof(float4))) return e;
     OPTP_CUDA(cudaMemcpyAsync(c.table_f64.p, table, n * sizeof(double), cudaMemcpyHostToDevice,
                               c.stream));
-    if (int e = launch_table_convert((const double*)c.table_f64.p, (float2*)c.table_f32.p, n_steps,
+    if (int e = launch_table_convert((const double*)c.table_f64.p, (float2*)c.table_f32.p,
+                                     (float4*)c.table_f4.p, n_steps,
                                      (int)n_nodes, c.stream))
         return e;
     c.table_steps = n_steps;

@@ -25,6 +25,7 @@ struct PathArgs {
     int n_nodes;
     double S0, r, q, T, sigma, v0, kappa, theta, xi, rho, bump, x0, h;
     const float2* table32;  // (value, next-value minus value) per node, n_steps rows
+    const float4* table4;   // window nodes (v_j, s_j, s_{j+1}, s_{j-1}), n_nodes + 4 per row
     const double* table64;  // n_steps x n_nodes
     unsigned int n_steps;
     unsigned long long n_base;
@@ -49,7 +50,7 @@ int launch_path_fp32(const PathArgs& a, cudaStream_t st);
 int launch_path_fp64(const PathArgs& a, cudaStream_t st);
 bool path_fp32_supported(int proc);
 // builds the (value, slope) fp32 table from an fp64 device table
-int launch_table_convert(const double* t64, float2* t32, unsigned int n_steps, int n_nodes,
+int launch_table_convert(const double* t64, float2* t32, float4* t4, unsigned int n_steps, int n_nodes,
                          cudaStream_t st);
 
 // which per-step path state the payoffs need

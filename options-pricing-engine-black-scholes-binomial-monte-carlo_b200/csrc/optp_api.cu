@@ -113,6 +113,7 @@ int optp_shutdown(void) {
     arena_free(c.out0);
     arena_free(c.out1);
     arena_free(c.table_f32);
+    arena_free(c.table_f4);
     arena_free(c.table_f64);
     cudaFree(c.partials);
     cudaFree(c.ticket);
@@ -129,6 +130,14 @@ int optp_set_option(const char* key, long value) {
     if (!key) return set_error(OPTP_E_ARG, "null option key");
     if (!strcmp(key, "crr_band")) {
         g_ctx.crr_no_band = (value == 0);
+        return 0;
+    }
+    if (!strcmp(key, "lv_direct")) {
+        g_ctx.lv_direct = (value != 0);
+        return 0;
+    }
+    if (!strcmp(key, "lv_window")) {
+        g_ctx.lv_no_window = (value == 0);
         return 0;
     }
     if (!strcmp(key, "crr_band_only")) {

@@ -24,9 +24,11 @@ struct Context {
     unsigned int* ticket = nullptr;
     double* stats_dev = nullptr;  // kMaxPayoffs * OPTP_NSTATS
     double* stats_host = nullptr; // pinned mirror
-    Arena in0, in1, out0, out1, table_f32, table_f64;
+    Arena in0, in1, out0, out1, table_f32, table_f64, table_f4;
     uint32_t table_steps = 0, table_nodes = 0;
     uint64_t launches = 0;
+    bool lv_direct = false;      // "lv_direct" = 1: window nodes gathered from global/L1, no smem staging
+    bool lv_no_window = false;   // "lv_window" = 0: three-lookup (value, slope) path for LV Milstein
     bool crr_band_only = false;  // OPTP_CRR_BAND_ONLY=1: skip the fallback pass (diagnostics)
     bool crr_no_band = false;  // OPTP_CRR_NO_BAND=1: full-width CRR kernels only (A/B testing)
 };
