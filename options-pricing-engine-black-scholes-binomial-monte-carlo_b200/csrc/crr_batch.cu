@@ -273,7 +273,8 @@ constexpr int kBandSeg = OPTP_BAND_SEG;  // levels per segment
 // FLAGS: also return a bit mask of the nodes that chose exercise.
 template <int B, bool FLAGS>
 __device__ __forceinline__ unsigned int band_level(double (&v)[kBandMaxB], const UTab& U, double rho,
-                                                   double sbg, double sKg, double nb, bool& ex0) {
+                                                   double rho_top, double sbg, double sKg, double nb,
+                                                   bool& ex0) {
     double sa[2];
     sa[0] = sbg;
 #pragma unroll
@@ -288,8 +289,9 @@ __device__ __forceinline__ unsigned int band_level(double (&v)[kBandMaxB], const
         for (int t = 0; t < G; ++t) {
             const int i = g0 + t;
             if (i < B) {
-                const double up = (i + 1 < B) ? v[i + 1] : nb;
-                c[t] = fma(rho, up, v[i]);
+                // the lane's last node takes the next lane's first node; in lane 31 rho_top is 0, so
+                // the node above the window counts as 0 without a per-level select
+                c[t] = (i + 1 < B) ? fma(rho, v[i + 1], v[i]) : fma(rho_top, nb, v[i]);
             }
         }
 #pragma unroll
@@ -316,9 +318,9 @@ __device__ __forceinline__ unsigned int band_segment(double (&v)[kBandMaxB], con
                                                      bool& bottom_always_exercise) {
     // sb = sgn*S0*u^(2*(w0 + lane*B) - k): this lane's first node one level above the segment
     double sbg = sb;
-    double sKg = L.sK, back = 1.0;
+    double sKg = L.sK;
+    const double rho_top = (lane == 31) ? 0.0 : L.rho;
     double nb = __shfl_down_sync(0xffffffffu, v[0], 1);
-    if (lane == 31) nb = 0.0;
     unsigned int mask = 0;
     bool ex0 = true;
     // the last level is peeled: it is the only one that records the full exercise mask
@@ -326,20 +328,23 @@ __device__ __forceinline__ unsigned int band_segment(double (&v)[kBandMaxB], con
     for (int t = 0; t < nlev - 1; ++t) {
         sbg *= L.u_pd;
         sKg *= L.inv_pd;
-        back *= L.pd;
         bool e0;
-        band_level<B, false>(v, U, L.rho, sbg, sKg, nb, e0);
+        band_level<B, false>(v, U, L.rho, rho_top, sbg, sKg, nb, e0);
         ex0 = ex0 && e0;
         nb = __shfl_down_sync(0xffffffffu, v[0], 1);
-        if (lane == 31) nb = 0.0;
     }
     {
         sbg *= L.u_pd;
         sKg *= L.inv_pd;
-        back *= L.pd;
         bool e0;
-        mask = band_level<B, true>(v, U, L.rho, sbg, sKg, nb, e0);
+        mask = band_level<B, true>(v, U, L.rho, rho_top, sbg, sKg, nb, e0);
         ex0 = ex0 && e0;
+    }
+    // undo the pd^-nlev scaling: pd^nlev by square-and-multiply (nlev <= 64)
+    double back = 1.0, sq = L.pd;
+    for (int e = nlev; e > 0; e >>= 1) {
+        if (e & 1) back *= sq;
+        sq *= sq;
     }
     bottom_always_exercise = ex0;  // meaningful in lane 0: the window's bottom node, every level
 #pragma unroll
@@ -351,6 +356,29 @@ template <int B>
 __device__ __forceinline__ void band_store(const double (&v)[kBandMaxB], double* tile, int lane) {
 #pragma unroll
     for (int i = 0; i < B; ++i) tile[i * 32 + lane] = v[i];  // conflict-free, slot-major
+}
+
+// new layout (w0n, BN) from the tile holding the old layout (w0, width_old = 32*B_old, slot-major):
+// nodes below the old window enter with their exercise value, nodes above it with 0
+template <int BN>
+__device__ __forceinline__ void band_load(double (&v)[kBandMaxB], const double* tile, const UTab& U,
+                                          double sb, double sK, int j_first, int w0_old, int B_old,
+                                          int magic) {
+    const int width_old = 32 * B_old;
+#pragma unroll
+    for (int i = 0; i < BN; ++i) {
+        const int jr = j_first + i - w0_old;
+        double val;
+        if (jr < 0) {
+            val = fma(sb * U.hi[i >> 3], U.lo[i & 7], sK);
+        } else if (jr >= width_old) {
+            val = 0.0;
+        } else {
+            const int lo_ = (jr * magic) >> 16;   // jr / B_old, exact for jr < 2048
+            val = tile[(jr - lo_ * B_old) * 32 + lo_];
+        }
+        v[i] = val;
+    }
 }
 
 // lane-local scan of the registers at level k: first non-exercise slot, last slot above thr
@@ -493,24 +521,8 @@ __global__ void __launch_bounds__(kBandWarps * 32, 5) crr_band_kernel(CrrArgs a)
             const double sb = L.sgn * L.S0 * exp(ln_u * (double)(2 * (w0n + lane * Bn) - k));
             {
                 const int magic = (65536 + B - 1) / B;   // exact j / B for j < 2048
-                const int width_old = 32 * B;
-#pragma unroll
-                for (int i = 0; i < kBandMaxB; ++i) {
-                    if (i < Bn) {
-                        const int j = w0n + lane * Bn + i;
-                        const int jr = j - w0;
-                        double val;
-                        if (jr < 0) {  // entering from below: exercise value, closed form
-                            val = fma(sb * U.hi[i >> 3], U.lo[i & 7], L.sK);
-                        } else if (jr >= width_old) {
-                            val = 0.0;
-                        } else {
-                            const int lo_ = (jr * magic) >> 16;
-                            val = tile[(jr - lo_ * B) * 32 + lo_];
-                        }
-                        v[i] = val;
-                    }
-                }
+                const int B_old = B, w0_old = w0;
+                OPTP_BAND_SWITCH(Bn, band_load<BB>(v, tile, U, sb, L.sK, w0n + lane * BB, w0_old, B_old, magic));
             }
             __syncwarp();
             w0 = w0n;
