@@ -518,7 +518,8 @@ def main():
             "e2e": mc_e2e,
             "roofline": {"bound": "fp32_pipe", "achieved": mc_kernel_rate * OPS_PER_PATH_STEP["gbm_barrier"] / 1e12,
                          "peak": p32 / 1e12, "unit": "T lane-ops/s",
-                         "frac": mc_kernel_rate * OPS_PER_PATH_STEP["gbm_barrier"] / p32, "traffic": None,
+                         "frac": mc_kernel_rate * OPS_PER_PATH_STEP["gbm_barrier"] / p32,
+                         "traffic": 107520,  # ncu --set full, profiles/r1_ncu_full_final.md: dram read 0.1 MB, write 0 per launch
                          "ops_per_path_step": OPS_PER_PATH_STEP["gbm_barrier"], "kernel_ms": mc_kernel_ms,
                          "path_steps_per_s_per_gpu": mc_kernel_rate,
                          "peak_source": "optp_microbench FFMA issue rate measured in this run (MEASURED_PEAKS.json "

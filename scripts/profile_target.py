@@ -30,7 +30,10 @@ for _ in range(reps):
                                       100.0, 0.05, 1.0, "call", 130.0, "up-and-out"))
     if "terminal" in which:
         print("terminal", op.euro_price_mc(op.OptionSpec(100.0, 110.0, 1.0, 0.03, 0.2), "call", n_paths=1 << 28, seed=1))
-    if "crr" in which:
+    if "crr" in which:   # banded kernel (default) and the full-width kernel on the same contracts
         cols = cfg2_contracts(1 << 16)
-        print("crr", op.crr_batch(*cols, 1000, american=True)[:3])
+        print("crr band", op.crr_batch(*cols, 1000, american=True)[:3])
+        nv.set_option("crr_band", 0)
+        print("crr full", op.crr_batch(*cols, 1000, american=True)[:3])
+        nv.set_option("crr_band", 1)
 print("launches", nv.launch_count())

@@ -578,3 +578,63 @@ def test_heston_qe_production_kernel(op, case):
     exact = heston_call_semi_analytic(c["S0"], 100.0, c["T"], c["r"], c["q"], c["v0"], c["kappa"], c["theta"], c["xi"], c["rho"])
     big = ex.price_payoffs(pr.heston_paths(n_steps=32, n_paths=4_000_000, seed=8, scheme="qe", **c), specs[:1], c["r"], c["T"])[0]
     assert abs(big[0] - exact) <= 4.0 * big[1] + 0.02, (big, exact)
+
+
+# ------------------------------------------------------------------------------ BASELINE full sizes
+def test_full_size_config2_crr_batch(op):
+    """BASELINE config 2 at full size: 1 000 000 American puts, N = 1000.  Size-independent
+    properties + the reference fixture for the head of the batch."""
+    g = load_json("crr.json")
+    S0, K, T, r, q, sig, is_call = crr_tree.cfg2_contracts(1_000_000)
+    price, status = op.crr_batch(S0, K, T, r, q, sig, is_call, 1000, american=True, return_status=True)
+    assert price.shape == (1_000_000,) and not status.any() and np.isfinite(price).all()
+    np.testing.assert_allclose(price[:64], np.array(g["cfg2_first64_american_put_N1000"]), rtol=REL_CRR, atol=REL_CRR)
+    assert np.all(price >= np.maximum(K - S0, 0.0) - 1e-12)          # never below intrinsic
+    assert np.all(price <= K + 1e-12)                                 # a put is worth at most K
+    euro = op.crr_batch(S0, K, T, r, q, sig, is_call, 1000, american=False)
+    assert np.all(price >= euro - 1e-10)                               # early exercise never hurts
+    # permutation invariance: a contract's price does not depend on where it sits in the batch
+    perm = np.random.default_rng(1).permutation(1_000_000)
+    again = op.crr_batch(S0[perm], K[perm], T[perm], r[perm], q[perm], sig[perm], is_call[perm], 1000, american=True)
+    np.testing.assert_array_equal(again, price[perm])
+
+
+def test_full_size_config3_local_vol_barrier(op):
+    """BASELINE config 3: LV Milstein on the Dupire table, 252 steps, 1e8 effective paths."""
+    from optpricer_b200 import exotics as ex, processes as pr
+    tab = pr.SigmaTable(*dupire_grid_arrays())
+    n = 50_000_000
+    lp = pr.milstein_local_vol_paths(100.0, 0.05, 0.02, 1.0, 252, n, tab, seed=42)
+    specs = [ex.barrier_spec(100.0, "call", 130.0, "up-and-out"), ex.barrier_spec(100.0, "call", 130.0, "up-and-in"),
+             ex.vanilla_spec(100.0, "call")]
+    stats, _, _ = ex.path_stats(lp, specs, 0.05, 1.0)
+    assert all(s[0] == 2 * n for s in stats)
+    assert abs(stats[0][1] + stats[1][1] - stats[2][1]) <= 1e-9 * stats[2][1]        # in + out == vanilla, path by path
+    fwd_disc = 100.0 * math.exp(-0.02)                                               # E[e^{-rT} S_T] = S0 e^{-qT}
+    my = stats[2][3] / stats[2][0]
+    sy = math.sqrt(max(stats[2][4] / stats[2][0] - my * my, 0.0) / stats[2][0])
+    assert abs(my - fwd_disc) <= 4 * sy + 2e-4 * fwd_disc    # + the Milstein scheme's weak error at 252 steps
+    want = load_json("mc_paths.json")["desk_table_252x100k"]["uo130"]
+    p, se = ex.estimate(stats[0])
+    assert se < 1e-3 and abs(p - want[0]) <= 3 * want[1]
+    # sharding over 8 ranks reproduces the single-device statistics
+    parts = sum(ex.path_stats(lp, specs[:1], 0.05, 1.0, n_base=hi - lo, path_offset=lo)[0]
+                for lo, hi in [(k * n // 8, (k + 1) * n // 8) for k in range(8)])
+    np.testing.assert_allclose(parts[0][:6], stats[0][:6], rtol=1e-9)
+
+
+def test_full_size_config4_heston_asian(op):
+    """BASELINE config 4: Heston full-truncation Euler, 365 steps, 1e9 effective paths, arithmetic
+    Asian call with antithetic variates and the reference's control variate."""
+    from optpricer_b200 import exotics as ex, processes as pr
+    n = 500_000_000
+    lp = pr.heston_paths(100.0, 0.05, 0.0, 0.04, 2.0, 0.04, 0.3, -0.7, 1.0, 365, n, seed=42)
+    stats, _, _ = ex.path_stats(lp, [ex.asian_spec(100.0, "call"), ex.asian_spec(100.0, "call", "geometric")], 0.05, 1.0)
+    assert stats[0][0] == 2 * n == 1_000_000_000
+    plain = ex.estimate(stats[0])
+    cv = ex.estimate(stats[0], control_variate=True, expected_y=100.0)
+    want = load_json("mc_paths.json")["heston_365x50k"]["prices"]["asian|call|arithmetic|fixed"]
+    assert abs(plain[0] - want[0]) <= 3 * want[1] and abs(cv[0] - want[0]) <= 3 * want[1]
+    assert cv[1] < plain[1] < 3e-4                                    # the control variate helps
+    assert stats[0][1] >= stats[1][1]                                 # arithmetic >= geometric
+    assert abs(stats[0][3] / stats[0][0] - 100.0) < 5e-3              # martingale: E[e^{-rT} S_T] = S0
