@@ -549,6 +549,285 @@ __global__ void __launch_bounds__(kBandWarps * 32, 5) crr_band_kernel(CrrArgs a)
 }
 #undef OPTP_BAND_SWITCH
 
+// ---------------------------------------------------------------- two-zone banded American put kernel
+// Refinement of the banded kernel above, on three counts.
+//  (1) Inside the band almost every node is a CONTINUATION node: only the few nodes next to the
+//      early-exercise boundary can choose exercise.  The window is split in two zones:
+//        zone Z = [w0, w0 + 32)              full update  max(cont, K - S)   (3 FP64 ops + 2 selects per node)
+//        zone C = [w0 + 32, w0 + 32 + 32*M)  continuation only, A[j] = rho*A[j+1] + A[j]   (ONE DFMA per node)
+//      Z holds the margin below the boundary (the boundary index falls by at most one per level, see
+//      above: nlev + 2 nodes for a segment of nlev levels) and at least two nodes above it.
+//      Why C needs no exercise test, checked at run time: on every level V + S is non-decreasing in
+//      the node index when q >= 0 (induction: pu*S(j+1) + pd*S(j) = S*e^{-q dt}), so the exercise
+//      nodes of a level are contiguous from the bottom; as long as the TOP node of Z chooses
+//      continuation on every level of the segment, every node of C is a continuation node.  The
+//      kernel counts that test over the segment (last lane of the option) exactly like the
+//      bottom-node test (first lane); the count stops at the level where Z's top node leaves the
+//      tree (index > level: C has no real node from there on).  A contract that fails either test
+//      keeps status 2 and is priced by the full-width kernel.
+//  (2) The per-level cost of a warp is dominated by instructions that do not depend on how many
+//      lanes do useful work (neighbour shuffles, scaling multiplies, loop control), so G = 4 (or 2)
+//      options share one warp, 32/G lanes each, every lane owning G nodes of Z and G*M nodes of C
+//      of ITS option.  All options of a warp walk the same levels with the same layout (M = the
+//      widest C zone among them); everything else (lattice constants, window origin, band limits,
+//      failure flags) is per option.
+//  (3) The schedule is FIXED -- segments of kZoneSeg levels counted from level N, rigorous margin --
+//      so the arithmetic applied to a contract does not depend on its warp mates or on G: a
+//      contract's price is bit-identical whatever batch it is priced in.
+constexpr int kZoneWarps = 4;
+constexpr int kZoneSeg = 24;      // levels per segment; margin kZoneSeg + 2 and 2 + 2 nodes above fit 32
+constexpr int kZoneMaxM = 6;      // C zone up to 192 nodes
+constexpr int kZoneGroupTile = 32 * (1 + kZoneMaxM);  // doubles per option in the re-pack tile
+
+// nlev levels in layout (BZ = G, BC = G*M).  sb = sgn*S0*u^(2*(w0 + quad) - k): the first node of this
+// lane's quad of Z nodes one level above the segment (ulo holds the lane's factors within the quad).  Returns the exercise mask of this lane's Z nodes at the last
+// level; n_ex0 counts the levels at which the lane's first Z node chose exercise, n_exT the levels
+// t < n_chk at which its last Z node did.
+template <int G, int M>
+__device__ __forceinline__ unsigned int zone_segment(double (&z)[G], double (&c)[G * kZoneMaxM],
+                                                     const double (&ulo)[G], const Lattice& L, int gl,
+                                                     int src, double sb, int nlev, int n_chk,
+                                                     int& n_ex0_out, int& n_exT_out) {
+    constexpr int BZ = G, BC = G * M, LG = 32 / G;
+    double sbg = sb, sKg = L.sK;
+    const double rho = L.rho;
+    const double rho_top = (gl == LG - 1) ? 0.0 : rho;  // the node above the window counts as 0
+    const double rho_ztop = (BC > 0) ? rho : rho_top;
+    // exercise counters instead of predicate chains: ptxas folds `all = all && (e > c)` into a second
+    // and third DSETP per level, and the FP64 pipe is the one this loop loads most
+    int n_ex0 = 0, n_exT = 0;
+    // lane gl takes lane gl+1's first Z node; the option's last lane takes its first lane's first C
+    // node (the first lane's own first Z node is nobody's neighbour)
+    double nbz = __shfl_sync(0xffffffffu, (BC > 0 && gl == 0) ? c[0] : z[0], src);
+    double nbc = 0.0;
+    if (BC > 0) nbc = __shfl_sync(0xffffffffu, c[0], src);
+#pragma unroll 1
+    for (int t = 0; t < nlev; ++t) {
+        sbg *= L.u_pd;
+        sKg *= L.inv_pd;
+        double cz[BZ], ez[BZ];
+#pragma unroll
+        for (int i = 0; i < BZ; ++i)
+            cz[i] = (i + 1 < BZ) ? fma(rho, z[i + 1], z[i]) : fma(rho_ztop, nbz, z[i]);
+#pragma unroll
+        for (int i = 0; i < BZ; ++i) ez[i] = fma(sbg, ulo[i], sKg);
+        // everything is updated in place, in ascending node order, so no value has to be carried
+        // in a second register across the loop edge
+#pragma unroll
+        for (int i = 0; i < BC; ++i)
+            c[i] = (i + 1 < BC) ? fma(rho, c[i + 1], c[i]) : fma(rho_top, nbc, c[i]);
+#pragma unroll
+        for (int i = 0; i < BZ; ++i) {
+            const bool ex = ez[i] > cz[i];
+            if (i == 0) n_ex0 += ex ? 1 : 0;
+            if (i == BZ - 1) n_exT += (ex && t < n_chk) ? 1 : 0;
+            z[i] = ex ? ez[i] : cz[i];
+        }
+        if (BC > 0) nbc = __shfl_sync(0xffffffffu, c[0], src);
+        nbz = __shfl_sync(0xffffffffu, (BC > 0 && gl == 0) ? c[0] : z[0], src);
+    }
+    // exercise mask of the last level: a node chose exercise iff it holds the exercise value
+    unsigned int mask = 0;
+#pragma unroll
+    for (int i = 0; i < BZ; ++i) mask |= (z[i] == fma(sbg, ulo[i], sKg)) ? (1u << i) : 0u;
+    // undo the pd^-nlev scaling: pd^nlev by square-and-multiply
+    double back = 1.0, sq = L.pd;
+    for (int e = nlev; e > 0; e >>= 1) {
+        if (e & 1) back *= sq;
+        sq *= sq;
+    }
+#pragma unroll
+    for (int i = 0; i < BZ; ++i) z[i] *= back;
+#pragma unroll
+    for (int i = 0; i < BC; ++i) c[i] *= back;
+    n_ex0_out = n_ex0;
+    n_exT_out = n_exT;
+    return mask;
+}
+
+template <int G>
+__global__ void __launch_bounds__(kZoneWarps * 32, (G == 4) ? 4 : 5) crr_zone_kernel(CrrArgs a) {
+    constexpr int LG = 32 / G, BZ = G, BCMAX = G * kZoneMaxM;
+    __shared__ double tiles[kZoneWarps][G * kZoneGroupTile + 8];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int gl = lane & (LG - 1);        // lane within the option
+    const int gb = lane & ~(LG - 1);       // first lane of the option
+    const int src = gb | ((gl + 1) & (LG - 1));
+    const unsigned int gmask = (LG == 32) ? 0xffffffffu : ((1u << LG) - 1u);
+    double* tile = tiles[wib] + (lane / LG) * kZoneGroupTile;
+    const int N = a.N;
+    const unsigned long long warp0 = (unsigned long long)blockIdx.x * kZoneWarps + wib;
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * kZoneWarps;
+    for (unsigned long long o0 = warp0 * G; o0 < a.n; o0 += nwarps * G) {
+        const unsigned long long og = o0 + (unsigned long long)(lane / LG);
+        const bool active = og < a.n;
+        const unsigned long long o = active ? og : (a.n - 1);
+        const Lattice L = make_lattice(a, o);
+        if (active && !L.ok && gl == 0) {
+            a.price[o] = nan("");
+            a.status[o] = 1;
+        }
+        const double r = a.r[o], q = a.q[o], K = a.K[o];
+        const double dt = a.T[o] / (double)N;
+        const double one_m_disc = -expm1(-r * dt), one_m_dq = -expm1(-q * dt);
+        const bool eligible = active && L.ok && (L.sgn < 0.0) && q >= 0.0 && one_m_disc > 1e-9 &&
+                              one_m_disc > one_m_dq * (1.0 + 1e-6) && L.R >= kZoneSeg;
+        // an option that is not walked (declined, failed, past the end of the batch) rides along with
+        // a harmless plan; `fail` keeps its result from being written
+        bool fail = !eligible;
+        if (!__any_sync(0xffffffffu, eligible)) {
+            if (active && L.ok && gl == 0) a.status[o] = 2;
+            continue;
+        }
+        // exercise values: node m of Z (m = index - w0) is sgn*S0*u^(2*(w0 + (m & ~3)) - k) * u^(2*(m & 3)),
+        // the first factor through exp(), the second from {1, u^2, u^4, u^6} -- the SAME two factors
+        // whatever G is, so that a node's arithmetic does not depend on the lane layout
+        double ulo[G];
+        {
+            const double u2 = L.u * L.u;
+            const double t4[4] = {1.0, u2, u2 * u2, u2 * u2 * u2};
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                const int b = (gl * G + i) & 3;
+                ulo[i] = (b == 0) ? t4[0] : (b == 1) ? t4[1] : (b == 2) ? t4[2] : t4[3];
+            }
+        }
+        const int quad0 = (gl * G) & ~3;  // first node of this lane's quad, relative to w0
+        const double thr = K * 8.2718061255302767e-25;  // 2^-80 K
+        const double ln_u = log(L.u);
+        double z[BZ], c[BCMAX];
+#pragma unroll
+        for (int i = 0; i < BCMAX; ++i) c[i] = 0.0;
+        // ---- level N: closed form max(K - S, 0) (binomial.py:20-25).  Z is placed so that its top
+        // nodes are out of the money: everything above it is exactly 0, everything below it is an
+        // exercise node
+        int M = 0, k = N;
+        int w0;
+        unsigned int exmask = 0;
+        {
+            const double jz = 0.5 * ((double)N + log(K / L.S0) / ln_u);  // first out-of-the-money node
+            const double w = fmin(fmax(floor(jz) - 28.0, 0.0), (double)max(0, N + 1 - 32));
+            w0 = fail ? 0 : (int)w;
+            const double sbN = L.sgn * L.S0 * exp(ln_u * (double)(2 * (w0 + quad0) - N));
+#pragma unroll
+            for (int i = 0; i < BZ; ++i) {
+                const double e = fma(sbN, ulo[i], L.sK);
+                z[i] = e > 0.0 ? e : 0.0;
+                exmask |= (e > 0.0) ? (1u << i) : 0u;
+            }
+        }
+        while (true) {
+            // ---- measure the band [jlo, jhi) of the level held in registers (per option) ---------
+            const int BC = G * M;
+            const int zbase = w0 + gl * BZ, cbase = w0 + 32 + gl * BC;
+            const unsigned int contm = ~exmask & ((1u << BZ) - 1u);
+            const int first_cont = contm ? (__ffs(contm) - 1) : BZ;
+            int lastZ = -1, lastC = -1;
+#pragma unroll
+            for (int i = 0; i < BZ; ++i)
+                if (z[i] > thr && zbase + i <= k) lastZ = i;
+#pragma unroll
+            for (int i = 0; i < BCMAX; ++i)
+                if (i < BC && c[i] > thr && cbase + i <= k) lastC = i;
+            const unsigned int has_cont = (__ballot_sync(0xffffffffu, first_cont < BZ) >> gb) & gmask;
+            const unsigned int liveC = (__ballot_sync(0xffffffffu, lastC >= 0) >> gb) & gmask;
+            const unsigned int liveZ = (__ballot_sync(0xffffffffu, lastZ >= 0) >> gb) & gmask;
+            // the three lane indices below are always inside the option's own lanes
+            const int f_cont = has_cont ? (__ffs(has_cont) - 1) : 0;
+            const int f_c = liveC ? (31 - __clz(liveC)) : 0;
+            const int f_z = liveZ ? (31 - __clz(liveZ)) : 0;
+            const int s_cont = __shfl_sync(0xffffffffu, first_cont, gb + f_cont);
+            const int s_c = __shfl_sync(0xffffffffu, lastC, gb + f_c);
+            const int s_z = __shfl_sync(0xffffffffu, lastZ, gb + f_z);
+            int jlo = has_cont ? (w0 + f_cont * BZ + s_cont) : (w0 + 32);
+            int jhi = liveC ? (w0 + 32 + f_c * BC + s_c + 1) : (liveZ ? (w0 + f_z * BZ + s_z + 1) : w0);
+            if (jhi < jlo) jhi = jlo;
+            // the window bottom must still be inside the exercise region (or be node 0)
+            if (w0 > 0 && jlo <= w0) fail = true;
+            if (k == 0) break;
+            // ---- next segment: levels k-1 ... k-nlev, fixed schedule -------------------------------
+            const int nlev = min(kZoneSeg, k);
+            const int top = min(jhi, k + 1);  // exclusive; node `top` of level k is 0 (or dead)
+            // rigorous margin: the boundary index falls by at most one per level
+            int w0n = max(0, jlo - (nlev + 2));
+            int need = 0, n_chk = 0;
+            if (top > w0n + 32) {
+                need = (top - (w0n + 32) + 31) >> 5;
+                // the top test is evaluated while Z's top node exists: level >= w0n + 31
+                n_chk = min(nlev, max(0, k - (w0n + 31)));
+                if (need > kZoneMaxM) fail = true;
+            }
+            if (fail) {
+                w0n = 0;
+                need = 0;
+                n_chk = 0;
+            }
+            const int Mn = __reduce_max_sync(0xffffffffu, need);
+            const int BCn = G * Mn;
+            // ---- re-pack level k from (w0, M) to (w0n, Mn), node-ordered tile per option -----------
+#pragma unroll
+            for (int i = 0; i < BZ; ++i) tile[gl * BZ + i] = z[i];
+#pragma unroll
+            for (int i = 0; i < BCMAX; ++i)
+                if (i < BC) tile[32 + gl * BC + i] = c[i];
+            __syncwarp();
+            const int width_old = 32 * (1 + M);
+            // this lane's first Z node of the new layout at level k: sgn*S0*u^(2j - k)
+            const double sb = L.sgn * L.S0 * exp(ln_u * (double)(2 * (w0n + quad0) - k));
+#pragma unroll
+            for (int i = 0; i < BZ; ++i) {
+                const int j = w0n + gl * BZ + i;
+                const int jr = j - w0;
+                double val;
+                if (jr < 0) val = fma(sb, ulo[i], L.sK);           // below the old window: exercise
+                else if (jr >= width_old || j >= top) val = 0.0;   // above the band
+                else val = tile[jr];
+                z[i] = val;
+            }
+#pragma unroll
+            for (int i = 0; i < BCMAX; ++i) {
+                if (i < BCn) {
+                    const int j = w0n + 32 + gl * BCn + i;
+                    const int jr = j - w0;
+                    c[i] = (jr < 0 || jr >= width_old || j >= top) ? 0.0 : tile[jr];
+                }
+            }
+            __syncwarp();
+            w0 = w0n;
+            M = Mn;
+            int n_ex0 = 0, n_exT = 0;
+            switch (M) {
+                case 0: exmask = zone_segment<G, 0>(z, c, ulo, L, gl, src, sb, nlev, n_chk, n_ex0, n_exT); break;
+                case 1: exmask = zone_segment<G, 1>(z, c, ulo, L, gl, src, sb, nlev, n_chk, n_ex0, n_exT); break;
+                case 2: exmask = zone_segment<G, 2>(z, c, ulo, L, gl, src, sb, nlev, n_chk, n_ex0, n_exT); break;
+                case 3: exmask = zone_segment<G, 3>(z, c, ulo, L, gl, src, sb, nlev, n_chk, n_ex0, n_exT); break;
+                case 4: exmask = zone_segment<G, 4>(z, c, ulo, L, gl, src, sb, nlev, n_chk, n_ex0, n_exT); break;
+                case 5: exmask = zone_segment<G, 5>(z, c, ulo, L, gl, src, sb, nlev, n_chk, n_ex0, n_exT); break;
+                default: exmask = zone_segment<G, 6>(z, c, ulo, L, gl, src, sb, nlev, n_chk, n_ex0, n_exT); break;
+            }
+            // everything below the window is an exercise node only while the window's bottom node
+            // chose exercise at EVERY level; everything in C is a continuation node only while Z's
+            // top node chose continuation at every level it exists
+            const int bottom_ex = __shfl_sync(0xffffffffu, n_ex0, gb);
+            const int top_ex = __shfl_sync(0xffffffffu, n_exT, gb + LG - 1);
+            if (w0 > 0 && bottom_ex != nlev) fail = true;
+            if (top_ex != 0) fail = true;
+            k -= nlev;
+        }
+        // level 0: node 0 is in the window (w0 == 0) or below it (then it is an exercise node)
+        const double v0 = __shfl_sync(0xffffffffu, z[0], gb);
+        if (active && L.ok && gl == 0) {
+            if (fail) {
+                a.status[o] = 2;
+            } else {
+                a.price[o] = (w0 == 0) ? v0 : (K - L.S0);
+                a.status[o] = 0;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- generic N: one option per CTA
 template <bool AMER>
 __global__ void __launch_bounds__(256) crr_cta_kernel(CrrArgs a) {
@@ -628,12 +907,34 @@ static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st) {
         if (american && !c.crr_no_band) {
             // pass 1: banded kernel (American puts with r > q); pass 2: whatever it left at status 2
             int per_sm = 0;
-            OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, crr_band_kernel,
-                                                                    kBandWarps * 32, 0));
+            // options per warp of the two-zone kernel: 4 once the batch fills the machine that way
+            int G = 0;
+            if (c.crr_band_kernel == 2) {
+                G = c.crr_zone_group;
+                if (G == 0) {
+                    const unsigned long long warps = (unsigned long long)c.n_sm * 16;
+                    G = (a.n >= 4 * warps) ? 4 : (a.n >= 2 * warps) ? 2 : 1;
+                }
+            }
+            const void* fn = (G == 4)   ? (const void*)crr_zone_kernel<4>
+                             : (G == 2) ? (const void*)crr_zone_kernel<2>
+                             : (G == 1) ? (const void*)crr_zone_kernel<1>
+                                        : (const void*)crr_band_kernel;
+            static_assert(kBandWarps == kZoneWarps, "one grid computation for both banded kernels");
+            OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kZoneWarps * 32, 0));
             if (per_sm < 1) per_sm = 1;
-            const unsigned long long want = (a.n + kBandWarps - 1) / kBandWarps;
+            const unsigned long long per_warp = (G > 0) ? (unsigned long long)G : 1ull;
+            const unsigned long long want = (a.n + kBandWarps * per_warp - 1) / (kBandWarps * per_warp);
             const unsigned long long cap = (unsigned long long)c.n_sm * per_sm;
-            crr_band_kernel<<<(unsigned int)(want < cap ? want : cap), kBandWarps * 32, 0, st>>>(a);
+            const unsigned int grid = (unsigned int)(want < cap ? want : cap);
+            if (G == 4)
+                crr_zone_kernel<4><<<grid, kZoneWarps * 32, 0, st>>>(a);
+            else if (G == 2)
+                crr_zone_kernel<2><<<grid, kZoneWarps * 32, 0, st>>>(a);
+            else if (G == 1)
+                crr_zone_kernel<1><<<grid, kZoneWarps * 32, 0, st>>>(a);
+            else
+                crr_band_kernel<<<grid, kBandWarps * 32, 0, st>>>(a);
             c.launches++;
             OPTP_CUDA(cudaGetLastError());
             a.todo_only = 1;

@@ -132,6 +132,17 @@ int optp_set_option(const char* key, long value) {
         g_ctx.crr_no_band = (value == 0);
         return 0;
     }
+    if (!strcmp(key, "crr_band_kernel")) {
+        if (value != 1 && value != 2) return set_error(OPTP_E_ARG, "crr_band_kernel must be 1 or 2");
+        g_ctx.crr_band_kernel = (int)value;
+        return 0;
+    }
+    if (!strcmp(key, "crr_zone_group")) {
+        if (value != 0 && value != 1 && value != 2 && value != 4)
+            return set_error(OPTP_E_ARG, "crr_zone_group must be 0, 1, 2 or 4");
+        g_ctx.crr_zone_group = (int)value;
+        return 0;
+    }
     if (!strcmp(key, "lv_direct")) {
         g_ctx.lv_direct = (value != 0);
         return 0;
