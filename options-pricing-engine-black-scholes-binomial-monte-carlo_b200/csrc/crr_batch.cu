@@ -575,9 +575,13 @@ __global__ void __launch_bounds__(kBandWarps * 32, 5) crr_band_kernel(CrrArgs a)
 //      so the arithmetic applied to a contract does not depend on its warp mates or on G: a
 //      contract's price is bit-identical whatever batch it is priced in.
 constexpr int kZoneWarps = 4;
-constexpr int kZoneSeg = 24;      // levels per segment; margin kZoneSeg + 2 and 2 + 2 nodes above fit 32
+constexpr int kZoneSeg = 28;      // levels per segment: Z = [jlo - 30, jlo + 2), margin kZoneSeg + 2 below the boundary
 constexpr int kZoneMaxM = 6;      // C zone up to 192 nodes
-constexpr int kZoneGroupTile = 32 * (1 + kZoneMaxM);  // doubles per option in the re-pack tile
+// re-pack tile, node-ordered per option: node e lives at e + (e >> 4) (one pad double per 16, so the
+// lane-strided accesses of every layout spread over the banks); 248 = 8 (mod 16) staggers the options
+constexpr int kZoneGroupTile = 248;
+__device__ __forceinline__ int zone_pad(int e) { return e + (e >> 4); }
+static_assert(32 * (1 + kZoneMaxM) + (32 * (1 + kZoneMaxM) >> 4) <= kZoneGroupTile, "tile too small");
 
 // nlev levels in layout (BZ = G, BC = G*M).  sb = sgn*S0*u^(2*(w0 + quad) - k): the first node of this
 // lane's quad of Z nodes one level above the segment (ulo holds the lane's factors within the quad).  Returns the exercise mask of this lane's Z nodes at the last
@@ -586,7 +590,7 @@ constexpr int kZoneGroupTile = 32 * (1 + kZoneMaxM);  // doubles per option in t
 template <int G, int M>
 __device__ __forceinline__ unsigned int zone_segment(double (&z)[G], double (&c)[G * kZoneMaxM],
                                                      const double (&ulo)[G], const Lattice& L, int gl,
-                                                     int src, double sb, int nlev, int n_chk,
+                                                     int src, double sb, int nlev, int n_chk, double back,
                                                      int& n_ex0_out, int& n_exT_out) {
     constexpr int BZ = G, BC = G * M, LG = 32 / G;
     double sbg = sb, sKg = L.sK;
@@ -601,7 +605,7 @@ __device__ __forceinline__ unsigned int zone_segment(double (&z)[G], double (&c)
     double nbz = __shfl_sync(0xffffffffu, (BC > 0 && gl == 0) ? c[0] : z[0], src);
     double nbc = 0.0;
     if (BC > 0) nbc = __shfl_sync(0xffffffffu, c[0], src);
-#pragma unroll 1
+#pragma unroll 2
     for (int t = 0; t < nlev; ++t) {
         sbg *= L.u_pd;
         sKg *= L.inv_pd;
@@ -630,12 +634,7 @@ __device__ __forceinline__ unsigned int zone_segment(double (&z)[G], double (&c)
     unsigned int mask = 0;
 #pragma unroll
     for (int i = 0; i < BZ; ++i) mask |= (z[i] == fma(sbg, ulo[i], sKg)) ? (1u << i) : 0u;
-    // undo the pd^-nlev scaling: pd^nlev by square-and-multiply
-    double back = 1.0, sq = L.pd;
-    for (int e = nlev; e > 0; e >>= 1) {
-        if (e & 1) back *= sq;
-        sq *= sq;
-    }
+    // undo the pd^-nlev scaling (back = pd^nlev)
 #pragma unroll
     for (int i = 0; i < BZ; ++i) z[i] *= back;
 #pragma unroll
@@ -648,7 +647,7 @@ __device__ __forceinline__ unsigned int zone_segment(double (&z)[G], double (&c)
 template <int G>
 __global__ void __launch_bounds__(kZoneWarps * 32, (G == 4) ? 4 : 5) crr_zone_kernel(CrrArgs a) {
     constexpr int LG = 32 / G, BZ = G, BCMAX = G * kZoneMaxM;
-    __shared__ double tiles[kZoneWarps][G * kZoneGroupTile + 8];
+    __shared__ double tiles[kZoneWarps][G * kZoneGroupTile];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int gl = lane & (LG - 1);        // lane within the option
@@ -696,6 +695,15 @@ __global__ void __launch_bounds__(kZoneWarps * 32, (G == 4) ? 4 : 5) crr_zone_ke
         const int quad0 = (gl * G) & ~3;  // first node of this lane's quad, relative to w0
         const double thr = K * 8.2718061255302767e-25;  // 2^-80 K
         const double ln_u = log(L.u);
+        double back_full = 1.0;  // pd^kZoneSeg by square-and-multiply
+        {
+            double sq = L.pd;
+#pragma unroll
+            for (int e = kZoneSeg; e > 0; e >>= 1) {
+                if (e & 1) back_full *= sq;
+                sq *= sq;
+            }
+        }
         double z[BZ], c[BCMAX];
 #pragma unroll
         for (int i = 0; i < BCMAX; ++i) c[i] = 0.0;
@@ -718,30 +726,46 @@ __global__ void __launch_bounds__(kZoneWarps * 32, (G == 4) ? 4 : 5) crr_zone_ke
             }
         }
         while (true) {
-            // ---- measure the band [jlo, jhi) of the level held in registers (per option) ---------
+            // ---- level k goes to the tile (node-ordered); measure its band [jlo, jhi) per option -----
             const int BC = G * M;
-            const int zbase = w0 + gl * BZ, cbase = w0 + 32 + gl * BC;
-            const unsigned int contm = ~exmask & ((1u << BZ) - 1u);
-            const int first_cont = contm ? (__ffs(contm) - 1) : BZ;
-            int lastZ = -1, lastC = -1;
 #pragma unroll
-            for (int i = 0; i < BZ; ++i)
-                if (z[i] > thr && zbase + i <= k) lastZ = i;
+            for (int i = 0; i < BZ; ++i) tile[zone_pad(gl * BZ + i)] = z[i];
 #pragma unroll
             for (int i = 0; i < BCMAX; ++i)
-                if (i < BC && c[i] > thr && cbase + i <= k) lastC = i;
+                if (i < BC) tile[zone_pad(32 + gl * BC + i)] = c[i];
+            __syncwarp();
+            // jlo = first node that did not choose exercise
+            const unsigned int contm = ~exmask & ((1u << BZ) - 1u);
+            const int first_cont = contm ? (__ffs(contm) - 1) : BZ;
             const unsigned int has_cont = (__ballot_sync(0xffffffffu, first_cont < BZ) >> gb) & gmask;
-            const unsigned int liveC = (__ballot_sync(0xffffffffu, lastC >= 0) >> gb) & gmask;
-            const unsigned int liveZ = (__ballot_sync(0xffffffffu, lastZ >= 0) >> gb) & gmask;
-            // the three lane indices below are always inside the option's own lanes
-            const int f_cont = has_cont ? (__ffs(has_cont) - 1) : 0;
-            const int f_c = liveC ? (31 - __clz(liveC)) : 0;
-            const int f_z = liveZ ? (31 - __clz(liveZ)) : 0;
+            const int f_cont = has_cont ? (__ffs(has_cont) - 1) : 0;  // always one of the option's lanes
             const int s_cont = __shfl_sync(0xffffffffu, first_cont, gb + f_cont);
-            const int s_c = __shfl_sync(0xffffffffu, lastC, gb + f_c);
-            const int s_z = __shfl_sync(0xffffffffu, lastZ, gb + f_z);
-            int jlo = has_cont ? (w0 + f_cont * BZ + s_cont) : (w0 + 32);
-            int jhi = liveC ? (w0 + 32 + f_c * BC + s_c + 1) : (liveZ ? (w0 + f_z * BZ + s_z + 1) : w0);
+            const int jlo = has_cont ? (w0 + f_cont * BZ + s_cont) : (w0 + 32);
+            // jhi = 1 + last node worth more than 2^-80 K.  A put's value falls with the node index, so
+            // the live nodes are a prefix of the window: find the last lane whose FIRST node is live
+            // from the registers, then count the live nodes of that lane's chunk from the tile.
+            const bool c0_live = (BC > 0) && c[0] > thr && (w0 + 32 + gl * BC) <= k;
+            const bool z0_live = z[0] > thr && (w0 + gl * BZ) <= k;
+            const unsigned int liveC = (__ballot_sync(0xffffffffu, c0_live) >> gb) & gmask;
+            const unsigned int liveZ = (__ballot_sync(0xffffffffu, z0_live) >> gb) & gmask;
+            int chunk0, chunk_n;  // the chunk that holds the last live node (window-relative), its length
+            if (liveC) {
+                chunk0 = 32 + (31 - __clz(liveC)) * BC;
+                chunk_n = BC;
+            } else {
+                chunk0 = liveZ ? (31 - __clz(liveZ)) * BZ : 0;
+                chunk_n = liveZ ? BZ : 0;
+            }
+            int n_live = 0;
+            constexpr int kScanRounds = (BCMAX + LG - 1) / LG;
+#pragma unroll
+            for (int rr = 0; rr < kScanRounds; ++rr) {
+                const int e = gl + LG * rr;
+                bool live = false;
+                if (e < chunk_n) live = tile[zone_pad(chunk0 + e)] > thr && (w0 + chunk0 + e) <= k;
+                n_live += __popc((__ballot_sync(0xffffffffu, live) >> gb) & gmask);
+            }
+            int jhi = w0 + chunk0 + n_live;
             if (jhi < jlo) jhi = jlo;
             // the window bottom must still be inside the exercise region (or be node 0)
             if (w0 > 0 && jlo <= w0) fail = true;
@@ -765,13 +789,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, (G == 4) ? 4 : 5) crr_zone_ke
             }
             const int Mn = __reduce_max_sync(0xffffffffu, need);
             const int BCn = G * Mn;
-            // ---- re-pack level k from (w0, M) to (w0n, Mn), node-ordered tile per option -----------
-#pragma unroll
-            for (int i = 0; i < BZ; ++i) tile[gl * BZ + i] = z[i];
-#pragma unroll
-            for (int i = 0; i < BCMAX; ++i)
-                if (i < BC) tile[32 + gl * BC + i] = c[i];
-            __syncwarp();
+            // ---- re-pack level k from (w0, M) to (w0n, Mn) ------------------------------------------
             const int width_old = 32 * (1 + M);
             // this lane's first Z node of the new layout at level k: sgn*S0*u^(2j - k)
             const double sb = L.sgn * L.S0 * exp(ln_u * (double)(2 * (w0n + quad0) - k));
@@ -782,7 +800,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, (G == 4) ? 4 : 5) crr_zone_ke
                 double val;
                 if (jr < 0) val = fma(sb, ulo[i], L.sK);           // below the old window: exercise
                 else if (jr >= width_old || j >= top) val = 0.0;   // above the band
-                else val = tile[jr];
+                else val = tile[zone_pad(jr)];
                 z[i] = val;
             }
 #pragma unroll
@@ -790,21 +808,30 @@ __global__ void __launch_bounds__(kZoneWarps * 32, (G == 4) ? 4 : 5) crr_zone_ke
                 if (i < BCn) {
                     const int j = w0n + 32 + gl * BCn + i;
                     const int jr = j - w0;
-                    c[i] = (jr < 0 || jr >= width_old || j >= top) ? 0.0 : tile[jr];
+                    c[i] = (jr < 0 || jr >= width_old || j >= top) ? 0.0 : tile[zone_pad(jr)];
                 }
             }
             __syncwarp();
             w0 = w0n;
             M = Mn;
             int n_ex0 = 0, n_exT = 0;
+            double back = back_full;
+            if (nlev != kZoneSeg) {  // last, partial segment: pd^nlev by square-and-multiply
+                back = 1.0;
+                double sq = L.pd;
+                for (int e = nlev; e > 0; e >>= 1) {
+                    if (e & 1) back *= sq;
+                    sq *= sq;
+                }
+            }
             switch (M) {
-                case 0: exmask = zone_segment<G, 0>(z, c, ulo, L, gl, src, sb, nlev, n_chk, n_ex0, n_exT); break;
-                case 1: exmask = zone_segment<G, 1>(z, c, ulo, L, gl, src, sb, nlev, n_chk, n_ex0, n_exT); break;
-                case 2: exmask = zone_segment<G, 2>(z, c, ulo, L, gl, src, sb, nlev, n_chk, n_ex0, n_exT); break;
-                case 3: exmask = zone_segment<G, 3>(z, c, ulo, L, gl, src, sb, nlev, n_chk, n_ex0, n_exT); break;
-                case 4: exmask = zone_segment<G, 4>(z, c, ulo, L, gl, src, sb, nlev, n_chk, n_ex0, n_exT); break;
-                case 5: exmask = zone_segment<G, 5>(z, c, ulo, L, gl, src, sb, nlev, n_chk, n_ex0, n_exT); break;
-                default: exmask = zone_segment<G, 6>(z, c, ulo, L, gl, src, sb, nlev, n_chk, n_ex0, n_exT); break;
+                case 0: exmask = zone_segment<G, 0>(z, c, ulo, L, gl, src, sb, nlev, n_chk, back, n_ex0, n_exT); break;
+                case 1: exmask = zone_segment<G, 1>(z, c, ulo, L, gl, src, sb, nlev, n_chk, back, n_ex0, n_exT); break;
+                case 2: exmask = zone_segment<G, 2>(z, c, ulo, L, gl, src, sb, nlev, n_chk, back, n_ex0, n_exT); break;
+                case 3: exmask = zone_segment<G, 3>(z, c, ulo, L, gl, src, sb, nlev, n_chk, back, n_ex0, n_exT); break;
+                case 4: exmask = zone_segment<G, 4>(z, c, ulo, L, gl, src, sb, nlev, n_chk, back, n_ex0, n_exT); break;
+                case 5: exmask = zone_segment<G, 5>(z, c, ulo, L, gl, src, sb, nlev, n_chk, back, n_ex0, n_exT); break;
+                default: exmask = zone_segment<G, 6>(z, c, ulo, L, gl, src, sb, nlev, n_chk, back, n_ex0, n_exT); break;
             }
             // everything below the window is an exercise node only while the window's bottom node
             // chose exercise at EVERY level; everything in C is a continuation node only while Z's
