@@ -54,7 +54,8 @@ def _stale(target, sources):
 def _compile(nvcc, unit, extra, verbose):
     src = os.path.join(CSRC, unit)
     obj = os.path.join(OBJ_DIR, unit.replace(".cu", ".o"))
-    cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", src, "-o", obj]
+    # OPTP_NVCC_FLAGS: extra flags for experiments (e.g. -DOPTP_ZONE_MINB4=5); use with --force
+    cmd = [nvcc, *ARCH, *COMMON, *extra, *os.environ.get("OPTP_NVCC_FLAGS", "").split(), "-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
     with open(obj + ".log", "w") as f:

@@ -574,6 +574,9 @@ __global__ void __launch_bounds__(kBandWarps * 32, 5) crr_band_kernel(CrrArgs a)
 //  (3) The schedule is FIXED -- segments of kZoneSeg levels counted from level N, rigorous margin --
 //      so the arithmetic applied to a contract does not depend on its warp mates or on G: a
 //      contract's price is bit-identical whatever batch it is priced in.
+#ifndef OPTP_ZONE_MINB4
+#define OPTP_ZONE_MINB4 4
+#endif
 constexpr int kZoneWarps = 4;
 constexpr int kZoneSeg = 28;      // levels per segment: Z = [jlo - 30, jlo + 2), margin kZoneSeg + 2 below the boundary
 constexpr int kZoneMaxM = 6;      // C zone up to 192 nodes
@@ -645,7 +648,7 @@ __device__ __forceinline__ unsigned int zone_segment(double (&z)[G], double (&c)
 }
 
 template <int G>
-__global__ void __launch_bounds__(kZoneWarps * 32, (G == 4) ? 4 : 5) crr_zone_kernel(CrrArgs a) {
+__global__ void __launch_bounds__(kZoneWarps * 32, (G == 4) ? OPTP_ZONE_MINB4 : 5) crr_zone_kernel(CrrArgs a) {
     constexpr int LG = 32 / G, BZ = G, BCMAX = G * kZoneMaxM;
     __shared__ double tiles[kZoneWarps][G * kZoneGroupTile];
     const int lane = threadIdx.x & 31;

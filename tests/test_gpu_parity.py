@@ -183,33 +183,53 @@ def test_crr_ragged_sizes_against_oracle(op, N):
 
 
 def test_crr_banded_kernel_equals_full_width_kernel(op):
-    """The banded American-put kernel (exercise-region / zero-region cuts) against the full-width
-    kernel on the same contracts, including the corners of parameter space: deep in / out of the
-    money, tiny and long maturities, low and high volatility, q > 0, r <= q (declined -> fallback)."""
+    """The banded American-put kernels (exercise-region / zero-region cuts; two-zone kernel with 1, 2
+    and 4 options per warp, and the earlier single-zone kernel) against the full-width kernel on the
+    same contracts, including the corners of parameter space: deep in / out of the money, tiny and
+    long maturities, low and high volatility, q > 0, r <= q (declined -> fallback)."""
     from optpricer_b200 import _native as nv
     g = np.random.default_rng(99)
     n = 30_000
     S0 = g.uniform(20, 300, n); K = S0 * np.exp(g.uniform(-1.2, 1.2, n)); T = np.exp(g.uniform(np.log(0.01), np.log(5.0), n))
     sig = g.uniform(0.05, 0.9, n); r = g.uniform(0.0005, 0.12, n); q = np.where(g.random(n) < 0.5, 0.0, g.uniform(0.0, 0.1, n))
     is_call = (g.random(n) < 0.2).astype(np.uint8)
-    for N in (1000, 257, 64, 5):
-        banded, st_b = op.crr_batch(S0, K, T, r, q, sig, is_call, N, american=True, return_status=True)
-        nv.set_option("crr_band", 0)
-        try:
+    try:
+        for N in (1000, 257, 64, 29, 28, 5):
+            nv.set_option("crr_band", 0)
             full, st_f = op.crr_batch(S0, K, T, r, q, sig, is_call, N, american=True, return_status=True)
-        finally:
             nv.set_option("crr_band", 1)
-        np.testing.assert_array_equal(st_b, st_f)
-        ok = st_f == 0
-        np.testing.assert_allclose(banded[ok], full[ok], rtol=REL_CRR, atol=REL_CRR)
+            ok = st_f == 0
+            zone = {}
+            for G in (1, 2, 4):
+                nv.set_option("crr_zone_group", G)
+                zone[G], st_b = op.crr_batch(S0, K, T, r, q, sig, is_call, N, american=True, return_status=True)
+                np.testing.assert_array_equal(st_b, st_f)
+                np.testing.assert_allclose(zone[G][ok], full[ok], rtol=REL_CRR, atol=REL_CRR)
+            # the arithmetic applied to a contract does not depend on the lane layout or on its warp mates
+            np.testing.assert_array_equal(zone[1][ok], zone[2][ok])
+            np.testing.assert_array_equal(zone[1][ok], zone[4][ok])
+            nv.set_option("crr_zone_group", 4)
+            perm = g.permutation(n)
+            shuffled = op.crr_batch(S0[perm], K[perm], T[perm], r[perm], q[perm], sig[perm], is_call[perm], N, american=True)
+            np.testing.assert_array_equal(shuffled[ok[perm]], zone[4][perm][ok[perm]])
+            nv.set_option("crr_zone_group", 0)
+            nv.set_option("crr_band_kernel", 1)   # the single-zone banded kernel
+            single, st_s = op.crr_batch(S0, K, T, r, q, sig, is_call, N, american=True, return_status=True)
+            nv.set_option("crr_band_kernel", 2)
+            np.testing.assert_array_equal(st_s, st_f)
+            np.testing.assert_allclose(single[ok], full[ok], rtol=REL_CRR, atol=REL_CRR)
+    finally:
+        nv.set_option("crr_band", 1)
+        nv.set_option("crr_band_kernel", 2)
+        nv.set_option("crr_zone_group", 0)
     # how much of a typical book the banded kernel actually takes (config-2 contracts: all of it)
     S0, K, T, r, q, sig, is_call = crr_tree.cfg2_contracts(20_000)
     nv.set_option("crr_band_only", 1)
     try:
         _, st = op.crr_batch(S0, K, T, r, q, sig, is_call, 1000, american=True, return_status=True)
+        assert np.count_nonzero(st == 2) == 0
     finally:
         nv.set_option("crr_band_only", 0)
-    assert np.count_nonzero(st == 2) == 0
 
 
 def test_crr_batch_flags_bad_contracts_without_aborting(op):
