@@ -539,10 +539,11 @@ def main():
                              "fp64_frac": crr_rate_gpu * CRR_FP64_OPS_PER_OPTION / peaks["fp64_dfma_lane_ops"],
                              "note": "ALGORITHMIC figures (500 500 node updates x 24 B / x 5 FP64 ops per option) over "
                                      "measured LDS.64 bandwidth / DFMA rate. They exceed 1 because (a) tree levels live in "
-                                     "registers, not shared memory, and (b) the banded kernel updates only the nodes between "
-                                     "the early-exercise boundary and the 2^-80 K zero region (about 150k of the 500k node "
-                                     "updates, profiles/), with prices equal to the full-width kernel to 1e-10 "
-                                     "(tests/test_gpu_parity.py::test_crr_banded_kernel_equals_full_width_kernel). The "
+                                     "registers, not shared memory, and (b) the two-zone banded kernel updates only the nodes "
+                                     "between the early-exercise boundary and the 2^-80 K zero region (about 140k of the 500k "
+                                     "node updates; only the 32 nodes next to the boundary take the exercise test, the rest "
+                                     "cost one DFMA), four options per warp, with prices equal to the full-width kernel to "
+                                     "1e-10 (tests/test_gpu_parity.py::test_crr_banded_kernel_equals_full_width_kernel). The "
                                      "physical pipe fraction is `full_width.fp64_frac`.",
                              "peak_source": "optp_microbench LDS.64 bandwidth / DFMA rate measured in this run"},
                 "full_width": {"value": crr_full_rate * world, "unit": "options/s", "ms_per_step": crr_full_ms,

@@ -1026,26 +1026,54 @@ extern "C" int optp_crr_batch(const double* S0, const double* K, const double* T
     if (int e = arena_reserve(c.in0, 6 * colp + n + 256)) return e;
     if (int e = arena_reserve(c.out0, colp + n + 256)) return e;
     char* in = (char*)c.in0.p;
-    const double* src[6] = {S0, K, T, r, q, sigma};
-    for (int i = 0; i < 6; ++i)
-        OPTP_CUDA(cudaMemcpyAsync(in + i * colp, src[i], col, cudaMemcpyHostToDevice, c.stream));
-    OPTP_CUDA(cudaMemcpyAsync(in + 6 * colp, is_call, n, cudaMemcpyHostToDevice, c.stream));
     char* out = (char*)c.out0.p;
-    CrrArgs a{(const double*)(in),
-              (const double*)(in + colp),
-              (const double*)(in + 2 * colp),
-              (const double*)(in + 3 * colp),
-              (const double*)(in + 4 * colp),
-              (const double*)(in + 5 * colp),
-              (const uint8_t*)(in + 6 * colp),
-              (unsigned long long)n,
-              (int)N,
-              (double*)out,
-              (uint8_t*)(out + colp),
-              0};
-    if (int e = launch_crr(a, american, c.stream)) return e;
-    OPTP_CUDA(cudaMemcpyAsync(price_out, out, col, cudaMemcpyDeviceToHost, c.stream));
-    OPTP_CUDA(cudaMemcpyAsync(status_out, out + colp, n, cudaMemcpyDeviceToHost, c.stream));
+    const double* src[6] = {S0, K, T, r, q, sigma};
+    // Large batches are walked in slices on two streams, so the host->device copy of slice i+1 and
+    // the device->host copy of slice i-1 overlap the kernel of slice i.  A contract's price does not
+    // depend on the slice it is in (every kernel prices a contract from its own columns only).
+    const uint64_t slice = 1ull << 17;
+    const bool pipelined = n >= 4 * slice;
+    if (pipelined && !c.stream2)
+        OPTP_CUDA(cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking));
+    const uint64_t step = pipelined ? slice : n;
+    // The device->host copy of a slice is issued AFTER the next slice has been queued: a copy into
+    // pageable host memory blocks the calling thread until it is done.
+    auto copy_back = [&](uint64_t lo, uint64_t m, cudaStream_t st) -> int {
+        OPTP_CUDA(cudaMemcpyAsync(price_out + lo, (double*)out + lo, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+        OPTP_CUDA(cudaMemcpyAsync(status_out + lo, out + colp + lo, m, cudaMemcpyDeviceToHost, st));
+        return 0;
+    };
+    int which = 0;
+    uint64_t prev_lo = 0, prev_m = 0;
+    cudaStream_t prev_st = nullptr;
+    for (uint64_t lo = 0; lo < n; lo += step, which ^= 1) {
+        const uint64_t m = (n - lo < step) ? (n - lo) : step;
+        cudaStream_t st = (pipelined && which) ? c.stream2 : c.stream;
+        for (int i = 0; i < 6; ++i)
+            OPTP_CUDA(cudaMemcpyAsync(in + i * colp + lo * sizeof(double), src[i] + lo, m * sizeof(double),
+                                      cudaMemcpyHostToDevice, st));
+        OPTP_CUDA(cudaMemcpyAsync(in + 6 * colp + lo, is_call + lo, m, cudaMemcpyHostToDevice, st));
+        CrrArgs a{(const double*)(in) + lo,
+                  (const double*)(in + colp) + lo,
+                  (const double*)(in + 2 * colp) + lo,
+                  (const double*)(in + 3 * colp) + lo,
+                  (const double*)(in + 4 * colp) + lo,
+                  (const double*)(in + 5 * colp) + lo,
+                  (const uint8_t*)(in + 6 * colp) + lo,
+                  (unsigned long long)m,
+                  (int)N,
+                  (double*)out + lo,
+                  (uint8_t*)(out + colp) + lo,
+                  0};
+        if (int e = launch_crr(a, american, st)) return e;
+        if (prev_m)
+            if (int e = copy_back(prev_lo, prev_m, prev_st)) return e;
+        prev_lo = lo;
+        prev_m = m;
+        prev_st = st;
+    }
+    if (int e = copy_back(prev_lo, prev_m, prev_st)) return e;
     OPTP_CUDA(cudaStreamSynchronize(c.stream));
+    if (pipelined) OPTP_CUDA(cudaStreamSynchronize(c.stream2));
     return 0;
 }

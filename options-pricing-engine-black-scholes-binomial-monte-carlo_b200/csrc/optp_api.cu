@@ -120,6 +120,7 @@ int optp_shutdown(void) {
     cudaFree(c.stats_dev);
     cudaFreeHost(c.stats_host);
     cudaStreamDestroy(c.stream);
+    if (c.stream2) cudaStreamDestroy(c.stream2);
     c = Context();
     return 0;
 }

@@ -20,6 +20,7 @@ struct Context {
     bool ready = false;
     int n_sm = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // second stream of the sliced CRR batch pipeline (created on demand)
     double* partials = nullptr;   // [kMaxBlocks][kMaxVals]
     unsigned int* ticket = nullptr;
     double* stats_dev = nullptr;  // kMaxPayoffs * OPTP_NSTATS
