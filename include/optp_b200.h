@@ -107,6 +107,9 @@ uint64_t optp_launch_count(void);
  *                   grid cell (default), 0 = always the three-lookup (value, slope) path
  *   "crr_band_only" 1 = skip the full-width fallback pass; contracts the banded kernel declined
  *                   keep status 2 (diagnostics only)
+ *   "crr_band_kernel" 2 = two-zone banded kernel (default), 1 = the earlier single-zone banded kernel
+ *   "crr_zone_group"  options per warp of the two-zone kernel: 1, 2, 4, or 0 = by batch size (default);
+ *                   prices are bit-identical for every setting
  * Returns OPTP_E_ARG for an unknown key. */
 int optp_set_option(const char* key, long value);
 /* Pinned host staging memory for callers that want DMA-able buffers. */
