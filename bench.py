@@ -481,6 +481,20 @@ def main():
                           "contracts_per_s": n_rows / book_s, "seconds": book_s,
                           "priced": sum(1 for r in priced if r.get("price") is not None),
                           "checksum": float(sum(r["price"] for r in priced[:100]))})
+        # the bump-and-reprice caller (risk.py:146-203) over a 20k-instrument book,
+        # 8 reprices each, N=500 American trees, as ONE device batch
+        from optpricer_b200 import risk as rk
+        rS0, rK, rT, rr, rq, rsig, _ = cfg2_contracts(20_000, seed=3)
+        book_r = [dict(S=float(rS0[i]), K=float(rK[i]), T=float(rT[i]), r=float(rr[i]), q=0.0, sigma=float(rsig[i]),
+                       kind="put", position=1.0) for i in range(20_000)]
+        tp = rk.TreePricer(500, american=True)
+        rk.portfolio_risk(book_r[:100], tp)
+        t0 = time.perf_counter()
+        pr_ = rk.portfolio_risk(book_r, tp)
+        risk_s = time.perf_counter() - t0
+        workloads.append({"workload": "portfolio_risk (risk.py:146-203) on 20k American puts, N=500 trees, 8 reprices each, one batch",
+                          "value": 8 * 20_000 / risk_s, "unit": "tree reprices/s (end to end, incl. Python)",
+                          "seconds": risk_s, "total_delta": pr_["total_delta"], "total_value": pr_["total_value"]})
         # cfg 1 as is: latency of one euro_price_mc call (200k paths) through the public API
         opt = __import__("optpricer_b200").OptionSpec(100.0, 110.0, 1.0, 0.03, 0.2)
         mc.euro_price_mc(opt, "call", n_paths=200_000, seed=1)

@@ -12,6 +12,8 @@ from .binomial import crr, crr_vec, crr_batch
 from .exotics import barrier_price, asian_price, digital_price, lookback_price, price_payoffs
 from .processes import (gbm_paths, heston_paths, milstein_local_vol_paths, local_vol_paths,
                         gbm_milstein_paths, sabr_paths, merton_jump_paths, SigmaTable, LazyPaths)
+from .risk import TreePricer, McPricer, numerical_greeks, scenario_grid, portfolio_risk
+from .validation import stress_test, convergence_analysis
 from ._native import NativeUnavailable
 
 __version__ = "0.1.0"
@@ -21,4 +23,6 @@ __all__ = [
     "barrier_price", "asian_price", "digital_price", "lookback_price", "price_payoffs",
     "gbm_paths", "heston_paths", "milstein_local_vol_paths", "local_vol_paths",
     "gbm_milstein_paths", "sabr_paths", "merton_jump_paths", "SigmaTable", "LazyPaths", "NativeUnavailable",
+    "TreePricer", "McPricer", "numerical_greeks", "scenario_grid", "portfolio_risk", "stress_test",
+    "convergence_analysis",
 ]
