@@ -129,6 +129,45 @@ def _cpu_crr_task(args):
     return hi - lo, time.perf_counter() - t0, float(p[0])
 
 
+def _cpu_crr_c_task(args):
+    """The table-based C restatement (oracle/crr_tree.c) on a slice of config-2 contracts: what a
+    hand-optimised scalar CPU implementation of the same lattice does (not the reference's numpy path)."""
+    lo, hi = args
+    from oracle import crr_c
+    S0, K, T, r, q, sig, is_call = cfg2_contracts(hi)
+    t0 = time.perf_counter()
+    p, _ = crr_c.crr_loop_fast(S0[lo:hi], K[lo:hi], T[lo:hi], r[lo:hi], q[lo:hi], sig[lo:hi], is_call[lo:hi], CRR_N, True)
+    return hi - lo, time.perf_counter() - t0, float(p[0])
+
+
+def _cpu_extra_task(args):
+    """The other BASELINE configurations on the oracle port (SURVEY 8d CPU baseline (i) and (iii)):
+    returns (path-steps, seconds) of one bounded call."""
+    what, seed = args
+    from oracle import path_schemes, payoffs, terminal_mc, sigma_grid
+    t0 = time.perf_counter()
+    if what == "terminal":     # cfg 1: euro_price_mc, chunks of 100k as the reference streams them
+        n_paths = 2_000_000
+        terminal_mc.euro_mc(100.0, 110.0, 1.0, 0.03, 0.2, 0.0, "call", n_paths=n_paths, seed=seed)
+        units = 2 * n_paths
+    elif what == "heston_asian":   # cfg 4: heston_paths + asian_price, 365 steps
+        n_steps, n_base = 365, 10_000
+        z2, zp = path_schemes.draw_normals(seed, n_steps, n_base, 2)
+        paths = path_schemes.heston_fte(z2, zp, S0=100.0, r=0.05, q=0.0, v0=0.04, kappa=2.0, theta=0.04, xi=0.3,
+                                        rho=-0.7, T=1.0)
+        payoffs.asian(paths, 100.0, 0.05, 1.0, "call")
+        units = 2 * n_base * n_steps
+    else:                          # cfg 3: milstein_local_vol_paths on the tabulated Dupire surface + barrier_price
+        n_steps, n_base = 252, 10_000
+        z = np.load(os.path.join(ROOT, "tests", "golden", "dupire_table_252x256.npz"))
+        grid = sigma_grid.SigmaGrid(z["table"], float(z["x0"]), float(z["h"]), float(z["dt"]))
+        (zz,) = path_schemes.draw_normals(seed, n_steps, n_base)
+        paths = path_schemes.lv_milstein(zz, grid, S0=100.0, r=0.05, q=0.02, T=1.0)
+        payoffs.barrier(paths, 100.0, 0.05, 1.0, "call", 130.0, "up-and-out")
+        units = 2 * n_base * n_steps
+    return units, time.perf_counter() - t0
+
+
 def cpu_step(pool, workers, mc_base, crr_per_worker, step):
     """One bounded sample of each workload on `workers` host processes; returns units and seconds."""
     t0 = time.perf_counter()
@@ -154,6 +193,13 @@ def cpu_baseline_single_core():
     n, dt, _ = _cpu_crr_task((0, 160))
     crr = {"value": n / dt, "unit": "options/s", "cores": 1, "kind": "port",
            "sample": "oracle crr_loop (numpy restatement of binomial.py:7-38) on the first 160 config-2 contracts"}
+    try:
+        nc, dtc, _ = _cpu_crr_c_task((0, 4000))
+        crr["optimised_c"] = {"value": nc / dtc, "unit": "options/s", "cores": 1, "kind": "port",
+                              "sample": "oracle/crr_tree.c table-based loop (no pow() per node, gcc -O2) on the first "
+                                        "4000 config-2 contracts; NOT the reference's numpy path"}
+    except Exception as e:  # the C oracle is optional test infrastructure
+        crr["optimised_c"] = {"unavailable": str(e)[:200]}
     return mc, crr
 
 
@@ -171,6 +217,24 @@ def reference_arm(args):
         for s in range(args.steps):
             a, b, c, d = cpu_step(pool, workers, mc_base, crr_per, 100 + s)
             u_mc += a; t_mc += b; u_crr += c; t_crr += d
+        try:
+            t0 = time.perf_counter()
+            cc = list(pool.map(_cpu_crr_c_task, [(w * 2000, (w + 1) * 2000) for w in range(workers)]))
+            crr_c_v = sum(c[0] for c in cc) / (time.perf_counter() - t0)
+        except Exception:
+            crr_c_v = None
+        extra = []
+        for what, label in (("terminal", "cfg1 euro_price_mc (terminal GBM, antithetic + CV), 2M paths per process"),
+                            ("heston_asian", "cfg4 heston_paths + asian_price, 365 steps x 10k base paths per process"),
+                            ("lvm_barrier", "cfg3 milstein_local_vol_paths (tabulated Dupire sigma) + barrier_price, "
+                                            "252 steps x 10k base paths per process")):
+            try:
+                t0 = time.perf_counter()
+                res = list(pool.map(_cpu_extra_task, [(what, 7 + w) for w in range(workers)]))
+                extra.append({"workload": label, "value": sum(x[0] for x in res) / (time.perf_counter() - t0),
+                              "unit": "path-steps/s", "cores": workers, "kind": "port"})
+            except Exception as e:
+                extra.append({"workload": label, "unavailable": str(e)[:200]})
     mc_v, crr_v = u_mc / t_mc, u_crr / t_crr
     sample_mc = f"{workers} processes x (252 steps x {mc_base} base paths + mirrors) per step, oracle numpy port"
     sample_crr = f"{workers} processes x {crr_per} config-2 contracts per step, oracle numpy port"
@@ -186,7 +250,11 @@ def reference_arm(args):
                 "ms_per_step": 1e3 * t_crr / args.steps,
                 "cpu_baseline": {"value": crr_v, "unit": "options/s", "cores": workers, "kind": "port",
                                  "sample": sample_crr},
+                "optimised_c": {"value": crr_c_v, "unit": "options/s", "cores": workers, "kind": "port",
+                                "sample": f"{workers} processes x 2000 config-2 contracts, oracle/crr_tree.c table-based "
+                                          "loop (not the reference's numpy path)"},
                 "e2e": {"value": crr_v, "unit": "options/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
+        "workloads": extra,
         "gpu_launches": 0,
     }
     print(json.dumps(line))

@@ -7,7 +7,7 @@ Restates reference src/optpricer/binomial.py:
                      loop over crr_scalar (the reference has no batched heterogeneous API).
 Same operation order as the reference (d = 1/u, disc applied after the weighted sum,
 exercise value recomputed with two pow() per node) so values are bit-identical.
-A faster C restatement of the same recursion lives in oracle/crr_tree.c.
+A C restatement of the same recursion lives in oracle/crr_tree.c (loader: oracle/crr_c.py).
 """
 from __future__ import annotations
 

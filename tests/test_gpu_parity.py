@@ -166,6 +166,20 @@ def test_crr_cfg2_batch_against_reference_and_oracle(op):
     np.testing.assert_array_equal(again, price[100:229])
 
 
+def test_crr_cfg2_sample_against_c_oracle(op):
+    """8192 config-2 contracts at N = 1000 (American and European) against the table-based C
+    restatement (oracle/crr_tree.c, itself pinned to the reference fixtures at 1e-11)."""
+    from oracle import crr_c
+    S0, K, T, r, q, sig, is_call = crr_tree.cfg2_contracts(1_000_000)
+    sl = slice(500_000, 508_192)
+    cols = [a[sl] for a in (S0, K, T, r, q, sig, is_call)]
+    for american in (True, False):
+        want, st_w = crr_c.crr_loop_fast(*cols, 1000, american)
+        got, st_g = op.crr_batch(*cols, 1000, american=american, return_status=True)
+        np.testing.assert_array_equal(st_g, st_w)
+        np.testing.assert_allclose(got, want, rtol=REL_CRR, atol=REL_CRR)
+
+
 @pytest.mark.parametrize("N", [1, 2, 31, 32, 33, 255, 256, 257, 1000, 1023, 1024, 1500])
 def test_crr_ragged_sizes_against_oracle(op, N):
     g = np.random.default_rng(N)

@@ -58,6 +58,35 @@ def test_crr_cases():
         assert all(close(float(a), b) for a, b in zip(v, c["prices"]))
 
 
+def test_crr_c_restatement_against_reference_fixtures():
+    """oracle/crr_tree.c: the reference-order loop to 1e-13, the table-based loop to 1e-11."""
+    from oracle import crr_c
+    g = load_json("crr.json")
+    ok = [c for c in g["cases"] if "error" not in c and c["N"] <= 1024]
+    bad = [c for c in g["cases"] if "error" in c and c["N"] > 0]
+    for american in (True, False):
+        for N in sorted({c["N"] for c in ok}):
+            grp = [c for c in ok + bad if c["N"] == N and c["american"] == american]
+            if not grp:
+                continue
+            cols = [[c[k] for c in grp] for k in ("S0", "K", "T", "r", "q", "sigma")]
+            call = [1 if c["kind"] == "call" else 0 for c in grp]
+            for fn, tol in ((crr_c.crr_loop_ref, 1e-13), (crr_c.crr_loop_fast, 1e-11)):
+                if fn is crr_c.crr_loop_ref and N > 300:
+                    continue   # two pow() per node: keep the CPU suite short
+                price, status = fn(*cols, call, N, american)
+                for c, p, st in zip(grp, price, status):
+                    if "error" in c:
+                        assert st == 1 and p != p, c
+                    else:
+                        assert st == 0 and abs(p - c["price"]) <= tol * max(1.0, abs(c["price"])), (c, p)
+    S0, K, T, r, q, sig, is_call = crr_tree.cfg2_contracts(1_000_000)
+    price, _ = crr_c.crr_loop_fast(S0[:64], K[:64], T[:64], r[:64], q[:64], sig[:64], is_call[:64], 1000, True)
+    np.testing.assert_allclose(price, g["cfg2_first64_american_put_N1000"], rtol=1e-11)
+    with pytest.raises(ValueError, match="N must be positive."):
+        crr_c.crr_loop_ref([100.0], [100.0], [1.0], [0.05], [0.0], [0.2], [1], 0, False)
+
+
 def _grid_from_samples(npz):
     x0, h, dt = npz["lvm_table/grid"]
     return sigma_grid.SigmaGrid(npz["lvm_table/table"], x0, h, dt)
