@@ -78,88 +78,113 @@ class McPricer:
         return out
 
 
-def _price_points(pricer_func, points):
-    """points: list of (S, K, T, r, q, sigma, kind) -> list of floats."""
-    if not points:
-        return []
+def _price_points(pricer_func, cols, kinds):
+    """cols: six equal-length float arrays (S, K, T, r, q, sigma); kinds: list of str -> float array."""
+    n = len(kinds)
+    if n == 0:
+        return np.empty(0)
     if hasattr(pricer_func, "batch"):
-        cols = list(zip(*points))
-        return [float(v) for v in pricer_func.batch(*[list(c) for c in cols])]
-    return [float(pricer_func(*p)) for p in points]
+        return np.asarray(pricer_func.batch(*cols, kinds), dtype=float)
+    return np.array([float(pricer_func(*[float(c[i]) for c in cols], kinds[i])) for i in range(n)])
 
 
 _DT = 1.0 / 365.0
+_SLOTS = 8   # P0, S up, S down, vol up, vol down, T - 1 day, r up, r down (risk.py:57-85, in that order)
 
 
-def _greek_points(S, K, T, r, q, sigma, kind, bump_pct):
-    """The reprice points of risk.py:57-85, in the reference's evaluation order."""
+def _greek_points(S, K, T, r, q, sigma, bump_pct):
+    """The reprice points of risk.py:57-85 for n contracts at once: six (n, 8) arrays, the bump sizes and
+    the theta mask.  Contracts with T <= 1 day have no theta point (risk.py:74-79); their slot repeats the
+    unbumped contract and is ignored."""
+    S, K, T, r, q, sigma = [np.asarray(x, dtype=float).reshape(-1) for x in (S, K, T, r, q, sigma)]
     eps_S = bump_pct * S
-    eps_v = max(bump_pct * sigma, 1e-4)
+    eps_v = np.maximum(bump_pct * sigma, 1e-4)
     eps_r = bump_pct
-    pts = [(S, K, T, r, q, sigma, kind),
-           (S + eps_S, K, T, r, q, sigma, kind), (S - eps_S, K, T, r, q, sigma, kind),
-           (S, K, T, r, q, sigma + eps_v, kind), (S, K, T, r, q, max(sigma - eps_v, 1e-6), kind)]
     has_theta = T > _DT
-    if has_theta:
-        pts.append((S, K, T - _DT, r, q, sigma, kind))
-    pts += [(S, K, T, r + eps_r, q, sigma, kind), (S, K, T, r - eps_r, q, sigma, kind)]
-    return pts, (eps_S, eps_v, eps_r, has_theta)
+    rep = lambda x: np.repeat(x[:, None], _SLOTS, axis=1)  # noqa: E731
+    Sm, Km, Tm, rm, qm, vm = rep(S), rep(K), rep(T), rep(r), rep(q), rep(sigma)
+    Sm[:, 1] = S + eps_S
+    Sm[:, 2] = S - eps_S
+    vm[:, 3] = sigma + eps_v
+    vm[:, 4] = np.maximum(sigma - eps_v, 1e-6)
+    Tm[:, 5] = np.where(has_theta, T - _DT, T)
+    rm[:, 6] = r + eps_r
+    rm[:, 7] = r - eps_r
+    return (Sm, Km, Tm, rm, qm, vm), (eps_S, eps_v, eps_r, has_theta)
 
 
 def _greeks_from_prices(P, eps):
+    """P: (n, 8) prices -> dict of (n,) arrays."""
     eps_S, eps_v, eps_r, has_theta = eps
-    P0, P_up, P_dn, P_vup, P_vdn = P[:5]
-    i = 5
-    theta = 0.0
-    if has_theta:
-        theta = (P[5] - P0) / _DT
-        i = 6
-    P_rup, P_rdn = P[i], P[i + 1]
-    return {"delta": float((P_up - P_dn) / (2.0 * eps_S)),
-            "gamma": float((P_up - 2.0 * P0 + P_dn) / (eps_S ** 2)),
-            "vega": float((P_vup - P_vdn) / (2.0 * eps_v)),
-            "theta": float(theta),
-            "rho": float((P_rup - P_rdn) / (2.0 * eps_r))}
+    return {"delta": (P[:, 1] - P[:, 2]) / (2.0 * eps_S),
+            "gamma": (P[:, 1] - 2.0 * P[:, 0] + P[:, 2]) / (eps_S ** 2),
+            "vega": (P[:, 3] - P[:, 4]) / (2.0 * eps_v),
+            "theta": np.where(has_theta, (P[:, 5] - P[:, 0]) / _DT, 0.0),
+            "rho": (P[:, 6] - P[:, 7]) / (2.0 * eps_r)}
+
+
+def _reprice(pricer_func, S, K, T, r, q, sigma, kinds, bump_pct):
+    mats, eps = _greek_points(S, K, T, r, q, sigma, bump_pct)
+    if not hasattr(pricer_func, "batch"):
+        # a plain callable is evaluated exactly where the reference evaluates it (no theta point for
+        # contracts inside their last day)
+        P = np.empty(mats[0].shape)
+        for i in range(P.shape[0]):
+            for j in range(_SLOTS):
+                if j == 5 and not eps[3][i]:
+                    P[i, j] = P[i, 0]
+                else:
+                    P[i, j] = float(pricer_func(*[float(m[i, j]) for m in mats], kinds[i]))
+        return P, eps
+    flat_kinds = [k for k in kinds for _ in range(_SLOTS)]
+    P = _price_points(pricer_func, [m.reshape(-1) for m in mats], flat_kinds).reshape(mats[0].shape)
+    return P, eps
 
 
 def numerical_greeks(pricer_func, S, K, T, r, q, sigma, kind, *, bump_pct=0.01):
     """Greeks via central finite differences on an arbitrary pricer (risk.py:27-92).
     Keys: delta, gamma, vega, theta, rho."""
-    pts, eps = _greek_points(S, K, T, r, q, sigma, kind, bump_pct)
-    return _greeks_from_prices(_price_points(pricer_func, pts), eps)
+    P, eps = _reprice(pricer_func, [S], [K], [T], [r], [q], [sigma], [kind], bump_pct)
+    return {k: float(v[0]) for k, v in _greeks_from_prices(P, eps).items()}
 
 
 def scenario_grid(pricer_func, S, K, T, r, q, sigma, kind, spot_range, vol_range):
     """Evaluate a pricer across a 2-D (spot x vol) scenario grid (risk.py:99-139)."""
     spot_range = np.asarray(spot_range, dtype=float)
     vol_range = np.asarray(vol_range, dtype=float)
-    pts = [(float(s), K, T, r, q, float(v), kind) for s in spot_range for v in vol_range]
-    prices = np.array(_price_points(pricer_func, pts), dtype=float).reshape(len(spot_range), len(vol_range))
+    shape = (len(spot_range), len(vol_range))
+    n = shape[0] * shape[1]
+    Sg = np.broadcast_to(spot_range[:, None], shape).reshape(-1)
+    vg = np.broadcast_to(vol_range[None, :], shape).reshape(-1)
+    cols = [Sg, np.full(n, float(K)), np.full(n, float(T)), np.full(n, float(r)), np.full(n, float(q)), vg]
+    prices = _price_points(pricer_func, cols, [kind] * n).reshape(shape)
     return {"spot_values": spot_range.copy(), "vol_values": vol_range.copy(), "prices": prices}
 
 
 def portfolio_risk(instruments, pricer_func, *, bump_pct=0.01):
     """Aggregate risk for a portfolio of instruments (risk.py:146-203): dicts with keys S, K, T, r, q,
     sigma, kind, position.  All reprices of all instruments form one device batch."""
-    pts, spans = [], []
-    for inst in instruments:
-        p, eps = _greek_points(inst["S"], inst["K"], inst["T"], inst["r"], inst["q"], inst["sigma"],
-                               inst["kind"], bump_pct)
-        spans.append((len(pts), len(p), eps))
-        pts += p
-    prices = _price_points(pricer_func, pts)
+    get = lambda key: np.array([inst[key] for inst in instruments], dtype=float)  # noqa: E731
+    kinds = [inst["kind"] for inst in instruments]
+    pos = get("position")
+    if len(instruments):
+        P, eps = _reprice(pricer_func, get("S"), get("K"), get("T"), get("r"), get("q"), get("sigma"), kinds,
+                          bump_pct)
+        g = _greeks_from_prices(P, eps)
+    else:
+        P, g = np.empty((0, _SLOTS)), {k: np.empty(0) for k in ("delta", "gamma", "vega", "theta", "rho")}
     totals = {"delta": 0.0, "gamma": 0.0, "vega": 0.0, "theta": 0.0, "rho": 0.0}
     total_value = 0.0
     inst_greeks = []
-    for inst, (lo, n, eps) in zip(instruments, spans):
-        pos = inst["position"]
-        g = _greeks_from_prices(prices[lo:lo + n], eps)
-        price = prices[lo]   # risk.py:188-191 re-prices the unbumped contract: the same number
-        scaled = {k: pos * v for k, v in g.items()}
-        for k in totals:
+    names = list(totals)
+    scaled_cols = {k: (pos * g[k]).tolist() for k in names}
+    values = (pos * P[:, 0]).tolist()   # risk.py:188-191 re-prices the unbumped contract: the same number
+    for i in range(len(instruments)):   # summed in instrument order, like the reference
+        scaled = {k: scaled_cols[k][i] for k in names}
+        for k in names:
             totals[k] += scaled[k]
-        total_value += pos * price
-        inst_greeks.append({**scaled, "price": pos * price})
+        total_value += values[i]
+        inst_greeks.append({**scaled, "price": values[i]})
     return {"total_delta": totals["delta"], "total_gamma": totals["gamma"], "total_vega": totals["vega"],
             "total_theta": totals["theta"], "total_rho": totals["rho"], "total_value": total_value,
             "instrument_greeks": inst_greeks}
