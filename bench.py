@@ -530,10 +530,10 @@ def main():
                           "value": rate, "unit": "path-steps/s/GPU", "ms": ms,
                           "fp32_pipe_frac": rate * OPS_PER_PATH_STEP["terminal"] / peaks["fp32_ffma_lane_ops"],
                           "price": pt[0], "stderr": pt[1]})
-        # cfg 5: 10k-contract book (1/3 European, 1/3 barrier, 1/3 arithmetic Asian) through price_book;
-        # bounded to 2^18 base paths per contract here (BASELINE: 1e7); paths shard over the ranks
+        # cfg 5 at BASELINE size: 10k-contract book (1/3 European, 1/3 barrier, 1/3 arithmetic Asian)
+        # through price_book, 5e6 base paths (1e7 effective) per contract; paths shard over the ranks
         from optpricer_b200 import book as bk
-        n_rows, book_paths = 10_000, 1 << 18
+        n_rows, book_paths = 10_000, 5_000_000
         rows = bk.synthetic_book(n_rows, n_paths=book_paths)
         bk.price_book(rows[:200], mc_paths=book_paths)
         barrier()

@@ -672,3 +672,31 @@ def test_full_size_config4_heston_asian(op):
     assert cv[1] < plain[1] < 3e-4                                    # the control variate helps
     assert stats[0][1] >= stats[1][1]                                 # arithmetic >= geometric
     assert abs(stats[0][3] / stats[0][0] - 100.0) < 5e-3              # martingale: E[e^{-rT} S_T] = S0
+
+
+def test_full_size_config5_book(op):
+    """BASELINE config 5 at full size on ONE device: 10 000 contracts (European / barrier / arithmetic
+    Asian, price_book.py row schema), 1e7 effective paths each.  European rows against the closed form,
+    every row against a bounded re-run with another seed, plus the orderings the payoffs guarantee."""
+    from optpricer_b200 import book as bk
+    rows = bk.synthetic_book(10_000, n_paths=5_000_000)
+    out = bk.price_book(rows, mc_paths=5_000_000)
+    assert len(out) == 10_000 and all(r.get("price") is not None and math.isfinite(r["price"]) for r in out)
+    n_euro = 0
+    for row, res in zip(rows, out):
+        if row["method"] == "mc":
+            want = bk._bs_price(row["S0"], row["K"], row["T"], row["r"], row["q"], row["sigma"], row["kind"])
+            assert abs(res["price"] - want) <= 5 * res["stderr"] + 1e-4, (row, res, want)
+            n_euro += 1
+        else:
+            vanilla = bk._bs_price(row["S0"], row["K"], row["T"], row["r"], row["q"], row["sigma"], row["kind"])
+            if row["exotic_type"] == "barrier":                      # knock-out <= vanilla
+                assert -1e-9 <= res["price"] <= vanilla + 5 * res["stderr"] + 1e-3, (row, res, vanilla)
+            assert res["stderr"] < 0.02
+    assert 3000 < n_euro < 3700
+    # an independent, smaller run (other Philox key) of a sample of rows agrees within combined errors
+    pick = list(range(0, 10_000, 500))
+    again = bk.price_book([dict(rows[i], n_paths=200_000) for i in pick], mc_paths=200_000, seed=77)
+    for i, b in zip(pick, again):
+        a = out[i]
+        assert abs(a["price"] - b["price"]) <= 5 * math.hypot(a["stderr"], b["stderr"]) + 1e-4, (rows[i], a, b)
