@@ -157,6 +157,19 @@ int optp_mc_path_dev(const optp_process* proc, const optp_payoff* payoffs, uint3
                      void* stream);
 /* Stage a sigma(S,t) table (n_steps x n_nodes fp64, host) in HBM for later _dev calls. */
 int optp_sigma_table_upload(const double* table, uint32_t n_steps, uint32_t n_nodes);
+/* Tabulate the Dupire local volatility of a raw-SVI surface ON THE DEVICE and stage it like
+ * optp_sigma_table_upload does: row i = step time i*T/n_steps, node j at ln S = x0 + h*j.
+ * Replaces the host loop over the reference's callable dupire_local_vol_func(surface, r, q)
+ * (calibration.py:362-390 -> dupire_local_vol, :268-359; slices: SVIParams :14-66, surface lookup
+ * VolSurface._get_forward :108-122 and .iv_from_logm :125-148).
+ *   expiries[n_exp] ascending; svi[n_exp][5] = a, b, rho, m, sigma per slice;
+ *   (fwd_T, fwd_F)[n_fwd] the surface's forward curve (required; np.interp with flat ends);
+ *   dT = the finite-difference bump of dw/dT (reference default 1e-4);
+ *   table_out (optional, host): receives the n_steps x n_nodes fp64 table. */
+int optp_dupire_table(const double* expiries, const double* svi, uint32_t n_exp,
+                      const double* fwd_T, const double* fwd_F, uint32_t n_fwd, double T,
+                      uint32_t n_steps, double x0, double h, uint32_t n_nodes, double dT,
+                      double* table_out);
 
 /* Materialise paths for API compatibility with the generators' ndarray return value
  * (processes.py:56,162,381): paths_out is (n_steps+1, n_eff) fp64 C-order with the t=0 row;

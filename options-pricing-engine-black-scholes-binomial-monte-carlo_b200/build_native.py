@@ -32,6 +32,7 @@ UNITS = {
     "mc_fp32.cu": [],
     "mc_fp64.cu": ["-fmad=false"],
     "crr_batch.cu": [],
+    "dupire_table.cu": ["-fmad=false"],
     "microbench.cu": [],
 }
 HEADERS = ["optp_common.cuh", "mc_kernels.cuh", os.path.join("..", "..", "include", "optp_b200.h")]

@@ -28,7 +28,7 @@ EXPORTS = (
     "optp_abi_version", "optp_init", "optp_shutdown", "optp_last_error", "optp_device_count",
     "optp_launch_count", "optp_set_option", "optp_host_alloc", "optp_host_free",
     "optp_mc_terminal", "optp_mc_terminal_dev", "optp_mc_path", "optp_mc_path_dev", "optp_mc_book",
-    "optp_sigma_table_upload", "optp_paths", "optp_payoff_from_paths",
+    "optp_sigma_table_upload", "optp_dupire_table", "optp_paths", "optp_payoff_from_paths",
     "optp_crr_batch", "optp_crr_batch_dev", "optp_microbench",
 )
 
@@ -87,6 +87,7 @@ def _declare(lib):
     lib.optp_mc_path_dev.argtypes = path + [vp]
     lib.optp_mc_book.argtypes = [C.POINTER(OptpBookItem), u64, C.POINTER(OptpPayoff), u64, vp]
     lib.optp_sigma_table_upload.argtypes = [vp, u32, u32]
+    lib.optp_dupire_table.argtypes = [vp, vp, u32, vp, vp, u32, d, u32, d, d, u32, d, vp]
     lib.optp_paths.argtypes = [C.POINTER(OptpProcess), u32, u64, i, i, u64, u64, vp, vp, vp]
     lib.optp_payoff_from_paths.argtypes = [vp, u64, u64, C.POINTER(OptpPayoff), vp, vp]
     crr = [vp, vp, vp, vp, vp, vp, vp, u64, u32, i, vp, vp]

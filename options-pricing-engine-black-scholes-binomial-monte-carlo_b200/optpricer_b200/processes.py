@@ -58,6 +58,39 @@ class SigmaTable:
         return cls(table, x0, h, dt)
 
 
+    @classmethod
+    def from_svi_surface(cls, surface, *, S0, T, n_steps, n_nodes=256, half_width=1.6, dT=1e-4,
+                         forward_curve=None):
+        """Tabulate the Dupire local volatility of a raw-SVI surface on the device (optp_dupire_table):
+        the same values as `from_callable(dupire_local_vol_func(surface, r, q), ...)` without the
+        n_steps host evaluations of the reference's callable (calibration.py:268-390).
+
+        `surface` is the reference's VolSurface (or anything with `.slices` = {expiry: object with
+        a, b, rho, m, sigma}); the forward curve is taken from it (`forward_curve=` overrides).  The
+        reference falls back to F = mean(S nodes) when the surface has no curve (calibration.py:317-320);
+        so does this."""
+        slices = dict(sorted(dict(surface.slices).items()))
+        if not slices:
+            raise ValueError("At least one SVI slice is required.")
+        fwd = forward_curve if forward_curve is not None else getattr(surface, "_forward_curve", None)
+        dt = T / n_steps
+        x0 = float(np.log(S0) - half_width)
+        h = 2.0 * half_width / (n_nodes - 1)
+        if not fwd:
+            fwd = {1.0: float(np.exp(x0 + h * np.arange(n_nodes)).mean())}
+        fwd = dict(sorted(fwd.items()))
+        exp_arr = np.array(list(slices), dtype=np.float64)
+        svi = np.array([[p.a, p.b, p.rho, p.m, p.sigma] for p in slices.values()], dtype=np.float64)
+        fT = np.array(list(fwd), dtype=np.float64)
+        fF = np.array(list(fwd.values()), dtype=np.float64)
+        table = np.empty((int(n_steps), int(n_nodes)), dtype=np.float64)
+        lib = nv.init()
+        nv.check(lib.optp_dupire_table(nv.ptr(exp_arr), nv.ptr(svi), len(exp_arr), nv.ptr(fT), nv.ptr(fF), len(fT),
+                                       float(T), int(n_steps), x0, h, int(n_nodes), float(dT), nv.ptr(table)),
+                 "optp_dupire_table")
+        return cls(table, x0, h, dt)
+
+
 class LazyPaths:
     """A path set described by (process, n_steps, n_paths, antithetic, seed); see module docstring."""
 

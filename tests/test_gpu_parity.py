@@ -700,3 +700,47 @@ def test_full_size_config5_book(op):
     for i, b in zip(pick, again):
         a = out[i]
         assert abs(a["price"] - b["price"]) <= 5 * math.hypot(a["stderr"], b["stderr"]) + 1e-4, (rows[i], a, b)
+
+
+# ------------------------------------------------------------------------------ device Dupire tabulation
+class _Slice:
+    def __init__(self, a, b, rho, m, sigma):
+        self.a, self.b, self.rho, self.m, self.sigma = a, b, rho, m, sigma
+
+
+class _Surface:
+    """Duck-typed stand-in for the reference's VolSurface (calibration.py:72-148): .slices and the
+    private forward curve, built from the fitted parameters stored by make_golden.py."""
+    def __init__(self, js, with_forwards=True):
+        self.slices = {float(T): _Slice(*p) for T, p in js["svi"].items()}
+        self._forward_curve = {float(T): F for T, F in js["forwards"].items()} if with_forwards else {}
+
+
+def test_dupire_table_on_device_matches_reference_and_oracle(op):
+    """optp_dupire_table against (a) the 252 x 256 table the UNMODIFIED reference's callable produced
+    (tests/golden/dupire_table_252x256.npz) and (b) the oracle restatement on other grids, including
+    the reference's no-forward-curve fallback.  The central difference in T amplifies last-ulp
+    differences of exp/log by ~1e4, hence 1e-9 relative."""
+    from optpricer_b200 import processes as pr
+    from oracle import dupire
+    js = load_json("dupire_surface.json")
+    table, x0, h, dt = dupire_grid_arrays()
+    got = pr.SigmaTable.from_svi_surface(_Surface(js), S0=js["S0"], T=1.0, n_steps=252)
+    assert got.table.shape == table.shape and got.x0 == x0 and got.h == h and got.dt == dt
+    np.testing.assert_allclose(got.table, table, rtol=1e-9, atol=0)
+    slices = {float(T): tuple(p) for T, p in js["svi"].items()}
+    fwds = {float(T): F for T, F in js["forwards"].items()}
+    for (T, n_steps, n_nodes, hw, with_fwd) in ((0.6, 37, 64, 1.0, True), (2.5, 50, 33, 2.0, True), (1.0, 16, 40, 1.2, False)):
+        dev = pr.SigmaTable.from_svi_surface(_Surface(js, with_fwd), S0=95.0, T=T, n_steps=n_steps, n_nodes=n_nodes,
+                                             half_width=hw)
+        nodes = np.exp(dev.x0 + dev.h * np.arange(n_nodes))
+        surf = dupire.Surface(slices, fwds if with_fwd else {1.0: float(nodes.mean())})
+        want = sigma_grid.tabulate(surf.sigma_loc(), S0=95.0, T=T, n_steps=n_steps, n_nodes=n_nodes, half_width=hw)
+        np.testing.assert_allclose(dev.table, want.table, rtol=1e-9, atol=0)
+    # the device-tabulated surface prices like the host-tabulated one (same Philox draws)
+    host = pr.SigmaTable(table, x0, h, dt)
+    a = op.barrier_price(pr.milstein_local_vol_paths(100.0, 0.05, 0.02, 1.0, 252, 200_000, got, seed=5),
+                         100.0, 0.05, 1.0, "call", 130.0, "up-and-out")
+    b = op.barrier_price(pr.milstein_local_vol_paths(100.0, 0.05, 0.02, 1.0, 252, 200_000, host, seed=5),
+                         100.0, 0.05, 1.0, "call", 130.0, "up-and-out")
+    assert abs(a[0] - b[0]) <= 1e-6 * b[0]
