@@ -32,7 +32,8 @@ struct CrrArgs {
     int N;
     double* price;
     uint8_t* status;
-    int todo_only;  // full-width kernels: price only contracts the band kernel left at status 2
+    int todo_only;  // full-width kernels: 0 = every contract, else only contracts whose status equals this
+                    // value (2 = declined by a banded kernel, 3 = American call that is never exercised early)
 };
 
 struct Lattice {
@@ -191,7 +192,7 @@ crr_warp_kernel(CrrArgs a) {
     const unsigned long long warp0 = (unsigned long long)blockIdx.x * kWarpsPerCta + wib;
     const unsigned long long nwarps = (unsigned long long)gridDim.x * kWarpsPerCta;
     for (unsigned long long o = warp0; o < a.n; o += nwarps) {
-        if (a.todo_only && a.status[o] != 2) continue;
+        if (a.todo_only && a.status[o] != a.todo_only) continue;
         const Lattice L = make_lattice(a, o);
         if (!L.ok) {  // binomial.py:16-17 -> per-contract status instead of raising
             if (lane == 0) {
@@ -675,11 +676,16 @@ __global__ void __launch_bounds__(kZoneWarps * 32, (G == 4) ? OPTP_ZONE_MINB4 : 
         const double one_m_disc = -expm1(-r * dt), one_m_dq = -expm1(-q * dt);
         const bool eligible = active && L.ok && (L.sgn < 0.0) && q >= 0.0 && one_m_disc > 1e-9 &&
                               one_m_disc > one_m_dq * (1.0 + 1e-6) && L.R >= kZoneSeg;
+        // An American call on an asset that pays no dividend is never exercised early: with q <= 0 and
+        // r > 0, cont >= S*e^{-q dt} - K*disc > S - K at every node, so binomial.py:30-36 always keeps the
+        // continuation value.  Such contracts (status 3) go to the European full-width kernel, which is
+        // the same recursion without the per-node exercise value and compare.
+        const unsigned char declined = (L.sgn > 0.0 && q <= 0.0 && one_m_disc > 1e-9) ? 3 : 2;
         // an option that is not walked (declined, failed, past the end of the batch) rides along with
         // a harmless plan; `fail` keeps its result from being written
         bool fail = !eligible;
         if (!__any_sync(0xffffffffu, eligible)) {
-            if (active && L.ok && gl == 0) a.status[o] = 2;
+            if (active && L.ok && gl == 0) a.status[o] = declined;
             continue;
         }
         // exercise values: node m of Z (m = index - w0) is sgn*S0*u^(2*(w0 + (m & ~3)) - k) * u^(2*(m & 3)),
@@ -849,7 +855,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, (G == 4) ? OPTP_ZONE_MINB4 : 
         const double v0 = __shfl_sync(0xffffffffu, z[0], gb);
         if (active && L.ok && gl == 0) {
             if (fail) {
-                a.status[o] = 2;
+                a.status[o] = declined;
             } else {
                 a.price[o] = (w0 == 0) ? v0 : (K - L.S0);
                 a.status[o] = 0;
@@ -967,8 +973,12 @@ static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st) {
                 crr_band_kernel<<<grid, kBandWarps * 32, 0, st>>>(a);
             c.launches++;
             OPTP_CUDA(cudaGetLastError());
-            a.todo_only = 1;
-            if (c.crr_band_only) return 0;  // diagnostics: leave the status-2 contracts unpriced
+            if (c.crr_band_only) return 0;  // diagnostics: leave the declined contracts unpriced
+            if (G > 0) {  // two-zone kernel: never-exercised calls were marked 3 -> European recursion
+                a.todo_only = 3;
+                if (int e = launch_full_warp(a, 0, st)) return e;
+            }
+            a.todo_only = 2;
         }
         return launch_full_warp(a, american, st);
     } else {
