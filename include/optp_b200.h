@@ -13,6 +13,10 @@
  *   - every function returns an int status: 0 ok, >0 argument error (OPTP_E_*),
  *     <0 CUDA runtime error (-(cudaError_t)); optp_last_error() gives the text.
  *   - the library keeps no pointer after a call returns.
+ *   - threads: the library owns ONE context per process (stream, reduction scratch, staging
+ *     arenas); every entry point takes a process-wide lock, so concurrent calls from several
+ *     host threads are serialised, never interleaved.  The _dev variants share the reduction
+ *     scratch too: queue them on ONE stream at a time (or order the streams with events).
  *   - no CPU fallback exists: without a usable CUDA device every compute entry
  *     point returns a negative status.
  */
@@ -101,7 +105,8 @@ int optp_device_count(void);
 /* Number of kernels this library has launched since optp_init (bench.py "gpu_launches"). */
 uint64_t optp_launch_count(void);
 /* Tuning / diagnostics switches (all default to the production setting):
- *   "crr_band"      1 = American puts with r > q go through the banded kernel (default), 0 = every
+ *   "crr_band"      1 = American puts (r > 0, q >= 0) and, as dual puts, American calls (q > 0) go
+ *                   through the banded kernel (default), 0 = every
  *                   contract through the full-width kernels (A/B checks of the band cuts)
  *   "lv_window"     1 = LV Milstein uses the one-load window table when the bump is smaller than a
  *                   grid cell (default), 0 = always the three-lookup (value, slope) path

@@ -32,8 +32,12 @@ struct CrrArgs {
     int N;
     double* price;
     uint8_t* status;
-    int todo_only;  // full-width kernels: 0 = every contract, else only contracts whose status equals this
-                    // value (2 = declined by a banded kernel, 3 = American call that is never exercised early)
+    int todo_only;  // 0 = every contract, else only contracts whose status equals this value (2 = declined by
+                    // a banded kernel, 3 = American call that is never exercised early)
+    // two-zone kernel work lists (compaction of the contracts whose band was too wide for a lane layout):
+    // wl_in = {count, items...} to walk instead of [0, n), or null; wl_out = list the too-wide ones go to
+    const unsigned int* wl_in;
+    unsigned int* wl_out;
 };
 
 struct Lattice {
@@ -44,10 +48,10 @@ struct Lattice {
 };
 
 // binomial.py:11-17
-__device__ __forceinline__ Lattice make_lattice(const CrrArgs& a, unsigned long long o) {
+__device__ __forceinline__ Lattice make_lattice_of(double S0, double K, double T, double r, double q,
+                                                   double sg, bool is_call, int N) {
     Lattice L;
-    const double T = a.T[o], r = a.r[o], q = a.q[o], sg = a.sigma[o];
-    const double dt = T / (double)a.N;
+    const double dt = T / (double)N;
     L.u = exp(sg * sqrt(dt));
     const double d = 1.0 / L.u;
     const double disc = exp(-r * dt);
@@ -55,15 +59,19 @@ __device__ __forceinline__ Lattice make_lattice(const CrrArgs& a, unsigned long 
     L.ok = (p > 0.0) && (p < 1.0);
     L.pu = disc * p;
     L.pd = disc * (1.0 - p);
-    L.S0 = a.S0[o];
-    L.sgn = a.is_call[o] ? 1.0 : -1.0;
-    L.sK = -L.sgn * a.K[o];
+    L.S0 = S0;
+    L.sgn = is_call ? 1.0 : -1.0;
+    L.sK = -L.sgn * K;
     L.inv_pd = 1.0 / L.pd;
     L.rho = L.pu * L.inv_pd;
     L.u_pd = L.u * L.inv_pd;
     const double al = fabs(log(L.pd));
     L.R = (al * 16777216.0 > 138.0) ? max(1, (int)(138.0 / al)) : (1 << 24);
     return L;
+}
+
+__device__ __forceinline__ Lattice make_lattice(const CrrArgs& a, unsigned long long o) {
+    return make_lattice_of(a.S0[o], a.K[o], a.T[o], a.r[o], a.q[o], a.sigma[o], a.is_call[o] != 0, a.N);
 }
 
 // signed base of lane `lane` in layout B at level k:  sgn*S0*u^(2*lane*B - k)
@@ -580,19 +588,26 @@ __global__ void __launch_bounds__(kBandWarps * 32, 5) crr_band_kernel(CrrArgs a)
 #endif
 constexpr int kZoneWarps = 4;
 constexpr int kZoneSeg = 28;      // levels per segment: Z = [jlo - 30, jlo + 2), margin kZoneSeg + 2 below the boundary
-constexpr int kZoneMaxM = 6;      // C zone up to 192 nodes
+// A lane holds at most 24 C nodes: 6 chunks of 32 nodes per option at four options per warp (band up to
+// 224 nodes), 12 at two (416), 24 at one (800).  A contract whose band is too wide for the layout it was
+// tried in keeps status 4 and is walked again by the next narrower-group pass (launch_crr); the
+// arithmetic applied to a node does not depend on the layout, so neither does the price.
+constexpr int kZoneLaneC = 24;
+__host__ __device__ constexpr int zone_max_m(int G) { return kZoneLaneC / G; }
 // re-pack tile, node-ordered per option: node e lives at e + (e >> 4) (one pad double per 16, so the
 // lane-strided accesses of every layout spread over the banks); 248 = 8 (mod 16) staggers the options
-constexpr int kZoneGroupTile = 248;
+__host__ __device__ constexpr int zone_group_tile(int G) { return G == 4 ? 248 : G == 2 ? 456 : 856; }
 __device__ __forceinline__ int zone_pad(int e) { return e + (e >> 4); }
-static_assert(32 * (1 + kZoneMaxM) + (32 * (1 + kZoneMaxM) >> 4) <= kZoneGroupTile, "tile too small");
+static_assert(32 * (1 + zone_max_m(4)) + (32 * (1 + zone_max_m(4)) >> 4) <= zone_group_tile(4), "tile too small");
+static_assert(32 * (1 + zone_max_m(2)) + (32 * (1 + zone_max_m(2)) >> 4) <= zone_group_tile(2), "tile too small");
+static_assert(32 * (1 + zone_max_m(1)) + (32 * (1 + zone_max_m(1)) >> 4) <= zone_group_tile(1), "tile too small");
 
 // nlev levels in layout (BZ = G, BC = G*M).  sb = sgn*S0*u^(2*(w0 + quad) - k): the first node of this
 // lane's quad of Z nodes one level above the segment (ulo holds the lane's factors within the quad).  Returns the exercise mask of this lane's Z nodes at the last
 // level; n_ex0 counts the levels at which the lane's first Z node chose exercise, n_exT the levels
 // t < n_chk at which its last Z node did.
 template <int G, int M>
-__device__ __forceinline__ unsigned int zone_segment(double (&z)[G], double (&c)[G * kZoneMaxM],
+__device__ __forceinline__ unsigned int zone_segment(double (&z)[G], double (&c)[kZoneLaneC],
                                                      const double (&ulo)[G], const Lattice& L, int gl,
                                                      int src, double sb, int nlev, int n_chk, double back,
                                                      int& n_ex0_out, int& n_exT_out) {
@@ -649,43 +664,72 @@ __device__ __forceinline__ unsigned int zone_segment(double (&z)[G], double (&c)
 }
 
 template <int G>
-__global__ void __launch_bounds__(kZoneWarps * 32, (G == 4) ? OPTP_ZONE_MINB4 : 5) crr_zone_kernel(CrrArgs a) {
-    constexpr int LG = 32 / G, BZ = G, BCMAX = G * kZoneMaxM;
-    __shared__ double tiles[kZoneWarps][G * kZoneGroupTile];
+__global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_kernel(CrrArgs a) {
+    constexpr int LG = 32 / G, BZ = G, BCMAX = kZoneLaneC, kMaxM = zone_max_m(G), kGroupTile = zone_group_tile(G);
+    __shared__ double tiles[kZoneWarps][G * kGroupTile];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int gl = lane & (LG - 1);        // lane within the option
     const int gb = lane & ~(LG - 1);       // first lane of the option
     const int src = gb | ((gl + 1) & (LG - 1));
     const unsigned int gmask = (LG == 32) ? 0xffffffffu : ((1u << LG) - 1u);
-    double* tile = tiles[wib] + (lane / LG) * kZoneGroupTile;
+    double* tile = tiles[wib] + (lane / LG) * kGroupTile;
     const int N = a.N;
     const unsigned long long warp0 = (unsigned long long)blockIdx.x * kZoneWarps + wib;
     const unsigned long long nwarps = (unsigned long long)gridDim.x * kZoneWarps;
-    for (unsigned long long o0 = warp0 * G; o0 < a.n; o0 += nwarps * G) {
+    // retry passes walk the compacted list of contracts the previous layout was too narrow for
+    const unsigned long long n_work = a.wl_in ? (unsigned long long)a.wl_in[0] : a.n;
+    for (unsigned long long o0 = warp0 * G; o0 < n_work; o0 += nwarps * G) {
         const unsigned long long og = o0 + (unsigned long long)(lane / LG);
-        const bool active = og < a.n;
-        const unsigned long long o = active ? og : (a.n - 1);
-        const Lattice L = make_lattice(a, o);
-        if (active && !L.ok && gl == 0) {
+        const bool wanted = og < n_work;
+        const unsigned long long ow = wanted ? og : (n_work - 1);
+        const unsigned long long o = a.wl_in ? (unsigned long long)a.wl_in[1 + ow] : ow;
+        // An American call with q > 0 is priced as its DUAL PUT: on a CRR lattice (u*d = 1)
+        //     C_k[j](S0, K, r, q) = P_k[k - j](S0' = K, K' = S0, r' = q, q' = r)
+        // holds node by node (change of numeraire: p' = 1 - p*u*e^{-(r-q)dt} is the up-probability of
+        // K/S, e^{-q dt} its discount factor; the exercise test is the same inequality divided by S/K'),
+        // so the put machinery below prices it; the result differs from the direct recursion by
+        // rounding only (1e-13 relative, tests/test_gpu_parity.py).
+        const bool is_call = a.is_call[o] != 0;
+        const double r_in = a.r[o], q_in = a.q[o];
+        const bool dual = is_call && q_in > 0.0 && r_in >= 0.0;
+        const double r = dual ? q_in : r_in, q = dual ? r_in : q_in;
+        const double K = dual ? a.S0[o] : a.K[o];
+        Lattice L = make_lattice_of(dual ? a.K[o] : a.S0[o], K, a.T[o], r, q, a.sigma[o], is_call && !dual, N);
+        const double dt = a.T[o] / (double)N;
+        if (dual) {  // status 1 is decided by the contract's own probability (binomial.py:15-17)
+            const double d = 1.0 / L.u;
+            const double p = (exp((r_in - q_in) * dt) - d) / (L.u - d);
+            L.ok = L.ok && (p > 0.0) && (p < 1.0);
+            if (!((p > 0.0) && (p < 1.0)) && wanted && gl == 0) {
+                a.price[o] = nan("");
+                a.status[o] = 1;
+            }
+        } else if (wanted && !L.ok && gl == 0) {
             a.price[o] = nan("");
             a.status[o] = 1;
         }
-        const double r = a.r[o], q = a.q[o], K = a.K[o];
-        const double dt = a.T[o] / (double)N;
         const double one_m_disc = -expm1(-r * dt), one_m_dq = -expm1(-q * dt);
-        const bool eligible = active && L.ok && (L.sgn < 0.0) && q >= 0.0 && one_m_disc > 1e-9 &&
-                              one_m_disc > one_m_dq * (1.0 + 1e-6) && L.R >= kZoneSeg;
+        // q > r: the exercise boundary sits at or below S1 = K(1 - disc)/(1 - e^{-q dt}) ~ K r/q from level
+        // N-1 on (a node whose children are both exercise nodes is one iff S <= S1), i.e. it JUMPS down
+        // from the strike between level N and N-1; the first segment is set up for that below.
+        // j1 = first level-N node above S1 (N + 2 = no jump); needs ln u, computed here so that r, q and dt
+        // do not stay live across the walk
+        int j1 = N + 2;
+        if (one_m_dq > one_m_disc)
+            j1 = (int)fmin(fmax(floor(0.5 * ((double)N + log(K * (one_m_disc / one_m_dq) / L.S0) / log(L.u))) + 1.0, 0.0),
+                           (double)(N + 1));
+        const bool eligible = wanted && L.ok && (L.sgn < 0.0) && q >= 0.0 && one_m_disc > 1e-9 && L.R >= kZoneSeg;
         // An American call on an asset that pays no dividend is never exercised early: with q <= 0 and
         // r > 0, cont >= S*e^{-q dt} - K*disc > S - K at every node, so binomial.py:30-36 always keeps the
         // continuation value.  Such contracts (status 3) go to the European full-width kernel, which is
         // the same recursion without the per-node exercise value and compare.
-        const unsigned char declined = (L.sgn > 0.0 && q <= 0.0 && one_m_disc > 1e-9) ? 3 : 2;
+        const unsigned char declined = (is_call && q_in <= 0.0 && -expm1(-r_in * dt) > 1e-9) ? 3 : 2;
         // an option that is not walked (declined, failed, past the end of the batch) rides along with
         // a harmless plan; `fail` keeps its result from being written
-        bool fail = !eligible;
+        bool fail = !eligible, too_wide = false;
         if (!__any_sync(0xffffffffu, eligible)) {
-            if (active && L.ok && gl == 0) a.status[o] = declined;
+            if (wanted && L.ok && gl == 0) a.status[o] = declined;
             continue;
         }
         // exercise values: node m of Z (m = index - w0) is sgn*S0*u^(2*(w0 + (m & ~3)) - k) * u^(2*(m & 3)),
@@ -724,6 +768,11 @@ __global__ void __launch_bounds__(kZoneWarps * 32, (G == 4) ? OPTP_ZONE_MINB4 : 
         unsigned int exmask = 0;
         {
             const double jz = 0.5 * ((double)N + log(K / L.S0) / ln_u);  // first out-of-the-money node
+            // q > r and more than one option per warp: by level 0 the band reaches from below S1 to ~10.2
+            // standard deviations above the strike, i.e. at least (jz - j1) + 5.1 sqrt(N) nodes.  A contract
+            // that cannot fit this layout goes to the next one now instead of after a wasted partial walk.
+            if (G > 1 && !fail && j1 <= N + 1 && (jz - (double)j1) + 4.6 * sqrt((double)N) > (double)(32 * (1 + kMaxM)))
+                fail = too_wide = true;
             const double w = fmin(fmax(floor(jz) - 28.0, 0.0), (double)max(0, N + 1 - 32));
             w0 = fail ? 0 : (int)w;
             const double sbN = L.sgn * L.S0 * exp(ln_u * (double)(2 * (w0 + quad0) - N));
@@ -749,7 +798,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, (G == 4) ? OPTP_ZONE_MINB4 : 
             const unsigned int has_cont = (__ballot_sync(0xffffffffu, first_cont < BZ) >> gb) & gmask;
             const int f_cont = has_cont ? (__ffs(has_cont) - 1) : 0;  // always one of the option's lanes
             const int s_cont = __shfl_sync(0xffffffffu, first_cont, gb + f_cont);
-            const int jlo = has_cont ? (w0 + f_cont * BZ + s_cont) : (w0 + 32);
+            int jlo = has_cont ? (w0 + f_cont * BZ + s_cont) : (w0 + 32);
             // jhi = 1 + last node worth more than 2^-80 K.  A put's value falls with the node index, so
             // the live nodes are a prefix of the window: find the last lane whose FIRST node is live
             // from the registers, then count the live nodes of that lane's chunk from the tile.
@@ -778,7 +827,36 @@ __global__ void __launch_bounds__(kZoneWarps * 32, (G == 4) ? OPTP_ZONE_MINB4 : 
             if (jhi < jlo) jhi = jlo;
             // the window bottom must still be inside the exercise region (or be node 0)
             if (w0 > 0 && jlo <= w0) fail = true;
-            if (k == 0) break;
+            if (k == 0 || !__any_sync(0xffffffffu, !fail)) break;  // nothing left to walk in this warp
+            int width_old = 32 * (1 + M);
+            if (k == N && __any_sync(0xffffffffu, j1 <= N + 1 && !fail)) {
+                // q > r (see `jump`): from level N-1 on the boundary is the first node above S1, far below
+                // the strike.  Level N is re-tabulated in the tile from a lower origin, so that the
+                // generic re-pack below finds the payoffs of the in-the-money continuation nodes there.
+                const bool mine = !fail && j1 <= N + 1 && j1 < jlo;  // (a warp mate's jump must not touch this option)
+                int wl = w0, span = 0;
+                if (mine) {
+                    jlo = j1;
+                    wl = max(0, j1 - (kZoneSeg + 2));
+                    span = w0 + 32 - wl;
+                    if (span > 32 * (1 + kMaxM)) fail = too_wide = true;
+                }
+                __syncwarp();
+                if (mine && !fail && wl < w0) {
+                    const double u2 = exp(2.0 * ln_u);  // (L.u is not kept live across the walk)
+                    for (int e0 = 4 * gl; e0 < span; e0 += 4 * LG) {
+                        const double sbq = L.sgn * L.S0 * exp(ln_u * (double)(2 * (wl + e0) - N));
+                        double f = 1.0;
+                        for (int i = 0; i < 4; ++i, f *= u2) {
+                            const double e = fma(sbq, f, L.sK);
+                            if (e0 + i < span) tile[zone_pad(e0 + i)] = e > 0.0 ? e : 0.0;
+                        }
+                    }
+                    w0 = wl;
+                    width_old = span;
+                }
+                __syncwarp();
+            }
             // ---- next segment: levels k-1 ... k-nlev, fixed schedule -------------------------------
             const int nlev = min(kZoneSeg, k);
             const int top = min(jhi, k + 1);  // exclusive; node `top` of level k is 0 (or dead)
@@ -789,7 +867,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, (G == 4) ? OPTP_ZONE_MINB4 : 
                 need = (top - (w0n + 32) + 31) >> 5;
                 // the top test is evaluated while Z's top node exists: level >= w0n + 31
                 n_chk = min(nlev, max(0, k - (w0n + 31)));
-                if (need > kZoneMaxM) fail = true;
+                if (!fail && need > kMaxM) fail = too_wide = true;
             }
             if (fail) {
                 w0n = 0;
@@ -799,7 +877,6 @@ __global__ void __launch_bounds__(kZoneWarps * 32, (G == 4) ? OPTP_ZONE_MINB4 : 
             const int Mn = __reduce_max_sync(0xffffffffu, need);
             const int BCn = G * Mn;
             // ---- re-pack level k from (w0, M) to (w0n, Mn) ------------------------------------------
-            const int width_old = 32 * (1 + M);
             // this lane's first Z node of the new layout at level k: sgn*S0*u^(2j - k)
             const double sb = L.sgn * L.S0 * exp(ln_u * (double)(2 * (w0n + quad0) - k));
 #pragma unroll
@@ -833,15 +910,20 @@ __global__ void __launch_bounds__(kZoneWarps * 32, (G == 4) ? OPTP_ZONE_MINB4 : 
                     sq *= sq;
                 }
             }
+#define OPTP_ZONE_CASE(m)                                                                                          \
+    case m:                                                                                                        \
+        if constexpr ((m) <= kMaxM)                                                                                \
+            exmask = zone_segment<G, ((m) <= kMaxM ? (m) : 0)>(z, c, ulo, L, gl, src, sb, nlev, n_chk, back, n_ex0, n_exT); \
+        break;
             switch (M) {
-                case 0: exmask = zone_segment<G, 0>(z, c, ulo, L, gl, src, sb, nlev, n_chk, back, n_ex0, n_exT); break;
-                case 1: exmask = zone_segment<G, 1>(z, c, ulo, L, gl, src, sb, nlev, n_chk, back, n_ex0, n_exT); break;
-                case 2: exmask = zone_segment<G, 2>(z, c, ulo, L, gl, src, sb, nlev, n_chk, back, n_ex0, n_exT); break;
-                case 3: exmask = zone_segment<G, 3>(z, c, ulo, L, gl, src, sb, nlev, n_chk, back, n_ex0, n_exT); break;
-                case 4: exmask = zone_segment<G, 4>(z, c, ulo, L, gl, src, sb, nlev, n_chk, back, n_ex0, n_exT); break;
-                case 5: exmask = zone_segment<G, 5>(z, c, ulo, L, gl, src, sb, nlev, n_chk, back, n_ex0, n_exT); break;
-                default: exmask = zone_segment<G, 6>(z, c, ulo, L, gl, src, sb, nlev, n_chk, back, n_ex0, n_exT); break;
+                OPTP_ZONE_CASE(0) OPTP_ZONE_CASE(1) OPTP_ZONE_CASE(2) OPTP_ZONE_CASE(3) OPTP_ZONE_CASE(4)
+                OPTP_ZONE_CASE(5) OPTP_ZONE_CASE(6) OPTP_ZONE_CASE(7) OPTP_ZONE_CASE(8) OPTP_ZONE_CASE(9)
+                OPTP_ZONE_CASE(10) OPTP_ZONE_CASE(11) OPTP_ZONE_CASE(12) OPTP_ZONE_CASE(13) OPTP_ZONE_CASE(14)
+                OPTP_ZONE_CASE(15) OPTP_ZONE_CASE(16) OPTP_ZONE_CASE(17) OPTP_ZONE_CASE(18) OPTP_ZONE_CASE(19)
+                OPTP_ZONE_CASE(20) OPTP_ZONE_CASE(21) OPTP_ZONE_CASE(22) OPTP_ZONE_CASE(23) OPTP_ZONE_CASE(24)
+                default: break;
             }
+#undef OPTP_ZONE_CASE
             // everything below the window is an exercise node only while the window's bottom node
             // chose exercise at EVERY level; everything in C is a continuation node only while Z's
             // top node chose continuation at every level it exists
@@ -853,9 +935,13 @@ __global__ void __launch_bounds__(kZoneWarps * 32, (G == 4) ? OPTP_ZONE_MINB4 : 
         }
         // level 0: node 0 is in the window (w0 == 0) or below it (then it is an exercise node)
         const double v0 = __shfl_sync(0xffffffffu, z[0], gb);
-        if (active && L.ok && gl == 0) {
+        if (wanted && L.ok && gl == 0) {
             if (fail) {
-                a.status[o] = declined;
+                if (too_wide && G > 1) {
+                    a.wl_out[1 + atomicAdd(a.wl_out, 1u)] = (unsigned int)o;  // status is settled by a later pass
+                } else {
+                    a.status[o] = declined;
+                }
             } else {
                 a.price[o] = (w0 == 0) ? v0 : (K - L.S0);
                 a.status[o] = 0;
@@ -934,11 +1020,24 @@ static int launch_full_warp(const CrrArgs& a, int american, cudaStream_t st) {
     return 0;
 }
 
-static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st) {
+// Work lists of the two-zone kernel: per slot two lists of {count, n items}.
+static size_t crr_worklist_bytes(unsigned long long n) {
+    return ((size_t)(n + 1) * sizeof(unsigned int) + 255) & ~(size_t)255;
+}
+static int crr_reserve_worklists(unsigned long long n) {
+    return arena_reserve(ctx().work, 4 * crr_worklist_bytes(n) + 512);
+}
+
+// `slot` (0 or 1) selects the work-list scratch: launches that may be in flight together (the two
+// streams of the sliced host pipeline) must use different slots.
+static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st, int slot = 0) {
     Context& c = ctx();
     CrrArgs a = a_in;
     a.todo_only = 0;
+    a.wl_in = nullptr;
+    a.wl_out = nullptr;
     if (a.n == 0) return 0;
+    if (a.n >= (1ull << 32)) return set_error(OPTP_E_TOO_LARGE, "a CRR batch holds at most 2^32 - 1 contracts");
     if (a.N <= 1023) {
         if (american && !c.crr_no_band) {
             // pass 1: banded kernel (American puts with r > q); pass 2: whatever it left at status 2
@@ -951,6 +1050,17 @@ static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st) {
                     const unsigned long long warps = (unsigned long long)c.n_sm * 16;
                     G = (a.n >= 4 * warps) ? 4 : (a.n >= 2 * warps) ? 2 : 1;
                 }
+            }
+            unsigned int* wl[2] = {nullptr, nullptr};
+            if (G >= 2) {
+                if (int e = crr_reserve_worklists(a.n)) return e;
+                const size_t list_bytes = crr_worklist_bytes(a.n);
+                char* base = (char*)c.work.p + (size_t)slot * ((c.work.cap / 2) & ~(size_t)255);
+                wl[0] = (unsigned int*)base;
+                wl[1] = (unsigned int*)(base + list_bytes);
+                OPTP_CUDA(cudaMemsetAsync(wl[0], 0, sizeof(unsigned int), st));
+                OPTP_CUDA(cudaMemsetAsync(wl[1], 0, sizeof(unsigned int), st));
+                a.wl_out = wl[0];
             }
             const void* fn = (G == 4)   ? (const void*)crr_zone_kernel<4>
                              : (G == 2) ? (const void*)crr_zone_kernel<2>
@@ -973,6 +1083,29 @@ static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st) {
                 crr_band_kernel<<<grid, kBandWarps * 32, 0, st>>>(a);
             c.launches++;
             OPTP_CUDA(cudaGetLastError());
+            // contracts whose band was too wide for G options per warp were appended to wl[0]: walk that
+            // list two per warp, then what is too wide even so (wl[1]) one per warp
+            const unsigned int* wl_in = a.wl_out;
+            for (int g2 = G / 2; g2 >= 1; g2 /= 2) {
+                a.wl_in = wl_in;
+                a.wl_out = (g2 == 2) ? wl[1] : nullptr;
+                const void* fn2 = (g2 == 2) ? (const void*)crr_zone_kernel<2> : (const void*)crr_zone_kernel<1>;
+                OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn2, kZoneWarps * 32, 0));
+                if (per_sm < 1) per_sm = 1;
+                const unsigned long long want2 = (a.n + kZoneWarps * g2 - 1) / (kZoneWarps * g2);
+                const unsigned long long cap2 = (unsigned long long)c.n_sm * per_sm;
+                const unsigned int grid2 = (unsigned int)(want2 < cap2 ? want2 : cap2);
+                if (g2 == 2)
+                    crr_zone_kernel<2><<<grid2, kZoneWarps * 32, 0, st>>>(a);
+                else
+                    crr_zone_kernel<1><<<grid2, kZoneWarps * 32, 0, st>>>(a);
+                c.launches++;
+                OPTP_CUDA(cudaGetLastError());
+                wl_in = a.wl_out;
+            }
+            a.wl_in = nullptr;
+            a.wl_out = nullptr;
+            a.todo_only = 0;
             if (c.crr_band_only) return 0;  // diagnostics: leave the declined contracts unpriced
             if (G > 0) {  // two-zone kernel: never-exercised calls were marked 3 -> European recursion
                 a.todo_only = 3;
@@ -1011,7 +1144,7 @@ extern "C" int optp_crr_batch_dev(const double* S0, const double* K, const doubl
                                   const double* r, const double* q, const double* sigma,
                                   const uint8_t* is_call, uint64_t n, uint32_t N, int american,
                                   double* price_out, uint8_t* status_out, void* stream) {
-    if (int e = require_ready()) return e;
+    OPTP_ENTER();
     if (N == 0 || N > (1u << 24)) return set_error(OPTP_E_ARG, "N must be positive.");
     if (n && (!S0 || !K || !T || !r || !q || !sigma || !is_call || !price_out || !status_out))
         return set_error(OPTP_E_ARG, "null pointer argument");
@@ -1023,7 +1156,7 @@ extern "C" int optp_crr_batch(const double* S0, const double* K, const double* T
                               const double* q, const double* sigma, const uint8_t* is_call,
                               uint64_t n, uint32_t N, int american, double* price_out,
                               uint8_t* status_out) {
-    if (int e = require_ready()) return e;
+    OPTP_ENTER();
     if (N == 0 || N > (1u << 24)) return set_error(OPTP_E_ARG, "N must be positive.");
     if (n == 0) return 0;
     if (!S0 || !K || !T || !r || !q || !sigma || !is_call || !price_out || !status_out)
@@ -1046,6 +1179,10 @@ extern "C" int optp_crr_batch(const double* S0, const double* K, const double* T
     if (pipelined && !c.stream2)
         OPTP_CUDA(cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking));
     const uint64_t step = pipelined ? slice : n;
+    // scratch of both pipeline slots is reserved before anything is in flight (an arena never grows
+    // under a running kernel)
+    if (american)
+        if (int e = crr_reserve_worklists(step)) return e;
     // The device->host copy of a slice is issued AFTER the next slice has been queued: a copy into
     // pageable host memory blocks the calling thread until it is done.
     auto copy_back = [&](uint64_t lo, uint64_t m, cudaStream_t st) -> int {
@@ -1075,7 +1212,7 @@ extern "C" int optp_crr_batch(const double* S0, const double* K, const double* T
                   (double*)out + lo,
                   (uint8_t*)(out + colp) + lo,
                   0};
-        if (int e = launch_crr(a, american, st)) return e;
+        if (int e = launch_crr(a, american, st, (pipelined && which) ? 1 : 0)) return e;
         if (prev_m)
             if (int e = copy_back(prev_lo, prev_m, prev_st)) return e;
         prev_lo = lo;

@@ -107,7 +107,7 @@ extern "C" int optp_dupire_table(const double* expiries, const double* svi, uint
                                  const double* fwd_T, const double* fwd_F, uint32_t n_fwd, double T,
                                  uint32_t n_steps, double x0, double h, uint32_t n_nodes, double dT,
                                  double* table_out) {
-    if (int e = require_ready()) return e;
+    OPTP_ENTER();
     if (!expiries || !svi || n_exp == 0)
         return set_error(OPTP_E_ARG, "At least one SVI slice is required.");
     if (!fwd_T || !fwd_F || n_fwd == 0)

@@ -110,7 +110,7 @@ using namespace optp;
 extern "C" {
 
 int optp_sigma_table_upload(const double* table, uint32_t n_steps, uint32_t n_nodes) {
-    if (int e = require_ready()) return e;
+    OPTP_ENTER();
     OPTP_CUDA(cudaSetDevice(ctx().device));
     if (int e = upload_table(table, n_steps, n_nodes)) return e;
     OPTP_CUDA(cudaStreamSynchronize(ctx().stream));
@@ -122,7 +122,7 @@ int optp_mc_terminal_dev(double S0, double K, double T, double r, double q, doub
                          int is_call, uint64_t n_base, int antithetic, int mode, int fp32_cast,
                          uint64_t seed, uint64_t path_offset, const double* z_dev,
                          double* stats_dev, void* stream) {
-    if (int e = require_ready()) return e;
+    OPTP_ENTER();
     if (!stats_dev) return set_error(OPTP_E_ARG, "null stats pointer");
     if (n_base == 0) return set_error(OPTP_E_ARG, "n_base must be positive");
     if (mode == OPTP_MODE_FP64_HOSTZ && !z_dev)
@@ -150,7 +150,7 @@ int optp_mc_terminal_dev(double S0, double K, double T, double r, double q, doub
 int optp_mc_terminal(double S0, double K, double T, double r, double q, double sigma, int is_call,
                      uint64_t n_base, int antithetic, int mode, int fp32_cast, uint64_t seed,
                      uint64_t path_offset, const double* z, double stats_out[OPTP_NSTATS]) {
-    if (int e = require_ready()) return e;
+    OPTP_ENTER();
     if (!stats_out) return set_error(OPTP_E_ARG, "null stats pointer");
     Context& c = ctx();
     OPTP_CUDA(cudaSetDevice(c.device));
@@ -181,7 +181,7 @@ int optp_mc_path_dev(const optp_process* proc, const optp_payoff* payoffs, uint3
                      uint32_t n_steps, uint64_t n_base, int antithetic, int mode, uint64_t seed,
                      uint64_t path_offset, const double* z_dev, double* payoff_out_dev,
                      double* terminal_out_dev, double* stats_dev, void* stream) {
-    if (int e = require_ready()) return e;
+    OPTP_ENTER();
     if (int e = check_process(proc, n_steps, n_base)) return e;
     if (int e = check_payoffs(payoffs, n_payoffs)) return e;
     if (!stats_dev) return set_error(OPTP_E_ARG, "null stats pointer");
@@ -205,7 +205,7 @@ int optp_mc_path(const optp_process* proc, const optp_payoff* payoffs, uint32_t 
                  uint32_t n_steps, uint64_t n_base, int antithetic, int mode, uint64_t seed,
                  uint64_t path_offset, const double* z, double* payoff_out, double* terminal_out,
                  double* stats_out) {
-    if (int e = require_ready()) return e;
+    OPTP_ENTER();
     if (int e = check_process(proc, n_steps, n_base)) return e;
     if (int e = check_payoffs(payoffs, n_payoffs)) return e;
     if (!stats_out) return set_error(OPTP_E_ARG, "null stats pointer");
@@ -252,7 +252,7 @@ int optp_mc_path(const optp_process* proc, const optp_payoff* payoffs, uint32_t 
 // ------------------------------------------------------------------ book of items
 int optp_mc_book(const optp_book_item* items, uint64_t n_items, const optp_payoff* payoffs,
                  uint64_t n_payoffs_total, double* stats_out) {
-    if (int e = require_ready()) return e;
+    OPTP_ENTER();
     if (n_items == 0) return 0;
     if (!items || !stats_out) return set_error(OPTP_E_ARG, "null pointer argument");
     Context& c = ctx();
@@ -310,7 +310,7 @@ int optp_mc_book(const optp_book_item* items, uint64_t n_items, const optp_payof
 int optp_paths(const optp_process* proc, uint32_t n_steps, uint64_t n_base, int antithetic, int mode,
                uint64_t seed, uint64_t path_offset, const double* z, double* paths_out,
                double* var_out) {
-    if (int e = require_ready()) return e;
+    OPTP_ENTER();
     if (int e = check_process(proc, n_steps, n_base)) return e;
     if (!paths_out) return set_error(OPTP_E_ARG, "null paths pointer");
     if (mode != OPTP_MODE_FP64_PHILOX && mode != OPTP_MODE_FP64_HOSTZ)
@@ -356,7 +356,7 @@ int optp_paths(const optp_process* proc, uint32_t n_steps, uint64_t n_base, int 
 int optp_payoff_from_paths(const double* paths, uint64_t n_rows, uint64_t n_cols,
                            const optp_payoff* payoff, double* payoff_out,
                            double stats_out[OPTP_NSTATS]) {
-    if (int e = require_ready()) return e;
+    OPTP_ENTER();
     if (!paths || n_rows < 1 || n_cols < 1) return set_error(OPTP_E_ARG, "empty paths array");
     if (int e = check_payoffs(payoff, 1)) return e;
     if (!stats_out) return set_error(OPTP_E_ARG, "null stats pointer");

@@ -245,7 +245,7 @@ static int run_peak(double* per_second, double* mhz) {
 using namespace optp;
 
 extern "C" int optp_microbench(int which, double* per_second_out, double* sm_clock_mhz_out) {
-    if (int e = require_ready()) return e;
+    OPTP_ENTER();
     if (!per_second_out) return set_error(OPTP_E_ARG, "null output pointer");
     switch (which) {
         case 0: return run_peak<0>(per_second_out, sm_clock_mhz_out);

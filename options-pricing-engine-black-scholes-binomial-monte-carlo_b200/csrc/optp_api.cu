@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 #include "optp_common.cuh"
 
 namespace optp {
@@ -9,7 +10,12 @@ namespace optp {
 static Context g_ctx;
 static thread_local char g_err[512] = "";
 
+static std::recursive_mutex g_api_mutex;  // recursive: optp_init may call optp_shutdown
+
 Context& ctx() { return g_ctx; }
+
+ApiLock::ApiLock() { g_api_mutex.lock(); }
+ApiLock::~ApiLock() { g_api_mutex.unlock(); }
 
 int set_error(int code, const char* fmt, ...) {
     va_list ap;
@@ -69,14 +75,7 @@ int optp_device_count(void) {
     return n;
 }
 
-int optp_init(int device) {
-    Context& c = g_ctx;
-    if (c.ready && c.device == device) return 0;
-    if (c.ready) optp_shutdown();
-    int n = 0;
-    OPTP_CUDA(cudaGetDeviceCount(&n));
-    if (device < 0 || device >= n)
-        return set_error(OPTP_E_ARG, "device %d out of range (%d visible)", device, n);
+static int init_resources(Context& c, int device) {
     OPTP_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     OPTP_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -92,6 +91,41 @@ int optp_init(int device) {
     OPTP_CUDA(cudaMalloc(&c.stats_dev, sizeof(double) * kMaxPayoffs * OPTP_NSTATS));
     OPTP_CUDA(cudaHostAlloc(&c.stats_host, sizeof(double) * kMaxPayoffs * OPTP_NSTATS,
                             cudaHostAllocDefault));
+    return 0;
+}
+
+static void release_resources(Context& c) {
+    arena_free(c.in0);
+    arena_free(c.in1);
+    arena_free(c.out0);
+    arena_free(c.out1);
+    arena_free(c.table_f32);
+    arena_free(c.table_f4);
+    arena_free(c.table_f64);
+    arena_free(c.work);
+    if (c.partials) cudaFree(c.partials);
+    if (c.ticket) cudaFree(c.ticket);
+    if (c.stats_dev) cudaFree(c.stats_dev);
+    if (c.stats_host) cudaFreeHost(c.stats_host);
+    if (c.stream) cudaStreamDestroy(c.stream);
+    if (c.stream2) cudaStreamDestroy(c.stream2);
+    cudaGetLastError();
+    c = Context();
+}
+
+int optp_init(int device) {
+    ApiLock lock;
+    Context& c = g_ctx;
+    if (c.ready && c.device == device) return 0;
+    if (c.ready) optp_shutdown();
+    int n = 0;
+    OPTP_CUDA(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n)
+        return set_error(OPTP_E_ARG, "device %d out of range (%d visible)", device, n);
+    if (int e = init_resources(c, device)) {
+        release_resources(c);  // a half-built context is torn down; the error text stays
+        return e;
+    }
     c.launches = 0;
     {
         const char* nb = getenv("OPTP_CRR_NO_BAND");
@@ -104,30 +138,20 @@ int optp_init(int device) {
 }
 
 int optp_shutdown(void) {
+    ApiLock lock;
     Context& c = g_ctx;
     if (!c.ready) return 0;
     cudaSetDevice(c.device);
     cudaStreamSynchronize(c.stream);
-    arena_free(c.in0);
-    arena_free(c.in1);
-    arena_free(c.out0);
-    arena_free(c.out1);
-    arena_free(c.table_f32);
-    arena_free(c.table_f4);
-    arena_free(c.table_f64);
-    cudaFree(c.partials);
-    cudaFree(c.ticket);
-    cudaFree(c.stats_dev);
-    cudaFreeHost(c.stats_host);
-    cudaStreamDestroy(c.stream);
-    if (c.stream2) cudaStreamDestroy(c.stream2);
-    c = Context();
+    if (c.stream2) cudaStreamSynchronize(c.stream2);
+    release_resources(c);
     return 0;
 }
 
 uint64_t optp_launch_count(void) { return g_ctx.launches; }
 
 int optp_set_option(const char* key, long value) {
+    ApiLock lock;
     if (!key) return set_error(OPTP_E_ARG, "null option key");
     if (!strcmp(key, "crr_band")) {
         g_ctx.crr_no_band = (value == 0);

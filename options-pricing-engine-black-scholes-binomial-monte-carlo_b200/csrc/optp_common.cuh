@@ -26,6 +26,7 @@ struct Context {
     double* stats_dev = nullptr;  // kMaxPayoffs * OPTP_NSTATS
     double* stats_host = nullptr; // pinned mirror
     Arena in0, in1, out0, out1, table_f32, table_f64, table_f4;
+    Arena work;  // work lists of the two-zone CRR kernel (crr_batch.cu)
     uint32_t table_steps = 0, table_nodes = 0;
     uint64_t launches = 0;
     bool lv_direct = false;      // "lv_direct" = 1: window nodes gathered from global/L1, no smem staging
@@ -45,6 +46,21 @@ int set_error(int code, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 int arena_reserve(Arena& a, size_t bytes);
 int require_ready();
+
+// The library keeps ONE context (stream, reduction scratch, staging arenas): every C-ABI entry point
+// holds this lock for its whole duration, so calls from several host threads are serialised instead
+// of racing on the scratch (ctypes releases the GIL around a call).
+struct ApiLock {
+    ApiLock();
+    ~ApiLock();
+    ApiLock(const ApiLock&) = delete;
+    ApiLock& operator=(const ApiLock&) = delete;
+};
+#define OPTP_ENTER()                                   \
+    optp::ApiLock api_lock__;                          \
+    do {                                               \
+        if (int e__ = optp::require_ready()) return e__; \
+    } while (0)
 
 #define OPTP_CUDA(call)                                           \
     do {                                                          \

@@ -1,0 +1,27 @@
+"""Throughput of American calls with dividends (dual-put route) and of puts with q > r through the
+two-zone CRR kernel, against the full-width kernel on the same contracts."""
+import sys, time
+sys.path.insert(0, "options-pricing-engine-black-scholes-binomial-monte-carlo_b200"); sys.path.insert(0, ".")
+import numpy as np
+from optpricer_b200 import binomial as bn, _native as nv
+from bench import cfg2_contracts
+nv.init(0)
+n = 200_000
+S0, K, T, r, q, sig, _ = cfg2_contracts(n)
+g = np.random.default_rng(1)
+for name, call, rr, qq in (("calls q~U(.5%,2.5%), r=3%", 1, np.full(n, 0.03), g.uniform(0.005, 0.025, n)),
+                           ("calls q~U(3%,6%), r=3%", 1, np.full(n, 0.03), g.uniform(0.03, 0.06, n)),
+                           ("puts  q~U(3%,6%), r=3%", 0, np.full(n, 0.03), g.uniform(0.03, 0.06, n)),
+                           ("puts  q=0, r=3% (cfg2)", 0, np.full(n, 0.03), np.zeros(n))):
+    c = np.full(n, call, dtype=np.uint8)
+    nv.set_option("crr_band", 1)
+    bn.crr_batch(S0[:1000], K[:1000], T[:1000], rr[:1000], qq[:1000], sig[:1000], c[:1000], 1000, american=True)
+    t0 = time.perf_counter(); a = bn.crr_batch(S0, K, T, rr, qq, sig, c, 1000, american=True); dt = time.perf_counter() - t0
+    nv.set_option("crr_band_only", 1)
+    _, st = bn.crr_batch(S0, K, T, rr, qq, sig, c, 1000, american=True, return_status=True)
+    nv.set_option("crr_band_only", 0)
+    nv.set_option("crr_band", 0)
+    t0 = time.perf_counter(); b = bn.crr_batch(S0, K, T, rr, qq, sig, c, 1000, american=True); dt2 = time.perf_counter() - t0
+    nv.set_option("crr_band", 1)
+    print("%s: banded %.3e options/s (declined %.2f%%), full-width %.3e options/s; max rel diff %.2e"
+          % (name, n / dt, 100.0 * np.mean(st == 2), n / dt2, np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-8))))

@@ -246,6 +246,38 @@ def test_crr_banded_kernel_equals_full_width_kernel(op):
         nv.set_option("crr_band_only", 0)
 
 
+def test_crr_dividend_calls_and_high_yield_puts_take_the_banded_kernel(op):
+    """American calls with q > 0 are priced as their dual puts (C(S0,K,r,q) = P(K,S0,q,r) node by node
+    on a CRR lattice) and puts with q > r start from the boundary S1 ~ K r/q below the strike: both go
+    through the two-zone kernel and must match the C restatement of binomial.py:7-38 at 1e-10."""
+    from oracle import crr_c
+    from optpricer_b200 import _native as nv
+    g = np.random.default_rng(2024)
+    n = 4096
+    S0 = g.uniform(50, 150, n); K = S0 * g.uniform(0.8, 1.2, n); T = g.uniform(0.1, 2.0, n)
+    sig = g.uniform(0.1, 0.6, n)
+    r = g.uniform(0.0, 0.08, n); q = g.uniform(0.002, 0.08, n)
+    is_call = (np.arange(n) % 2).astype(np.uint8)
+    r[:64] = 0.0                      # calls with r = 0 (dual put with q' = 0); puts with r = 0 are never exercised
+    want, st_w = crr_c.crr_loop_fast(S0, K, T, r, q, sig, is_call, 1000, True)
+    got, st_g = op.crr_batch(S0, K, T, r, q, sig, is_call, 1000, american=True, return_status=True)
+    np.testing.assert_array_equal(st_g, st_w)
+    np.testing.assert_allclose(got, want, rtol=REL_CRR, atol=REL_CRR)
+    # a few of them against the reference-order loop (two pow() per node) as well
+    ref, _ = crr_c.crr_loop_ref(S0[:96], K[:96], T[:96], r[:96], q[:96], sig[:96], is_call[:96], 1000, True)
+    np.testing.assert_allclose(got[:96], ref, rtol=REL_CRR, atol=REL_CRR)
+    # ... and the banded kernel really took them (status 2 = declined, left to the full-width kernel)
+    nv.set_option("crr_band_only", 1)
+    try:
+        _, st = op.crr_batch(S0, K, T, r, q, sig, is_call, 1000, american=True, return_status=True)
+    finally:
+        nv.set_option("crr_band_only", 0)
+    calls = is_call == 1
+    hy_puts = (~calls) & (q > r) & (r > 1e-3)
+    assert np.count_nonzero(st[calls] == 0) >= 0.9 * np.count_nonzero(calls)
+    assert np.count_nonzero(st[hy_puts] == 0) >= 0.8 * np.count_nonzero(hy_puts)
+
+
 def test_crr_batch_flags_bad_contracts_without_aborting(op):
     S0 = np.array([100.0, 100.0, 100.0]); K = np.array([100.0, 100.0, 90.0])
     T = np.array([1.0, 2.0, 1.0]); r = np.array([0.05, 0.30, 0.05]); q = np.zeros(3)
@@ -744,3 +776,37 @@ def test_dupire_table_on_device_matches_reference_and_oracle(op):
     b = op.barrier_price(pr.milstein_local_vol_paths(100.0, 0.05, 0.02, 1.0, 252, 200_000, host, seed=5),
                          100.0, 0.05, 1.0, "call", 130.0, "up-and-out")
     assert abs(a[0] - b[0]) <= 1e-6 * b[0]
+
+
+# ------------------------------------------------------------------------------ host threads
+def test_concurrent_host_threads_get_the_serial_results(op):
+    """ctypes releases the GIL around a call and the library owns one context: calls from several
+    Python threads must be serialised by the library (include/optp_b200.h, "threads"), never
+    interleaved on the shared scratch."""
+    from concurrent.futures import ThreadPoolExecutor
+    opt = op.OptionSpec(100.0, 110.0, 1.0, 0.03, 0.2)
+    g = np.random.default_rng(11)
+    n = 3000
+    S0 = g.uniform(50, 150, n)
+    K = S0 * g.uniform(0.8, 1.2, n)
+    T = g.uniform(0.1, 2.0, n)
+    sig = g.uniform(0.1, 0.6, n)
+
+    def mc(seed):
+        return op.euro_price_mc(opt, "call", n_paths=300_000, seed=seed)
+
+    def path(seed):
+        p = op.gbm_paths(100.0, 0.05, 0.0, 0.2, 1.0, 64, 200_000, seed=seed)
+        return op.barrier_price(p, 100.0, 0.05, 1.0, "call", 130.0, "up-and-out")
+
+    def tree(lo):
+        s = slice(lo, lo + 1000)
+        return op.crr_batch(S0[s], K[s], T[s], 0.03, 0.0, sig[s], 0, N=300, american=True)
+
+    jobs = [(mc, 1), (path, 2), (tree, 0), (mc, 3), (path, 4), (tree, 1000), (mc, 5), (tree, 2000), (path, 6)] * 3
+    serial = [f(x) for f, x in jobs]
+    with ThreadPoolExecutor(max_workers=6) as ex:
+        futs = [ex.submit(f, x) for f, x in jobs]
+        threaded = [f.result() for f in futs]
+    for a, b in zip(serial, threaded):
+        np.testing.assert_array_equal(np.asarray(a), np.asarray(b))
