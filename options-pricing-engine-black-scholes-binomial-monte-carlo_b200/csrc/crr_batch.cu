@@ -960,6 +960,7 @@ __global__ void __launch_bounds__(256) crr_cta_kernel(CrrArgs a) {
     double* bufB = sm + stride;
     double* W = sm + 2 * stride;  // u^(2j)
     for (unsigned long long o = blockIdx.x; o < a.n; o += gridDim.x) {
+        if (a.todo_only && a.status[o] != a.todo_only) continue;  // (block-uniform)
         const Lattice L = make_lattice(a, o);
         if (!L.ok) {
             if (threadIdx.x == 0) {
@@ -1020,6 +1021,25 @@ static int launch_full_warp(const CrrArgs& a, int american, cudaStream_t st) {
     return 0;
 }
 
+// Full-width pass (honours a.todo_only): one option per warp up to N = 1023, one per CTA beyond.
+static int launch_full(const CrrArgs& a, int american, cudaStream_t st) {
+    if (a.N <= 1023) return launch_full_warp(a, american, st);
+    Context& c = ctx();
+    const size_t smem = sizeof(double) * 3 * (size_t)(a.N + 2);
+    const unsigned long long cap = (unsigned long long)c.n_sm * 8;
+    const unsigned int grid = (unsigned int)(a.n < cap ? a.n : cap);
+    if (american) {
+        OPTP_CUDA(cudaFuncSetAttribute(crr_cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        crr_cta_kernel<true><<<grid, 256, smem, st>>>(a);
+    } else {
+        OPTP_CUDA(cudaFuncSetAttribute(crr_cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        crr_cta_kernel<false><<<grid, 256, smem, st>>>(a);
+    }
+    c.launches++;
+    OPTP_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // Work lists of the two-zone kernel: per slot two lists of {count, n items}.
 static size_t crr_worklist_bytes(unsigned long long n) {
     return ((size_t)(n + 1) * sizeof(unsigned int) + 255) & ~(size_t)255;
@@ -1038,102 +1058,87 @@ static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st, int sl
     a.wl_out = nullptr;
     if (a.n == 0) return 0;
     if (a.n >= (1ull << 32)) return set_error(OPTP_E_TOO_LARGE, "a CRR batch holds at most 2^32 - 1 contracts");
-    if (a.N <= 1023) {
-        if (american && !c.crr_no_band) {
-            // pass 1: banded kernel (American puts with r > q); pass 2: whatever it left at status 2
-            int per_sm = 0;
-            // options per warp of the two-zone kernel: 4 once the batch fills the machine that way
-            int G = 0;
-            if (c.crr_band_kernel == 2) {
-                G = c.crr_zone_group;
-                if (G == 0) {
-                    const unsigned long long warps = (unsigned long long)c.n_sm * 16;
-                    G = (a.n >= 4 * warps) ? 4 : (a.n >= 2 * warps) ? 2 : 1;
-                }
-            }
-            unsigned int* wl[2] = {nullptr, nullptr};
-            if (G >= 2) {
-                if (int e = crr_reserve_worklists(a.n)) return e;
-                const size_t list_bytes = crr_worklist_bytes(a.n);
-                char* base = (char*)c.work.p + (size_t)slot * ((c.work.cap / 2) & ~(size_t)255);
-                wl[0] = (unsigned int*)base;
-                wl[1] = (unsigned int*)(base + list_bytes);
-                OPTP_CUDA(cudaMemsetAsync(wl[0], 0, sizeof(unsigned int), st));
-                OPTP_CUDA(cudaMemsetAsync(wl[1], 0, sizeof(unsigned int), st));
-                a.wl_out = wl[0];
-            }
-            const void* fn = (G == 4)   ? (const void*)crr_zone_kernel<4>
-                             : (G == 2) ? (const void*)crr_zone_kernel<2>
-                             : (G == 1) ? (const void*)crr_zone_kernel<1>
-                                        : (const void*)crr_band_kernel;
-            static_assert(kBandWarps == kZoneWarps, "one grid computation for both banded kernels");
-            OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kZoneWarps * 32, 0));
-            if (per_sm < 1) per_sm = 1;
-            const unsigned long long per_warp = (G > 0) ? (unsigned long long)G : 1ull;
-            const unsigned long long want = (a.n + kBandWarps * per_warp - 1) / (kBandWarps * per_warp);
-            const unsigned long long cap = (unsigned long long)c.n_sm * per_sm;
-            const unsigned int grid = (unsigned int)(want < cap ? want : cap);
-            if (G == 4)
-                crr_zone_kernel<4><<<grid, kZoneWarps * 32, 0, st>>>(a);
-            else if (G == 2)
-                crr_zone_kernel<2><<<grid, kZoneWarps * 32, 0, st>>>(a);
-            else if (G == 1)
-                crr_zone_kernel<1><<<grid, kZoneWarps * 32, 0, st>>>(a);
-            else
-                crr_band_kernel<<<grid, kBandWarps * 32, 0, st>>>(a);
-            c.launches++;
-            OPTP_CUDA(cudaGetLastError());
-            // contracts whose band was too wide for G options per warp were appended to wl[0]: walk that
-            // list two per warp, then what is too wide even so (wl[1]) one per warp
-            const unsigned int* wl_in = a.wl_out;
-            for (int g2 = G / 2; g2 >= 1; g2 /= 2) {
-                a.wl_in = wl_in;
-                a.wl_out = (g2 == 2) ? wl[1] : nullptr;
-                const void* fn2 = (g2 == 2) ? (const void*)crr_zone_kernel<2> : (const void*)crr_zone_kernel<1>;
-                OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn2, kZoneWarps * 32, 0));
-                if (per_sm < 1) per_sm = 1;
-                const unsigned long long want2 = (a.n + kZoneWarps * g2 - 1) / (kZoneWarps * g2);
-                const unsigned long long cap2 = (unsigned long long)c.n_sm * per_sm;
-                const unsigned int grid2 = (unsigned int)(want2 < cap2 ? want2 : cap2);
-                if (g2 == 2)
-                    crr_zone_kernel<2><<<grid2, kZoneWarps * 32, 0, st>>>(a);
-                else
-                    crr_zone_kernel<1><<<grid2, kZoneWarps * 32, 0, st>>>(a);
-                c.launches++;
-                OPTP_CUDA(cudaGetLastError());
-                wl_in = a.wl_out;
-            }
-            a.wl_in = nullptr;
-            a.wl_out = nullptr;
-            a.todo_only = 0;
-            if (c.crr_band_only) return 0;  // diagnostics: leave the declined contracts unpriced
-            if (G > 0) {  // two-zone kernel: never-exercised calls were marked 3 -> European recursion
-                a.todo_only = 3;
-                if (int e = launch_full_warp(a, 0, st)) return e;
-            }
-            a.todo_only = 2;
-        }
-        return launch_full_warp(a, american, st);
-    } else {
+    if (a.N > 1023) {
         const size_t smem = sizeof(double) * 3 * (size_t)(a.N + 2);
         if (smem > 227 * 1024)
             return set_error(OPTP_E_TOO_LARGE, "N=%d needs %zu B of shared memory (max 232448)", a.N,
                              smem);
-        const unsigned long long cap = (unsigned long long)c.n_sm * 8;
-        const unsigned int grid = (unsigned int)(a.n < cap ? a.n : cap);
-        if (american) {
-            OPTP_CUDA(cudaFuncSetAttribute(crr_cta_kernel<true>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            crr_cta_kernel<true><<<grid, 256, smem, st>>>(a);
-        } else {
-            OPTP_CUDA(cudaFuncSetAttribute(crr_cta_kernel<false>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            crr_cta_kernel<false><<<grid, 256, smem, st>>>(a);
-        }
     }
-    c.launches++;
-    OPTP_CUDA(cudaGetLastError());
-    return 0;
+    if (american && !c.crr_no_band) {
+        // pass 1: banded kernel (American puts with r > q); pass 2: whatever it left at status 2
+        int per_sm = 0;
+        // options per warp of the two-zone kernel: 4 once the batch fills the machine that way
+        int G = 0;
+        if (c.crr_band_kernel == 2 || a.N > 1023) {  // (the single-zone kernel stops at N = 1023)
+            G = c.crr_zone_group;
+            if (G == 0) {
+                const unsigned long long warps = (unsigned long long)c.n_sm * 16;
+                G = (a.n >= 4 * warps) ? 4 : (a.n >= 2 * warps) ? 2 : 1;
+            }
+        }
+        unsigned int* wl[2] = {nullptr, nullptr};
+        if (G >= 2) {
+            if (int e = crr_reserve_worklists(a.n)) return e;
+            const size_t list_bytes = crr_worklist_bytes(a.n);
+            char* base = (char*)c.work.p + (size_t)slot * ((c.work.cap / 2) & ~(size_t)255);
+            wl[0] = (unsigned int*)base;
+            wl[1] = (unsigned int*)(base + list_bytes);
+            OPTP_CUDA(cudaMemsetAsync(wl[0], 0, sizeof(unsigned int), st));
+            OPTP_CUDA(cudaMemsetAsync(wl[1], 0, sizeof(unsigned int), st));
+            a.wl_out = wl[0];
+        }
+        const void* fn = (G == 4)   ? (const void*)crr_zone_kernel<4>
+                         : (G == 2) ? (const void*)crr_zone_kernel<2>
+                         : (G == 1) ? (const void*)crr_zone_kernel<1>
+                                    : (const void*)crr_band_kernel;
+        static_assert(kBandWarps == kZoneWarps, "one grid computation for both banded kernels");
+        OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kZoneWarps * 32, 0));
+        if (per_sm < 1) per_sm = 1;
+        const unsigned long long per_warp = (G > 0) ? (unsigned long long)G : 1ull;
+        const unsigned long long want = (a.n + kBandWarps * per_warp - 1) / (kBandWarps * per_warp);
+        const unsigned long long cap = (unsigned long long)c.n_sm * per_sm;
+        const unsigned int grid = (unsigned int)(want < cap ? want : cap);
+        if (G == 4)
+            crr_zone_kernel<4><<<grid, kZoneWarps * 32, 0, st>>>(a);
+        else if (G == 2)
+            crr_zone_kernel<2><<<grid, kZoneWarps * 32, 0, st>>>(a);
+        else if (G == 1)
+            crr_zone_kernel<1><<<grid, kZoneWarps * 32, 0, st>>>(a);
+        else
+            crr_band_kernel<<<grid, kBandWarps * 32, 0, st>>>(a);
+        c.launches++;
+        OPTP_CUDA(cudaGetLastError());
+        // contracts whose band was too wide for G options per warp were appended to wl[0]: walk that
+        // list two per warp, then what is too wide even so (wl[1]) one per warp
+        const unsigned int* wl_in = a.wl_out;
+        for (int g2 = G / 2; g2 >= 1; g2 /= 2) {
+            a.wl_in = wl_in;
+            a.wl_out = (g2 == 2) ? wl[1] : nullptr;
+            const void* fn2 = (g2 == 2) ? (const void*)crr_zone_kernel<2> : (const void*)crr_zone_kernel<1>;
+            OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn2, kZoneWarps * 32, 0));
+            if (per_sm < 1) per_sm = 1;
+            const unsigned long long want2 = (a.n + kZoneWarps * g2 - 1) / (kZoneWarps * g2);
+            const unsigned long long cap2 = (unsigned long long)c.n_sm * per_sm;
+            const unsigned int grid2 = (unsigned int)(want2 < cap2 ? want2 : cap2);
+            if (g2 == 2)
+                crr_zone_kernel<2><<<grid2, kZoneWarps * 32, 0, st>>>(a);
+            else
+                crr_zone_kernel<1><<<grid2, kZoneWarps * 32, 0, st>>>(a);
+            c.launches++;
+            OPTP_CUDA(cudaGetLastError());
+            wl_in = a.wl_out;
+        }
+        a.wl_in = nullptr;
+        a.wl_out = nullptr;
+        a.todo_only = 0;
+        if (c.crr_band_only) return 0;  // diagnostics: leave the declined contracts unpriced
+        if (G > 0) {  // two-zone kernel: never-exercised calls were marked 3 -> European recursion
+            a.todo_only = 3;
+            if (int e = launch_full(a, 0, st)) return e;
+        }
+        a.todo_only = 2;
+    }
+    return launch_full(a, american, st);
 }
 
 }  // namespace optp

@@ -180,7 +180,7 @@ def test_crr_cfg2_sample_against_c_oracle(op):
         np.testing.assert_allclose(got, want, rtol=REL_CRR, atol=REL_CRR)
 
 
-@pytest.mark.parametrize("N", [1, 2, 31, 32, 33, 255, 256, 257, 1000, 1023, 1024, 1500])
+@pytest.mark.parametrize("N", [1, 2, 31, 32, 33, 255, 256, 257, 1000, 1023, 1024, 1500, 4000, 9000])
 def test_crr_ragged_sizes_against_oracle(op, N):
     g = np.random.default_rng(N)
     n = 9
