@@ -678,11 +678,11 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
     const unsigned long long warp0 = (unsigned long long)blockIdx.x * kZoneWarps + wib;
     const unsigned long long nwarps = (unsigned long long)gridDim.x * kZoneWarps;
     // retry passes walk the compacted list of contracts the previous layout was too narrow for
-    const unsigned long long n_work = a.wl_in ? (unsigned long long)a.wl_in[0] : a.n;
+    const unsigned int n_work = a.wl_in ? a.wl_in[0] : (unsigned int)a.n;  // (launch_crr: n < 2^32)
     for (unsigned long long o0 = warp0 * G; o0 < n_work; o0 += nwarps * G) {
         const unsigned long long og = o0 + (unsigned long long)(lane / LG);
         const bool wanted = og < n_work;
-        const unsigned long long ow = wanted ? og : (n_work - 1);
+        const unsigned long long ow = wanted ? og : (unsigned long long)(n_work - 1);
         const unsigned long long o = a.wl_in ? (unsigned long long)a.wl_in[1 + ow] : ow;
         // An American call with q > 0 is priced as its DUAL PUT: on a CRR lattice (u*d = 1)
         //     C_k[j](S0, K, r, q) = P_k[k - j](S0' = K, K' = S0, r' = q, q' = r)
@@ -724,12 +724,16 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
         // r > 0, cont >= S*e^{-q dt} - K*disc > S - K at every node, so binomial.py:30-36 always keeps the
         // continuation value.  Such contracts (status 3) go to the European full-width kernel, which is
         // the same recursion without the per-node exercise value and compare.
-        const unsigned char declined = (is_call && q_in <= 0.0 && -expm1(-r_in * dt) > 1e-9) ? 3 : 2;
+        // (recomputed from the contract where it is needed: one register less across the walk)
+        auto declined_code = [&]() -> unsigned char {
+            const double r0 = a.r[o];
+            return (a.is_call[o] != 0 && a.q[o] <= 0.0 && -expm1(-r0 * (a.T[o] / (double)N)) > 1e-9) ? 3 : 2;
+        };
         // an option that is not walked (declined, failed, past the end of the batch) rides along with
         // a harmless plan; `fail` keeps its result from being written
         bool fail = !eligible, too_wide = false;
         if (!__any_sync(0xffffffffu, eligible)) {
-            if (wanted && L.ok && gl == 0) a.status[o] = declined;
+            if (wanted && L.ok && gl == 0) a.status[o] = declined_code();
             continue;
         }
         // exercise values: node m of Z (m = index - w0) is sgn*S0*u^(2*(w0 + (m & ~3)) - k) * u^(2*(m & 3)),
@@ -746,7 +750,8 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             }
         }
         const int quad0 = (gl * G) & ~3;  // first node of this lane's quad, relative to w0
-        const double thr = K * 8.2718061255302767e-25;  // 2^-80 K
+        const double sS0 = L.sgn * L.S0;  // (exact: sgn = -1 for every option that is walked)
+        const double thr = K * 8.2718061255302767e-25;  // 2^-80 K (K itself is not kept across the walk)
         const double ln_u = log(L.u);
         double back_full = 1.0;  // pd^kZoneSeg by square-and-multiply
         {
@@ -775,7 +780,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
                 fail = too_wide = true;
             const double w = fmin(fmax(floor(jz) - 28.0, 0.0), (double)max(0, N + 1 - 32));
             w0 = fail ? 0 : (int)w;
-            const double sbN = L.sgn * L.S0 * exp(ln_u * (double)(2 * (w0 + quad0) - N));
+            const double sbN = sS0 * exp(ln_u * (double)(2 * (w0 + quad0) - N));
 #pragma unroll
             for (int i = 0; i < BZ; ++i) {
                 const double e = fma(sbN, ulo[i], L.sK);
@@ -783,7 +788,11 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
                 exmask |= (e > 0.0) ? (1u << i) : 0u;
             }
         }
-        while (true) {
+        // Level k goes to the tile (node-ordered) and its band [jlo, jhi) is measured per option: once for
+        // level N here, then after every segment.  (The level-N specials live OUTSIDE the walk loop: the loop
+        // body is what the instruction caches have to hold.)
+        int jlo = 0, jhi = 0;
+        auto measure_band = [&]() {
             // ---- level k goes to the tile (node-ordered); measure its band [jlo, jhi) per option -----
             const int BC = G * M;
 #pragma unroll
@@ -798,7 +807,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             const unsigned int has_cont = (__ballot_sync(0xffffffffu, first_cont < BZ) >> gb) & gmask;
             const int f_cont = has_cont ? (__ffs(has_cont) - 1) : 0;  // always one of the option's lanes
             const int s_cont = __shfl_sync(0xffffffffu, first_cont, gb + f_cont);
-            int jlo = has_cont ? (w0 + f_cont * BZ + s_cont) : (w0 + 32);
+            jlo = has_cont ? (w0 + f_cont * BZ + s_cont) : (w0 + 32);
             // jhi = 1 + last node worth more than 2^-80 K.  A put's value falls with the node index, so
             // the live nodes are a prefix of the window: find the last lane whose FIRST node is live
             // from the registers, then count the live nodes of that lane's chunk from the tile.
@@ -823,40 +832,51 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
                 if (e < chunk_n) live = tile[zone_pad(chunk0 + e)] > thr && (w0 + chunk0 + e) <= k;
                 n_live += __popc((__ballot_sync(0xffffffffu, live) >> gb) & gmask);
             }
-            int jhi = w0 + chunk0 + n_live;
+            jhi = w0 + chunk0 + n_live;
             if (jhi < jlo) jhi = jlo;
             // the window bottom must still be inside the exercise region (or be node 0)
             if (w0 > 0 && jlo <= w0) fail = true;
-            if (k == 0 || !__any_sync(0xffffffffu, !fail)) break;  // nothing left to walk in this warp
-            int width_old = 32 * (1 + M);
-            if (k == N && __any_sync(0xffffffffu, j1 <= N + 1 && !fail)) {
-                // q > r (see `jump`): from level N-1 on the boundary is the first node above S1, far below
-                // the strike.  Level N is re-tabulated in the tile from a lower origin, so that the
-                // generic re-pack below finds the payoffs of the in-the-money continuation nodes there.
-                const bool mine = !fail && j1 <= N + 1 && j1 < jlo;  // (a warp mate's jump must not touch this option)
-                int wl = w0, span = 0;
-                if (mine) {
-                    jlo = j1;
-                    wl = max(0, j1 - (kZoneSeg + 2));
-                    span = w0 + 32 - wl;
-                    if (span > 32 * (1 + kMaxM)) fail = too_wide = true;
-                }
-                __syncwarp();
-                if (mine && !fail && wl < w0) {
-                    const double u2 = exp(2.0 * ln_u);  // (L.u is not kept live across the walk)
-                    for (int e0 = 4 * gl; e0 < span; e0 += 4 * LG) {
-                        const double sbq = L.sgn * L.S0 * exp(ln_u * (double)(2 * (wl + e0) - N));
-                        double f = 1.0;
-                        for (int i = 0; i < 4; ++i, f *= u2) {
-                            const double e = fma(sbq, f, L.sK);
-                            if (e0 + i < span) tile[zone_pad(e0 + i)] = e > 0.0 ? e : 0.0;
-                        }
-                    }
-                    w0 = wl;
-                    width_old = span;
-                }
-                __syncwarp();
+        };
+        measure_band();
+        int width_old = 32;  // M = 0 at level N
+        if (k > 0 && __reduce_or_sync(0xffffffffu, (j1 <= N + 1 && !fail) ? 1u : 0u) != 0u) {
+            // q > r (see `jump`): from level N-1 on the boundary is the first node above S1, far below
+            // the strike.  Level N is re-tabulated in the tile from a lower origin, so that the
+            // generic re-pack below finds the payoffs of the in-the-money continuation nodes there.
+            const bool mine = !fail && j1 <= N + 1 && j1 < jlo;  // (a warp mate's jump must not touch this option)
+            int wl = w0, span = 0;
+            if (mine) {
+                jlo = j1;
+                wl = max(0, j1 - (kZoneSeg + 2));
+                span = w0 + 32 - wl;
+                if (span > 32 * (1 + kMaxM)) fail = too_wide = true;
             }
+            const bool refill = mine && !fail && wl < w0;
+            if (!refill) span = 0;
+            // (warp-uniform trip count: the shuffles of the walk need a provably converged warp)
+            const int rounds = (__reduce_max_sync(0xffffffffu, span) + 4 * LG - 1) / (4 * LG);
+            __syncwarp();  // the band scan above has finished reading the tile
+            const double u2 = exp(2.0 * ln_u);  // (L.u is not kept live across the walk)
+            for (int it = 0; it < rounds; ++it) {
+                const int e0 = 4 * (gl + LG * it);
+                const double sbq = sS0 * exp(ln_u * (double)(2 * (wl + e0) - N));
+                double f = 1.0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i, f *= u2) {
+                    const double e = fma(sbq, f, L.sK);
+                    if (e0 + i < span) tile[zone_pad(e0 + i)] = e > 0.0 ? e : 0.0;
+                }
+            }
+            if (refill) {
+                w0 = wl;
+                width_old = span;
+            }
+            __syncwarp();
+        }
+        while (true) {
+            // (REDUX, not a vote: ptxas treats the result of __any_sync as divergent, and a divergent exit here
+            // puts a BRA.DIV convergence check and a dozen register moves into every level loop below)
+            if (k == 0 || __reduce_or_sync(0xffffffffu, fail ? 0u : 1u) == 0u) break;  // nothing left to walk in this warp
             // ---- next segment: levels k-1 ... k-nlev, fixed schedule -------------------------------
             const int nlev = min(kZoneSeg, k);
             const int top = min(jhi, k + 1);  // exclusive; node `top` of level k is 0 (or dead)
@@ -878,7 +898,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             const int BCn = G * Mn;
             // ---- re-pack level k from (w0, M) to (w0n, Mn) ------------------------------------------
             // this lane's first Z node of the new layout at level k: sgn*S0*u^(2j - k)
-            const double sb = L.sgn * L.S0 * exp(ln_u * (double)(2 * (w0n + quad0) - k));
+            const double sb = sS0 * exp(ln_u * (double)(2 * (w0n + quad0) - k));
 #pragma unroll
             for (int i = 0; i < BZ; ++i) {
                 const int j = w0n + gl * BZ + i;
@@ -932,6 +952,8 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             if (w0 > 0 && bottom_ex != nlev) fail = true;
             if (top_ex != 0) fail = true;
             k -= nlev;
+            measure_band();
+            width_old = 32 * (1 + M);
         }
         // level 0: node 0 is in the window (w0 == 0) or below it (then it is an exercise node)
         const double v0 = __shfl_sync(0xffffffffu, z[0], gb);
@@ -940,10 +962,12 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
                 if (too_wide && G > 1) {
                     a.wl_out[1 + atomicAdd(a.wl_out, 1u)] = (unsigned int)o;  // status is settled by a later pass
                 } else {
-                    a.status[o] = declined;
+                    a.status[o] = declined_code();
                 }
             } else {
-                a.price[o] = (w0 == 0) ? v0 : (K - L.S0);
+                // below the window at level 0: immediate exercise, K - S0 (for a call, through its dual put, S0 - K)
+                const double intrinsic = (a.is_call[o] != 0) ? (a.S0[o] - a.K[o]) : (a.K[o] - a.S0[o]);
+                a.price[o] = (w0 == 0) ? v0 : intrinsic;
                 a.status[o] = 0;
             }
         }
