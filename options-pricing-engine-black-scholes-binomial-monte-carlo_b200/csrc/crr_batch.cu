@@ -38,6 +38,9 @@ struct CrrArgs {
     // wl_in = {count, items...} to walk instead of [0, n), or null; wl_out = list the too-wide ones go to
     const unsigned int* wl_in;
     unsigned int* wl_out;
+    // one-option-per-CTA kernel: level arrays in global memory (3*(N+2) doubles per CTA) when they do not
+    // fit in shared memory, else null
+    double* cta_scratch;
 };
 
 struct Lattice {
@@ -979,10 +982,11 @@ template <bool AMER>
 __global__ void __launch_bounds__(256) crr_cta_kernel(CrrArgs a) {
     extern __shared__ double sm[];
     const int N = a.N;
-    const int stride = N + 2;
-    double* bufA = sm;
-    double* bufB = sm + stride;
-    double* W = sm + 2 * stride;  // u^(2j)
+    const size_t stride = (size_t)N + 2;
+    double* base = a.cta_scratch ? a.cta_scratch + (size_t)blockIdx.x * 3 * stride : sm;
+    double* bufA = base;
+    double* bufB = base + stride;
+    double* W = base + 2 * stride;  // u^(2j)
     for (unsigned long long o = blockIdx.x; o < a.n; o += gridDim.x) {
         if (a.todo_only && a.status[o] != a.todo_only) continue;  // (block-uniform)
         const Lattice L = make_lattice(a, o);
@@ -1046,17 +1050,31 @@ static int launch_full_warp(const CrrArgs& a, int american, cudaStream_t st) {
 }
 
 // Full-width pass (honours a.todo_only): one option per warp up to N = 1023, one per CTA beyond.
-static int launch_full(const CrrArgs& a, int american, cudaStream_t st) {
-    if (a.N <= 1023) return launch_full_warp(a, american, st);
+static int launch_full(const CrrArgs& a_in, int american, cudaStream_t st, int slot) {
+    if (a_in.N <= 1023) return launch_full_warp(a_in, american, st);
     Context& c = ctx();
-    const size_t smem = sizeof(double) * 3 * (size_t)(a.N + 2);
+    CrrArgs a = a_in;
+    size_t smem = sizeof(double) * 3 * (size_t)(a.N + 2);
     const unsigned long long cap = (unsigned long long)c.n_sm * 8;
-    const unsigned int grid = (unsigned int)(a.n < cap ? a.n : cap);
+    unsigned int grid = (unsigned int)(a.n < cap ? a.n : cap);
+    a.cta_scratch = nullptr;
+    if (smem > 227 * 1024) {
+        // deeper than shared memory holds (N > 9685): ping-pong level arrays in global memory, at most 1 GiB per
+        // pipeline slot (they stay in L2 up to N ~ 10^4 x 148 CTAs)
+        const size_t per_cta = smem, budget = (size_t)1 << 30;
+        const size_t fit = budget / per_cta;
+        if (fit < 1) return set_error(OPTP_E_TOO_LARGE, "N=%d needs %zu B of level storage per option", a.N, per_cta);
+        if (grid > fit) grid = (unsigned int)fit;
+        const size_t slot_bytes = ((size_t)grid * per_cta + 255) & ~(size_t)255;
+        if (int e = arena_reserve(c.cta_scratch, 2 * slot_bytes)) return e;
+        a.cta_scratch = (double*)((char*)c.cta_scratch.p + (size_t)slot * ((c.cta_scratch.cap / 2) & ~(size_t)255));
+        smem = 0;
+    }
     if (american) {
-        OPTP_CUDA(cudaFuncSetAttribute(crr_cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem) OPTP_CUDA(cudaFuncSetAttribute(crr_cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         crr_cta_kernel<true><<<grid, 256, smem, st>>>(a);
     } else {
-        OPTP_CUDA(cudaFuncSetAttribute(crr_cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem) OPTP_CUDA(cudaFuncSetAttribute(crr_cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         crr_cta_kernel<false><<<grid, 256, smem, st>>>(a);
     }
     c.launches++;
@@ -1080,14 +1098,9 @@ static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st, int sl
     a.todo_only = 0;
     a.wl_in = nullptr;
     a.wl_out = nullptr;
+    a.cta_scratch = nullptr;
     if (a.n == 0) return 0;
     if (a.n >= (1ull << 32)) return set_error(OPTP_E_TOO_LARGE, "a CRR batch holds at most 2^32 - 1 contracts");
-    if (a.N > 1023) {
-        const size_t smem = sizeof(double) * 3 * (size_t)(a.N + 2);
-        if (smem > 227 * 1024)
-            return set_error(OPTP_E_TOO_LARGE, "N=%d needs %zu B of shared memory (max 232448)", a.N,
-                             smem);
-    }
     if (american && !c.crr_no_band) {
         // pass 1: banded kernel (American puts with r > q); pass 2: whatever it left at status 2
         int per_sm = 0;
@@ -1158,11 +1171,11 @@ static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st, int sl
         if (c.crr_band_only) return 0;  // diagnostics: leave the declined contracts unpriced
         if (G > 0) {  // two-zone kernel: never-exercised calls were marked 3 -> European recursion
             a.todo_only = 3;
-            if (int e = launch_full(a, 0, st)) return e;
+            if (int e = launch_full(a, 0, st, slot)) return e;
         }
         a.todo_only = 2;
     }
-    return launch_full(a, american, st);
+    return launch_full(a, american, st, slot);
 }
 
 }  // namespace optp

@@ -103,6 +103,7 @@ static void release_resources(Context& c) {
     arena_free(c.table_f4);
     arena_free(c.table_f64);
     arena_free(c.work);
+    arena_free(c.cta_scratch);
     if (c.partials) cudaFree(c.partials);
     if (c.ticket) cudaFree(c.ticket);
     if (c.stats_dev) cudaFree(c.stats_dev);

@@ -27,6 +27,7 @@ struct Context {
     double* stats_host = nullptr; // pinned mirror
     Arena in0, in1, out0, out1, table_f32, table_f64, table_f4;
     Arena work;  // work lists of the two-zone CRR kernel (crr_batch.cu)
+    Arena cta_scratch;  // level arrays of the one-option-per-CTA CRR kernel when N > 9685
     uint32_t table_steps = 0, table_nodes = 0;
     uint64_t launches = 0;
     bool lv_direct = false;      // "lv_direct" = 1: window nodes gathered from global/L1, no smem staging

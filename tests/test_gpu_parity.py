@@ -196,6 +196,31 @@ def test_crr_ragged_sizes_against_oracle(op, N):
         assert np.all(np.isnan(got[~ok]))
 
 
+def test_crr_trees_deeper_than_shared_memory(op):
+    """N > 9685: the one-option-per-CTA kernel keeps its level arrays in global memory; American puts still
+    take the two-zone passes first.  Against the C restatement (oracle/crr_tree.c)."""
+    from oracle import crr_c
+    from optpricer_b200 import _native as nv
+    g = np.random.default_rng(12)
+    n = 6
+    S0 = g.uniform(80, 120, n); K = S0 * g.uniform(0.9, 1.1, n); T = g.uniform(0.3, 1.5, n)
+    sig = g.uniform(0.15, 0.5, n); r = np.full(n, 0.04); q = np.array([0.0, 0.01, 0.0, 0.02, 0.0, 0.06])
+    is_call = np.array([0, 0, 1, 1, 0, 0], dtype=np.uint8)
+    N = 12_000
+    for american in (True, False):
+        want, st_w = crr_c.crr_loop_fast(S0, K, T, r, q, sig, is_call, N, american)
+        got, st_g = op.crr_batch(S0, K, T, r, q, sig, is_call, N, american=american, return_status=True)
+        np.testing.assert_array_equal(st_g, st_w)
+        np.testing.assert_allclose(got, want, rtol=REL_CRR, atol=REL_CRR)
+    nv.set_option("crr_band", 0)
+    try:
+        full = op.crr_batch(S0, K, T, r, q, sig, is_call, N, american=True)
+    finally:
+        nv.set_option("crr_band", 1)
+    banded = op.crr_batch(S0, K, T, r, q, sig, is_call, N, american=True)
+    np.testing.assert_allclose(full, banded, rtol=REL_CRR, atol=REL_CRR)
+
+
 def test_crr_banded_kernel_equals_full_width_kernel(op):
     """The banded American-put kernels (exercise-region / zero-region cuts; two-zone kernel with 1, 2
     and 4 options per warp, and the earlier single-zone kernel) against the full-width kernel on the
