@@ -614,7 +614,7 @@ def main():
             "roofline": {"bound": "fp32_pipe", "achieved": mc_kernel_rate * OPS_PER_PATH_STEP["gbm_barrier"] / 1e12,
                          "peak": p32 / 1e12, "unit": "T lane-ops/s",
                          "frac": mc_kernel_rate * OPS_PER_PATH_STEP["gbm_barrier"] / p32,
-                         "traffic": 107520,  # ncu --set full, profiles/r1_ncu_full_final.md: dram read 0.1 MB, write 0 per launch
+                         "traffic": 107264,  # ncu --set full of THIS launch (profiles/r1_ncu_full_bench_gbm.md): dram read 107 KB, write 0
                          "ops_per_path_step": OPS_PER_PATH_STEP["gbm_barrier"], "kernel_ms": mc_kernel_ms,
                          "path_steps_per_s_per_gpu": mc_kernel_rate,
                          "peak_source": "optp_microbench FFMA issue rate measured in this run (MEASURED_PEAKS.json "
@@ -630,7 +630,12 @@ def main():
                 "roofline": {"bound": "smem", "achieved": crr_rate_gpu * CRR_SMEM_BYTES_PER_OPTION / 1e9,
                              "peak": peaks["smem_lds64_bytes"] / 1e9, "unit": "GB/s",
                              "frac": crr_rate_gpu * CRR_SMEM_BYTES_PER_OPTION / peaks["smem_lds64_bytes"],
-                             "traffic": None, "bytes_per_option": CRR_SMEM_BYTES_PER_OPTION,
+                             # ncu --set full of this launch at 1M contracts (profiles/r1_ncu_full_bench_zone.md):
+                             # dram read 49.10 MB + write 0.38 MB (the 57 MB of contract columns and results)
+                             "traffic": 49_477_120 if n_c == 1_000_000 else None,
+                             "ncu_pipe_pct": {"fp64": 48.6, "issue_slots": 58.1, "smem_wavefronts": 29.8,
+                                              "source": "profiles/r1_ncu_full_bench_zone.md"},
+                             "bytes_per_option": CRR_SMEM_BYTES_PER_OPTION,
                              "fp64_frac": crr_rate_gpu * CRR_FP64_OPS_PER_OPTION / peaks["fp64_dfma_lane_ops"],
                              "note": "ALGORITHMIC figures (500 500 node updates x 24 B / x 5 FP64 ops per option) over "
                                      "measured LDS.64 bandwidth / DFMA rate. They exceed 1 because (a) tree levels live in "

@@ -1,0 +1,34 @@
+#!/bin/bash
+# Round-end evidence run (one B200): GPU tests, bench line, ncu launch list of the bench command,
+# ncu --set full captures.  Outputs land in gpurun_out/ (<= 64 MiB comes back: the multi-kernel report is
+# summarised on the box and dropped); the judged copies are committed under profiles/ (profiles/README.md).
+# Usage: bash scripts/round_artifacts.sh TAG [tests|bench|ncu ...]
+set -u
+TAG=${1:-r1}; shift || true
+WHAT=${*:-tests bench ncu}
+O=gpurun_out
+mkdir -p $O
+for w in $WHAT; do case $w in
+tests)
+  python -m pytest tests -m gpu -q > $O/pytest_gpu_$TAG.log 2>&1; echo "pytest exit $?" >> $O/pytest_gpu_$TAG.log
+  python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke_$TAG.log 2>&1; echo "smoke exit $?" >> $O/smoke_$TAG.log ;;
+bench)
+  python bench.py > $O/bench_$TAG.json 2> $O/bench_$TAG.err; echo "bench exit $?" >> $O/bench_$TAG.err
+  python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_ref_$TAG.json 2>> $O/bench_$TAG.err
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches_$TAG.csv \
+      python bench.py --steps 3 --warmup 3 --skip-cpu --skip-extra > $O/ncu_launch_$TAG.log 2>&1 ;;
+ncu)
+  # the bench's own launches of the two headline kernels (bench-size), one capture each
+  ncu --set full --clock-control none --import-source on -k regex:path_fp32 -s 4 -c 1 -f -o $O/prof_${TAG}_bench_gbm \
+      python bench.py --steps 1 --warmup 3 --skip-cpu --skip-extra > $O/ncu_full_gbm_$TAG.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:"crr_zone_kernel<4>" -s 4 -c 1 -f -o $O/prof_${TAG}_bench_zone \
+      python bench.py --steps 1 --warmup 3 --skip-cpu --skip-extra > $O/ncu_full_zone_$TAG.log 2>&1
+  # every production kernel at a size ncu replays quickly (third repetition of scripts/profile_target.py)
+  ncu --set full --clock-control none -k regex:"path_fp32|lv_fp32|terminal_fp32|crr_warp|crr_zone" -s 20 -c 10 -f \
+      -o /tmp/prof_${TAG}_all python scripts/profile_target.py > $O/ncu_full_all_$TAG.log 2>&1
+  python scripts/ncu_summary.py /tmp/prof_${TAG}_all.ncu-rep > $O/ncu_full_all_$TAG.md 2>> $O/ncu_full_all_$TAG.log
+  for r in bench_gbm bench_zone; do
+    python scripts/ncu_summary.py $O/prof_${TAG}_$r.ncu-rep > $O/ncu_full_${r}_$TAG.md 2>> $O/ncu_full_all_$TAG.log
+  done ;;
+esac; done
+du -sh $O; ls -la $O | tail -20
