@@ -38,6 +38,9 @@ struct CrrArgs {
     // wl_in = {count, items...} to walk instead of [0, n), or null; wl_out = list the too-wide ones go to
     const unsigned int* wl_in;
     unsigned int* wl_out;
+    // {number of contracts left at status 2, at status 3} by the two-zone passes, or null: a full-width
+    // filter pass with nothing to do returns at once instead of scanning n status bytes
+    unsigned int* decl_count;
     // one-option-per-CTA kernel: level arrays in global memory (3*(N+2) doubles per CTA) when they do not
     // fit in shared memory, else null
     double* cta_scratch;
@@ -202,6 +205,7 @@ crr_warp_kernel(CrrArgs a) {
     double* tile = tiles[wib];
     const unsigned long long warp0 = (unsigned long long)blockIdx.x * kWarpsPerCta + wib;
     const unsigned long long nwarps = (unsigned long long)gridDim.x * kWarpsPerCta;
+    if (a.todo_only && a.decl_count && a.decl_count[a.todo_only - 2] == 0) return;  // nothing was left for this pass
     for (unsigned long long o = warp0; o < a.n; o += nwarps) {
         if (a.todo_only && a.status[o] != a.todo_only) continue;
         const Lattice L = make_lattice(a, o);
@@ -736,7 +740,11 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
         // a harmless plan; `fail` keeps its result from being written
         bool fail = !eligible, too_wide = false;
         if (!__any_sync(0xffffffffu, eligible)) {
-            if (wanted && L.ok && gl == 0) a.status[o] = declined_code();
+            if (wanted && L.ok && gl == 0) {
+                const unsigned char dc = declined_code();
+                a.status[o] = dc;
+                if (a.decl_count) atomicAdd(&a.decl_count[dc - 2], 1u);
+            }
             continue;
         }
         // exercise values: node m of Z (m = index - w0) is sgn*S0*u^(2*(w0 + (m & ~3)) - k) * u^(2*(m & 3)),
@@ -965,7 +973,9 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
                 if (too_wide && G > 1) {
                     a.wl_out[1 + atomicAdd(a.wl_out, 1u)] = (unsigned int)o;  // status is settled by a later pass
                 } else {
-                    a.status[o] = declined_code();
+                    const unsigned char dc = declined_code();
+                    a.status[o] = dc;
+                    if (a.decl_count) atomicAdd(&a.decl_count[dc - 2], 1u);
                 }
             } else {
                 // below the window at level 0: immediate exercise, K - S0 (for a call, through its dual put, S0 - K)
@@ -987,6 +997,7 @@ __global__ void __launch_bounds__(256) crr_cta_kernel(CrrArgs a) {
     double* bufA = base;
     double* bufB = base + stride;
     double* W = base + 2 * stride;  // u^(2j)
+    if (a.todo_only && a.decl_count && a.decl_count[a.todo_only - 2] == 0) return;  // nothing was left for this pass
     for (unsigned long long o = blockIdx.x; o < a.n; o += gridDim.x) {
         if (a.todo_only && a.status[o] != a.todo_only) continue;  // (block-uniform)
         const Lattice L = make_lattice(a, o);
@@ -1087,7 +1098,7 @@ static size_t crr_worklist_bytes(unsigned long long n) {
     return ((size_t)(n + 1) * sizeof(unsigned int) + 255) & ~(size_t)255;
 }
 static int crr_reserve_worklists(unsigned long long n) {
-    return arena_reserve(ctx().work, 4 * crr_worklist_bytes(n) + 512);
+    return arena_reserve(ctx().work, 2 * (2 * crr_worklist_bytes(n) + 256) + 512);  // two slots of {list, list, counters}
 }
 
 // `slot` (0 or 1) selects the work-list scratch: launches that may be in flight together (the two
@@ -1098,6 +1109,7 @@ static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st, int sl
     a.todo_only = 0;
     a.wl_in = nullptr;
     a.wl_out = nullptr;
+    a.decl_count = nullptr;
     a.cta_scratch = nullptr;
     if (a.n == 0) return 0;
     if (a.n >= (1ull << 32)) return set_error(OPTP_E_TOO_LARGE, "a CRR batch holds at most 2^32 - 1 contracts");
@@ -1114,15 +1126,17 @@ static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st, int sl
             }
         }
         unsigned int* wl[2] = {nullptr, nullptr};
-        if (G >= 2) {
+        if (G >= 1) {
             if (int e = crr_reserve_worklists(a.n)) return e;
             const size_t list_bytes = crr_worklist_bytes(a.n);
             char* base = (char*)c.work.p + (size_t)slot * ((c.work.cap / 2) & ~(size_t)255);
             wl[0] = (unsigned int*)base;
             wl[1] = (unsigned int*)(base + list_bytes);
+            a.decl_count = (unsigned int*)(base + 2 * list_bytes);
             OPTP_CUDA(cudaMemsetAsync(wl[0], 0, sizeof(unsigned int), st));
             OPTP_CUDA(cudaMemsetAsync(wl[1], 0, sizeof(unsigned int), st));
-            a.wl_out = wl[0];
+            OPTP_CUDA(cudaMemsetAsync(a.decl_count, 0, 2 * sizeof(unsigned int), st));
+            if (G >= 2) a.wl_out = wl[0];
         }
         const void* fn = (G == 4)   ? (const void*)crr_zone_kernel<4>
                          : (G == 2) ? (const void*)crr_zone_kernel<2>
