@@ -157,6 +157,16 @@ __device__ __forceinline__ void box_muller(uint32_t w0, uint32_t w1, float& z0, 
     z1 = r * mufu_sin(a);
 }
 
+// Same pair scaled by s >= 0 at no cost: the caller passes c = -2 ln2 * s^2, so the radius comes out as
+// s * sqrt(-2 ln u) (z0 = s*Z0, z1 = s*Z1 with the SAME Z0, Z1 as box_muller on these words).
+__device__ __forceinline__ void box_muller_scaled(uint32_t w0, uint32_t w1, float c, float& z0, float& z1) {
+    const float u = u01_open_low(w0);
+    const float r = mufu_sqrt(c * mufu_lg2(u));
+    const float a = __uint2float_rn(w1) * 1.4629180792671596e-9f;
+    z0 = r * mufu_cos(a);
+    z1 = r * mufu_sin(a);
+}
+
 // Four random words of (seed, base path, block, stream), and the four normals they map to.
 // The two halves are separate so a kernel can request the words of block c+1 before it turns
 // the words of block c into normals: the integer Philox chain (IMAD.WIDE / LOP3) then overlaps
@@ -170,6 +180,11 @@ __device__ __forceinline__ uint4 philox_words(uint64_t seed, uint64_t path, uint
 __device__ __forceinline__ void normals_from_words(const uint4& w, float z[4]) {
     box_muller(w.x, w.y, z[0], z[1]);
     box_muller(w.z, w.w, z[2], z[3]);
+}
+
+__device__ __forceinline__ void normals_from_words_scaled(const uint4& w, float c, float z[4]) {
+    box_muller_scaled(w.x, w.y, c, z[0], z[1]);
+    box_muller_scaled(w.z, w.w, c, z[2], z[3]);
 }
 
 __device__ __forceinline__ void philox_normals4(uint64_t seed, uint64_t path, uint32_t block,
