@@ -11,8 +11,9 @@ american.  Methods on the hot path:
             row with seed=1, i.e. common random numbers -- share ONE simulated path set and are
             evaluated as several payoffs of the same launch (up to 16 per launch)
 All Monte Carlo items of the book are launched back to back by optp_mc_book and their statistics
-return in one device-to-host copy; with a torch.distributed process group the base paths of every
-item are sharded over the ranks and ONE all-reduce sums the whole book's statistics.
+return in one device-to-host copy; with a torch.distributed process group the items (or, for a book of
+few items, the base paths of every item) are sharded over the ranks and ONE all-reduce sums the whole
+book's statistics (shard_items).
 `method == "bs"` rows are closed-form Black-Scholes (not a hot path; priced on the host so a mixed
 book still comes back complete).  As in the reference, a failing row yields
 {"id", "price": None, "error": str} and does not abort the book.
@@ -115,10 +116,35 @@ def plan_book(rows, *, tree_steps=500, mc_paths=100_000, exotic_steps=500, exoti
     return results, crr_groups, items
 
 
-def book_stats(items, *, mode="fp32", rank=0, world=1):
-    """Run all Monte Carlo items through optp_mc_book for this rank's share of the base paths.
-    Returns the (n_blocks, 8) statistics array (item order, payoff order inside an item)."""
+def shard_items(items, rank, world):
+    """This rank's share of every item as a list of base-path ranges [(lo, hi), ...], one per item.
+
+    A book with many items (>= 4 per rank) is sharded BY ITEM: each item runs whole on one rank, so a rank
+    fills and launches 1/world of the work descriptors and no kernel shrinks to a launch-bound size; items
+    are dealt out longest-first to the least loaded rank (cost = base paths x steps), identically on every
+    rank.  A book with few items is sharded BY PATHS (every item on every rank, disjoint ranges of its base
+    paths).  Either way the statistics are additive, so ONE all-reduce over the (n_blocks, 8) array -- blocks
+    a rank did not touch stay zero -- gives the whole book (monte_carlo.py:67-74)."""
     from .distributed import shard_range
+    if world <= 1:
+        return [(0, it["n_base"]) for it in items]
+    if len(items) < 4 * world:
+        return [shard_range(it["n_base"], rank, world) for it in items]
+    cost = [it["n_base"] * (1 if it["kind"] == "terminal" else it["n_steps"]) for it in items]
+    order = sorted(range(len(items)), key=lambda i: (-cost[i], i))
+    load = [0] * world
+    owner = [0] * len(items)
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        owner[i] = r
+        load[r] += cost[i]
+    return [(0, it["n_base"]) if owner[i] == rank else (0, 0) for i, it in enumerate(items)]
+
+
+def book_stats(items, *, mode="fp32", rank=0, world=1):
+    """Run this rank's share (shard_items) of all Monte Carlo items through optp_mc_book.
+    Returns the (n_blocks, 8) statistics array (item order, payoff order inside an item)."""
+    shards = shard_items(items, rank, world)
     n_blocks = sum(len(it["rows"]) for it in items)
     stats = np.zeros((n_blocks, nv.NSTATS), dtype=np.float64)
     if not items:
@@ -127,8 +153,7 @@ def book_stats(items, *, mode="fp32", rank=0, world=1):
     arr = (nv.OptpBookItem * len(items))()
     specs = []
     live = 0
-    for it in items:
-        lo, hi = shard_range(it["n_base"], rank, world)
+    for it, (lo, hi) in zip(items, shards):
         a = arr[live]
         if hi == lo:
             it["_skip"] = True   # this rank has no paths of the item; its blocks stay zero

@@ -63,3 +63,27 @@ def test_synthetic_book_composition():
         if r["exotic_type"] == "barrier":
             assert (r["barrier"] > 100) == (r["barrier_type"] == "up-and-out")
     assert rows == book.synthetic_book(3000, n_paths=1000)
+
+
+def test_shard_items_by_item_for_large_books_and_by_paths_for_small_ones():
+    _, _, items = book.plan_book(book.synthetic_book(400, n_paths=1000), mc_paths=5000)
+    world = 8
+    shares = [book.shard_items(items, r, world) for r in range(world)]
+    cost = [it["n_base"] * (1 if it["kind"] == "terminal" else it["n_steps"]) for it in items]
+    loads = []
+    for sh in shares:
+        assert len(sh) == len(items)
+        loads.append(sum(c for c, (lo, hi) in zip(cost, sh) if hi > lo))
+    # every item runs whole on exactly one rank, and the ranks are balanced to within one item
+    for i, it in enumerate(items):
+        owners = [r for r in range(world) if shares[r][i] != (0, 0)]
+        assert len(owners) == 1 and shares[owners[0]][i] == (0, it["n_base"])
+    assert max(loads) - min(loads) <= max(cost)
+    # few items: every rank takes a disjoint range of every item's base paths
+    few = items[:5]
+    parts = [book.shard_items(few, r, world) for r in range(world)]
+    for i, it in enumerate(few):
+        edges = [parts[r][i] for r in range(world)]
+        assert edges[0][0] == 0 and edges[-1][1] == it["n_base"]
+        assert all(edges[r][1] == edges[r + 1][0] for r in range(world - 1))
+    assert book.shard_items(items, 0, 1) == [(0, it["n_base"]) for it in items]
