@@ -531,7 +531,7 @@ def main():
                           "fp32_pipe_frac": rate * OPS_PER_PATH_STEP["terminal"] / peaks["fp32_ffma_lane_ops"],
                           "price": pt[0], "stderr": pt[1]})
         # cfg 5 at BASELINE size: 10k-contract book (1/3 European, 1/3 barrier, 1/3 arithmetic Asian)
-        # through price_book, 5e6 base paths (1e7 effective) per contract; paths shard over the ranks
+        # through price_book, 5e6 base paths (1e7 effective) per contract; items are dealt over the ranks
         from optpricer_b200 import book as bk
         n_rows, book_paths = 10_000, 5_000_000
         rows = bk.synthetic_book(n_rows, n_paths=book_paths)
@@ -544,7 +544,7 @@ def main():
         steps_of = lambda r: 1 if r["method"] == "mc" else r["n_steps"]  # noqa: E731
         book_path_steps = sum(2.0 * book_paths * steps_of(r) for r in rows)
         workloads.append({"workload": "cfg5 book: 10k contracts (European / barrier / arithmetic Asian), price_book(), "
-                                      f"{2 * book_paths} effective paths each, 252 steps, sharded by paths over the ranks",
+                                      f"{2 * book_paths} effective paths each, 252 steps, items dealt over the ranks (book.shard_items)",
                           "value": book_path_steps / book_s, "unit": "path-steps/s (all GPUs, end to end)",
                           "contracts_per_s": n_rows / book_s, "seconds": book_s,
                           "priced": sum(1 for r in priced if r.get("price") is not None),
