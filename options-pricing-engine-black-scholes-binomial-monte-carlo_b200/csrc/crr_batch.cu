@@ -732,9 +732,12 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
         // continuation value.  Such contracts (status 3) go to the European full-width kernel, which is
         // the same recursion without the per-node exercise value and compare.
         // (recomputed from the contract where it is needed: one register less across the walk)
+        // The mirror image: an American put with r <= 0 and q >= 0 is never worth exercising early either
+        // (cont >= disc*K - S*e^{-q dt} >= K - S), so it takes the European recursion too.
         auto declined_code = [&]() -> unsigned char {
-            const double r0 = a.r[o];
-            return (a.is_call[o] != 0 && a.q[o] <= 0.0 && -expm1(-r0 * (a.T[o] / (double)N)) > 1e-9) ? 3 : 2;
+            const double r0 = a.r[o], q0 = a.q[o];
+            if (a.is_call[o] != 0) return (q0 <= 0.0 && -expm1(-r0 * (a.T[o] / (double)N)) > 1e-9) ? 3 : 2;
+            return (r0 <= 0.0 && q0 >= 0.0) ? 3 : 2;
         };
         // an option that is not walked (declined, failed, past the end of the batch) rides along with
         // a harmless plan; `fail` keeps its result from being written

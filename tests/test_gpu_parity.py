@@ -196,6 +196,30 @@ def test_crr_ragged_sizes_against_oracle(op, N):
         assert np.all(np.isnan(got[~ok]))
 
 
+def test_crr_never_exercised_contracts_take_the_european_recursion(op):
+    """American calls with q <= 0 < r and American puts with r <= 0 <= q are never exercised early
+    (binomial.py:30-36 always keeps the continuation value): they are routed to the European kernel and
+    must equal both the American full-width kernel and the European price bit for bit / to 1e-10."""
+    from optpricer_b200 import _native as nv
+    g = np.random.default_rng(31)
+    n = 2000
+    S0 = g.uniform(50, 150, n); K = S0 * g.uniform(0.8, 1.2, n); T = g.uniform(0.1, 2.0, n); sig = g.uniform(0.1, 0.6, n)
+    is_call = (np.arange(n) % 2).astype(np.uint8)
+    r = np.where(is_call == 1, g.uniform(0.001, 0.08, n), -g.uniform(0.0, 0.02, n))
+    r[2:40:2] = 0.0                                  # puts at r = 0 exactly
+    q = np.where(is_call == 1, -g.uniform(0.0, 0.02, n), g.uniform(0.0, 0.05, n))
+    amer, st = op.crr_batch(S0, K, T, r, q, sig, is_call, 500, american=True, return_status=True)
+    euro = op.crr_batch(S0, K, T, r, q, sig, is_call, 500, american=False)
+    assert np.all(st == 0)
+    np.testing.assert_array_equal(amer, euro)
+    nv.set_option("crr_band", 0)
+    try:
+        full = op.crr_batch(S0, K, T, r, q, sig, is_call, 500, american=True)
+    finally:
+        nv.set_option("crr_band", 1)
+    np.testing.assert_allclose(amer, full, rtol=REL_CRR, atol=REL_CRR)
+
+
 def test_crr_trees_deeper_than_shared_memory(op):
     """N > 9685: the one-option-per-CTA kernel keeps its level arrays in global memory; American puts still
     take the two-zone passes first.  Against the C restatement (oracle/crr_tree.c)."""
