@@ -605,6 +605,17 @@ __host__ __device__ constexpr int zone_max_m(int G) { return kZoneLaneC / G; }
 // lane-strided accesses of every layout spread over the banks); 248 = 8 (mod 16) staggers the options
 __host__ __device__ constexpr int zone_group_tile(int G) { return G == 4 ? 248 : G == 2 ? 456 : 856; }
 __device__ __forceinline__ int zone_pad(int e) { return e + (e >> 4); }
+// -DOPTP_ZONE_CHECK (OPTP_NVCC_FLAGS, build_native.py --force): every tile access of the two-zone kernel is
+// bounds-checked and traps -- the in-house stand-in for compute-sanitizer, run over the stress tests
+#ifdef OPTP_ZONE_CHECK
+__device__ __forceinline__ int zone_pad_checked(int e, int limit) {
+    if ((unsigned int)e >= (unsigned int)limit) __trap();
+    return zone_pad(e);
+}
+#define OPTP_ZP(e) zone_pad_checked((e), 32 * (1 + kMaxM))
+#else
+#define OPTP_ZP(e) zone_pad(e)
+#endif
 static_assert(32 * (1 + zone_max_m(4)) + (32 * (1 + zone_max_m(4)) >> 4) <= zone_group_tile(4), "tile too small");
 static_assert(32 * (1 + zone_max_m(2)) + (32 * (1 + zone_max_m(2)) >> 4) <= zone_group_tile(2), "tile too small");
 static_assert(32 * (1 + zone_max_m(1)) + (32 * (1 + zone_max_m(1)) >> 4) <= zone_group_tile(1), "tile too small");
@@ -810,10 +821,10 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             // ---- level k goes to the tile (node-ordered); measure its band [jlo, jhi) per option -----
             const int BC = G * M;
 #pragma unroll
-            for (int i = 0; i < BZ; ++i) tile[zone_pad(gl * BZ + i)] = z[i];
+            for (int i = 0; i < BZ; ++i) tile[OPTP_ZP(gl * BZ + i)] = z[i];
 #pragma unroll
             for (int i = 0; i < BCMAX; ++i)
-                if (i < BC) tile[zone_pad(32 + gl * BC + i)] = c[i];
+                if (i < BC) tile[OPTP_ZP(32 + gl * BC + i)] = c[i];
             __syncwarp();
             // jlo = first node that did not choose exercise
             const unsigned int contm = ~exmask & ((1u << BZ) - 1u);
@@ -843,7 +854,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             for (int rr = 0; rr < kScanRounds; ++rr) {
                 const int e = gl + LG * rr;
                 bool live = false;
-                if (e < chunk_n) live = tile[zone_pad(chunk0 + e)] > thr && (w0 + chunk0 + e) <= k;
+                if (e < chunk_n) live = tile[OPTP_ZP(chunk0 + e)] > thr && (w0 + chunk0 + e) <= k;
                 n_live += __popc((__ballot_sync(0xffffffffu, live) >> gb) & gmask);
             }
             jhi = w0 + chunk0 + n_live;
@@ -878,7 +889,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
 #pragma unroll
                 for (int i = 0; i < 4; ++i, f *= u2) {
                     const double e = fma(sbq, f, L.sK);
-                    if (e0 + i < span) tile[zone_pad(e0 + i)] = e > 0.0 ? e : 0.0;
+                    if (e0 + i < span) tile[OPTP_ZP(e0 + i)] = e > 0.0 ? e : 0.0;
                 }
             }
             if (refill) {
@@ -920,7 +931,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
                 double val;
                 if (jr < 0) val = fma(sb, ulo[i], L.sK);           // below the old window: exercise
                 else if (jr >= width_old || j >= top) val = 0.0;   // above the band
-                else val = tile[zone_pad(jr)];
+                else val = tile[OPTP_ZP(jr)];
                 z[i] = val;
             }
 #pragma unroll
@@ -928,7 +939,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
                 if (i < BCn) {
                     const int j = w0n + 32 + gl * BCn + i;
                     const int jr = j - w0;
-                    c[i] = (jr < 0 || jr >= width_old || j >= top) ? 0.0 : tile[zone_pad(jr)];
+                    c[i] = (jr < 0 || jr >= width_old || j >= top) ? 0.0 : tile[OPTP_ZP(jr)];
                 }
             }
             __syncwarp();
