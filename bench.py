@@ -615,6 +615,12 @@ def main():
                          "peak": p32 / 1e12, "unit": "T lane-ops/s",
                          "frac": mc_kernel_rate * OPS_PER_PATH_STEP["gbm_barrier"] / p32,
                          "traffic": 107264,  # ncu --set full of THIS launch (profiles/r1_ncu_full_bench_gbm.md): dram read 107 KB, write 0
+                         # the same figure against the nominal issue rate: 148 SMs x 128 FP32 lanes x the SM clock
+                         # sampled during the timed region (the measured FFMA rate above is ~91 % of it)
+                         "peak_nominal": 148 * 128 * (clocks or {}).get("sm_mhz", 1965.0) * 1e6 / 1e12
+                         if (clocks or {}).get("sm_mhz") else 148 * 128 * 1965.0e6 / 1e12,
+                         "frac_nominal": mc_kernel_rate * OPS_PER_PATH_STEP["gbm_barrier"]
+                         / (148 * 128 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6),
                          "ops_per_path_step": OPS_PER_PATH_STEP["gbm_barrier"], "kernel_ms": mc_kernel_ms,
                          "path_steps_per_s_per_gpu": mc_kernel_rate,
                          "peak_source": "optp_microbench FFMA issue rate measured in this run (MEASURED_PEAKS.json "

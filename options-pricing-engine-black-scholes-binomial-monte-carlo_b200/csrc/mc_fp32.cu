@@ -244,6 +244,9 @@ struct StepConst {
     float q_theta, q_E, q_c1, q_c2, q_K0, q_K1, q_K2, q_K3;
     // Merton jumps (log2 units): drift incl. compensator, mJ, sJ, mu = lam*dt, exp(-mu)
     float j_drift2, j_m2, j_s2, j_mu, j_p0;
+    // SABR: log2 sigma += s_nu2*Z2 + s_vdr2; beta = 1: log2 S += sigma*zc*s_sdt2 + sigma^2*s_mhdt2 + s_rq2;
+    // beta < 1: S += S*s_rqdt + sigma*S^beta*s_sdt*zc
+    float s_nu2, s_vdr2, s_beta, s_sdt2, s_mhdt2, s_rq2, s_rqdt, s_sdt;
 };
 
 // one time step of a base path and its mirror, per process
@@ -326,6 +329,45 @@ __device__ __forceinline__ void gbmm_step(LinState& p, LinState& m, float z, con
     }
 }
 
+// SABR with lognormal volatility (processes.py:199-215): the volatility is evolved exactly in log2 space
+// (one FFMA + one MUFU.EX2), then the price takes a log-Euler step (beta = 1) or an Euler step with the
+// reference's 1e-12 floor (beta < 1, S^beta = ex2(beta*lg2 S)).  The mirror negates both normals.
+template <int MASK, bool ANTI>
+__device__ __forceinline__ void sabr_step_log(LogState& p, LogState& m, float& lp, float& lm, float z0, float z1,
+                                              const StepConst& k) {
+    const float zc = fmaf(k.rho, z0, k.rhoc * z1);
+    {
+        lp += fmaf(k.s_nu2, z0, k.s_vdr2);
+        const float sg = mufu_ex2(lp);
+        p.x += fmaf(sg * zc, k.s_sdt2, fmaf(sg * sg, k.s_mhdt2, k.s_rq2));
+        observe_log<MASK>(p);
+    }
+    if (ANTI) {
+        lm += fmaf(-k.s_nu2, z0, k.s_vdr2);
+        const float sg = mufu_ex2(lm);
+        m.x += fmaf(-(sg * zc), k.s_sdt2, fmaf(sg * sg, k.s_mhdt2, k.s_rq2));
+        observe_log<MASK>(m);
+    }
+}
+
+template <int MASK, bool ANTI>
+__device__ __forceinline__ void sabr_step_lin(LinState& p, LinState& m, float& lp, float& lm, float z0, float z1,
+                                              const StepConst& k) {
+    const float zc = k.s_sdt * fmaf(k.rho, z0, k.rhoc * z1);
+    {
+        lp += fmaf(k.s_nu2, z0, k.s_vdr2);
+        const float sb = mufu_ex2(fmaf(k.s_beta, mufu_lg2(p.S), lp));  // sigma * S^beta
+        p.S = fmaxf(fmaf(sb, zc, fmaf(p.S, k.s_rqdt, p.S)), 1e-12f);
+        observe_lin<MASK>(p);
+    }
+    if (ANTI) {
+        lm += fmaf(-k.s_nu2, z0, k.s_vdr2);
+        const float sb = mufu_ex2(fmaf(k.s_beta, mufu_lg2(m.S), lm));
+        m.S = fmaxf(fmaf(-sb, zc, fmaf(m.S, k.s_rqdt, m.S)), 1e-12f);
+        observe_lin<MASK>(m);
+    }
+}
+
 template <int PROC, int MASK, bool ANTI>
 __global__ void __launch_bounds__(256, (PROC == OPTP_PROC_HESTON_FTE || PROC == OPTP_PROC_HESTON_QE) ? 4 : 5) path_fp32_kernel(PathArgs a) {
     extern __shared__ double dyn[];
@@ -376,6 +418,16 @@ __global__ void __launch_bounds__(256, (PROC == OPTP_PROC_HESTON_FTE || PROC == 
         k.j_mu = (float)(a.v0 * dt);
         k.j_p0 = (float)exp(-a.v0 * dt);
     }
+    if (PROC == OPTP_PROC_SABR) {  // v0 = alpha0, kappa = beta, xi = nu (mc_fp64.cu, processes.py:199-215)
+        k.s_nu2 = (float)(a.xi * sdt * L2E);
+        k.s_vdr2 = (float)(-0.5 * a.xi * a.xi * dt * L2E);
+        k.s_beta = (float)a.kappa;
+        k.s_sdt2 = (float)(sdt * L2E);
+        k.s_mhdt2 = (float)(-0.5 * dt * L2E);
+        k.s_rq2 = (float)((a.r - a.q) * dt * L2E);
+        k.s_rqdt = (float)((a.r - a.q) * dt);
+        k.s_sdt = (float)sdt;
+    }
     k.m_c1 = (float)((a.r - a.q) * dt - 0.5 * a.sigma * a.sigma * dt);
     k.m_ssdt = (float)(a.sigma * sdt);
     k.m_hs2dt = (float)(0.5 * a.sigma * a.sigma * dt);
@@ -383,7 +435,8 @@ __global__ void __launch_bounds__(256, (PROC == OPTP_PROC_HESTON_FTE || PROC == 
     const float inv_n = (float)(1.0 / (double)n_steps);
     const float df = (float)exp(-a.pay[0].r_disc * a.pay[0].T_disc);
     const unsigned long long n_eff = ANTI ? 2 * a.n_base : a.n_base;
-    constexpr int kDims = (PROC == OPTP_PROC_HESTON_FTE || PROC == OPTP_PROC_HESTON_QE) ? 2 : 1;
+    constexpr int kDims =
+        (PROC == OPTP_PROC_HESTON_FTE || PROC == OPTP_PROC_HESTON_QE || PROC == OPTP_PROC_SABR) ? 2 : 1;
     constexpr int kPerCall = 4 / kDims;  // steps served by one Philox call
     const unsigned int n_full = n_steps / kPerCall, n_tail = n_steps % kPerCall;
 
@@ -477,6 +530,44 @@ __global__ void __launch_bounds__(256, (PROC == OPTP_PROC_HESTON_FTE || PROC == 
             }
             ep = finish_log<MASK>(p, S0, inv_n);
             if (ANTI) em = finish_log<MASK>(m, S0, inv_n);
+        } else if (PROC == OPTP_PROC_SABR) {
+            float lp = mufu_lg2((float)a.v0), lm = lp;  // log2 alpha0
+            uint4 w = philox_words(a.seed, gpath, 0u, 0u);
+            if (a.kappa == 1.0) {
+                LogState p, m;
+#pragma unroll 1
+                for (unsigned int c = 0; c < n_full; ++c) {
+                    const uint4 wn = philox_words(a.seed, gpath, c + 1, 0u);
+                    normals_from_words(w, z);
+                    sabr_step_log<MASK, ANTI>(p, m, lp, lm, z[0], z[1], k);
+                    sabr_step_log<MASK, ANTI>(p, m, lp, lm, z[2], z[3], k);
+                    w = wn;
+                }
+                if (n_tail) {
+                    normals_from_words(w, z);
+                    sabr_step_log<MASK, ANTI>(p, m, lp, lm, z[0], z[1], k);
+                }
+                ep = finish_log<MASK>(p, S0, inv_n);
+                if (ANTI) em = finish_log<MASK>(m, S0, inv_n);
+            } else {
+                LinState p, m;
+                p.S = p.smax = p.smin = S0;
+                m = p;
+#pragma unroll 1
+                for (unsigned int c = 0; c < n_full; ++c) {
+                    const uint4 wn = philox_words(a.seed, gpath, c + 1, 0u);
+                    normals_from_words(w, z);
+                    sabr_step_lin<MASK, ANTI>(p, m, lp, lm, z[0], z[1], k);
+                    sabr_step_lin<MASK, ANTI>(p, m, lp, lm, z[2], z[3], k);
+                    w = wn;
+                }
+                if (n_tail) {
+                    normals_from_words(w, z);
+                    sabr_step_lin<MASK, ANTI>(p, m, lp, lm, z[0], z[1], k);
+                }
+                ep = finish_lin<MASK>(p, inv_n);
+                if (ANTI) em = finish_lin<MASK>(m, inv_n);
+            }
         } else {  // OPTP_PROC_GBM_MILSTEIN
             LinState p, m;
             p.S = p.smax = p.smin = S0;
@@ -883,7 +974,7 @@ int launch_table_convert(const double* t64, float2* t32, float4* t4, unsigned in
 // ------------------------------------------------------------------ dispatch
 bool path_fp32_supported(int proc) {
     return proc == OPTP_PROC_GBM || proc == OPTP_PROC_HESTON_FTE || proc == OPTP_PROC_GBM_MILSTEIN ||
-           proc == OPTP_PROC_HESTON_QE || proc == OPTP_PROC_MERTON ||
+           proc == OPTP_PROC_HESTON_QE || proc == OPTP_PROC_MERTON || proc == OPTP_PROC_SABR ||
            proc == OPTP_PROC_LV_MILSTEIN || proc == OPTP_PROC_LV_EULER;
 }
 
@@ -987,6 +1078,7 @@ int launch_path_fp32(const PathArgs& a, cudaStream_t st) {
         case OPTP_PROC_HESTON_FTE: return launch_mask<OPTP_PROC_HESTON_FTE>(a, mask, st);
         case OPTP_PROC_HESTON_QE: return launch_mask<OPTP_PROC_HESTON_QE>(a, mask, st);
         case OPTP_PROC_MERTON: return launch_mask<OPTP_PROC_MERTON>(a, mask, st);
+        case OPTP_PROC_SABR: return launch_mask<OPTP_PROC_SABR>(a, mask, st);
         case OPTP_PROC_GBM_MILSTEIN: return launch_mask<OPTP_PROC_GBM_MILSTEIN>(a, mask, st);
         case OPTP_PROC_LV_MILSTEIN: return launch_mask<OPTP_PROC_LV_MILSTEIN>(a, mask, st);
         case OPTP_PROC_LV_EULER: return launch_mask<OPTP_PROC_LV_EULER>(a, mask, st);

@@ -228,8 +228,9 @@ def heston_paths(S0, r, q, v0, kappa, theta, xi, rho, T, n_steps, n_paths, *, an
 
 
 def sabr_paths(S0, r, q, alpha0, beta, nu, rho, T, n_steps, n_paths, *, antithetic=True, seed=None,
-               rng="philox", mode="fp64"):
-    """SABR with lognormal vol (processes.py:168-217); fp64 kernels only."""
+               rng="philox", mode="fp32"):
+    """SABR with lognormal vol (processes.py:168-217): exact lognormal volatility, log-Euler price step for
+    beta = 1, Euler step with the reference's 1e-12 floor otherwise."""
     _check_sizes(n_steps, n_paths)
     if not (0.0 <= beta <= 1.0):
         raise ValueError("beta must be in [0, 1].")
@@ -238,7 +239,7 @@ def sabr_paths(S0, r, q, alpha0, beta, nu, rho, T, n_steps, n_paths, *, antithet
     if not (-1.0 <= rho <= 1.0):
         raise ValueError("rho must be in [-1, 1].")
     proc = dict(kind=nv.PROC_SABR, S0=S0, r=r, q=q, T=T, v0=alpha0, kappa=beta, xi=nu, rho=rho)
-    return LazyPaths(proc, n_steps, n_paths, antithetic, seed, rng, "fp64")
+    return LazyPaths(proc, n_steps, n_paths, antithetic, seed, rng, mode)
 
 
 def merton_jump_paths(S0, r, q, sigma, T, n_steps, n_paths, *, lam, mJ, sJ, antithetic=True, seed=None,

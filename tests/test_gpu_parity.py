@@ -391,7 +391,6 @@ def _lazy(op, meta, npz, rng, mode="fp64", seed=None, n_mult=1):
     if gen == "gbm_milstein":
         return pr.gbm_milstein_paths(**a, **kw)
     if gen == "sabr":
-        kw["mode"] = "fp64"
         return pr.sabr_paths(**a, **kw)
     if gen == "merton":
         return pr.merton_jump_paths(**a, **kw)
@@ -489,7 +488,7 @@ def test_check_mode_reference_test_fixtures(op, tag):
 
 
 @pytest.mark.parametrize("tag", BIG + ["gbm_small_anti0", "heston_small_anti0", "lvm_table_anti0", "lv_euler_table",
-                                       "gbm_milstein", "merton"])
+                                       "gbm_milstein", "merton", "sabr_beta1.0", "sabr_beta0.5"])
 @pytest.mark.parametrize("mode", ["fp32", "fp64"])
 def test_philox_within_three_reference_se(op, tag, mode):
     from optpricer_b200 import exotics as ex
@@ -511,7 +510,7 @@ def test_philox_within_three_reference_se(op, tag, mode):
                 assert 0.85 < 4.0 * se / ref_se < 1.18, (tag, k, se, ref_se)
 
 
-@pytest.mark.parametrize("gen", ["gbm", "heston", "lvm", "lve", "gbmm", "merton"])
+@pytest.mark.parametrize("gen", ["gbm", "heston", "lvm", "lve", "gbmm", "merton", "sabr1", "sabr05", "sabr0"])
 def test_fp32_tracks_fp64_on_same_philox_draws(op, gen):
     """Production fp32 arithmetic vs the reference operation order in fp64, SAME device normals:
     the price difference must be a small fraction of the standard error."""
@@ -530,6 +529,9 @@ def test_fp32_tracks_fp64_on_same_philox_draws(op, gen):
             return pr.local_vol_paths(100.0, 0.05, 0.02, 1.0, 252, n, table, seed=11, mode=mode)
         if gen == "merton":
             return pr.merton_jump_paths(100.0, 0.05, 0.0, 0.2, 1.0, 100, n, lam=0.8, mJ=-0.1, sJ=0.15, seed=11, mode=mode)
+        if gen.startswith("sabr"):   # alpha0 scaled so that the price volatility is ~20 % at S = 100 for every beta
+            beta = {"sabr1": 1.0, "sabr05": 0.5, "sabr0": 0.0}[gen]
+            return pr.sabr_paths(100.0, 0.05, 0.0, 0.2 * 100.0 ** (1.0 - beta), beta, 0.4, -0.3, 1.0, 200, n, seed=11, mode=mode)
         return pr.gbm_milstein_paths(100.0, 0.05, 0.0, 0.2, 1.0, 252, n, seed=11, mode=mode)
 
     specs = [ex.barrier_spec(100.0, "call", 130.0, "up-and-out"), ex.barrier_spec(100.0, "put", 85.0, "down-and-in"),
