@@ -18,6 +18,7 @@
 // Kernel 2 (any N up to the shared-memory limit): one option per CTA, ping-pong level
 //   arrays in shared memory.
 #include <math.h>
+#include <string.h>
 #include "optp_common.cuh"
 
 namespace optp {
@@ -35,9 +36,12 @@ struct CrrArgs {
     int todo_only;  // 0 = every contract, else only contracts whose status equals this value (2 = declined by
                     // a banded kernel, 3 = American call that is never exercised early)
     // two-zone kernel work lists (compaction of the contracts whose band was too wide for a lane layout):
-    // wl_in = {count, items...} to walk instead of [0, n), or null; wl_out = list the too-wide ones go to
+    // wl_in (wl_in_n items) = the contracts to walk instead of [0, n), or null; wl_out / wl_out_n = the list
+    // the too-wide ones are appended to.  The counters sit together in one header (one memset per batch).
     const unsigned int* wl_in;
+    const unsigned int* wl_in_n;
     unsigned int* wl_out;
+    unsigned int* wl_out_n;
     // {number of contracts left at status 2, at status 3} by the two-zone passes, or null: a full-width
     // filter pass with nothing to do returns at once instead of scanning n status bytes
     unsigned int* decl_count;
@@ -696,12 +700,12 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
     const unsigned long long warp0 = (unsigned long long)blockIdx.x * kZoneWarps + wib;
     const unsigned long long nwarps = (unsigned long long)gridDim.x * kZoneWarps;
     // retry passes walk the compacted list of contracts the previous layout was too narrow for
-    const unsigned int n_work = a.wl_in ? a.wl_in[0] : (unsigned int)a.n;  // (launch_crr: n < 2^32)
+    const unsigned int n_work = a.wl_in ? *a.wl_in_n : (unsigned int)a.n;  // (launch_crr: n < 2^32)
     for (unsigned long long o0 = warp0 * G; o0 < n_work; o0 += nwarps * G) {
         const unsigned long long og = o0 + (unsigned long long)(lane / LG);
         const bool wanted = og < n_work;
         const unsigned long long ow = wanted ? og : (unsigned long long)(n_work - 1);
-        const unsigned long long o = a.wl_in ? (unsigned long long)a.wl_in[1 + ow] : ow;
+        const unsigned long long o = a.wl_in ? (unsigned long long)a.wl_in[ow] : ow;
         // An American call with q > 0 is priced as its DUAL PUT: on a CRR lattice (u*d = 1)
         //     C_k[j](S0, K, r, q) = P_k[k - j](S0' = K, K' = S0, r' = q, q' = r)
         // holds node by node (change of numeraire: p' = 1 - p*u*e^{-(r-q)dt} is the up-probability of
@@ -985,7 +989,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
         if (wanted && L.ok && gl == 0) {
             if (fail) {
                 if (too_wide && G > 1) {
-                    a.wl_out[1 + atomicAdd(a.wl_out, 1u)] = (unsigned int)o;  // status is settled by a later pass
+                    a.wl_out[atomicAdd(a.wl_out_n, 1u)] = (unsigned int)o;  // status is settled by a later pass
                 } else {
                     const unsigned char dc = declined_code();
                     a.status[o] = dc;
@@ -1051,17 +1055,35 @@ __global__ void __launch_bounds__(256) crr_cta_kernel(CrrArgs a) {
     }
 }
 
+// cudaOccupancyMaxActiveBlocksPerMultiprocessor costs microseconds per call and its answer never changes for
+// a (kernel, block size, dynamic shared memory = 0) triple: remember it (calls are serialised by the API lock).
+static int occupancy_cached(const void* fn, int threads, int* per_sm) {
+    static const void* keys[16];
+    static int vals[16];
+    static int n_keys = 0;
+    for (int i = 0; i < n_keys; ++i)
+        if (keys[i] == fn) {
+            *per_sm = vals[i];
+            return 0;
+        }
+    int v = 0;
+    OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, fn, threads, 0));
+    if (v < 1) v = 1;
+    if (n_keys < 16) {
+        keys[n_keys] = fn;
+        vals[n_keys++] = v;
+    }
+    *per_sm = v;
+    return 0;
+}
+
 static int launch_full_warp(const CrrArgs& a, int american, cudaStream_t st) {
     Context& c = ctx();
     const unsigned long long want = (a.n + kWarpsPerCta - 1) / kWarpsPerCta;
     int per_sm = 0;
-    if (american)
-        OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, crr_warp_kernel<true>,
-                                                                kWarpsPerCta * 32, 0));
-    else
-        OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, crr_warp_kernel<false>,
-                                                                kWarpsPerCta * 32, 0));
-    if (per_sm < 1) per_sm = 1;
+    if (int e = occupancy_cached(american ? (const void*)crr_warp_kernel<true> : (const void*)crr_warp_kernel<false>,
+                                 kWarpsPerCta * 32, &per_sm))
+        return e;
     // persistent warps: exactly one resident wave, options strided over warps
     const unsigned long long cap = (unsigned long long)c.n_sm * per_sm;
     const unsigned int grid = (unsigned int)(want < cap ? want : cap);
@@ -1109,10 +1131,10 @@ static int launch_full(const CrrArgs& a_in, int american, cudaStream_t st, int s
 
 // Work lists of the two-zone kernel: per slot two lists of {count, n items}.
 static size_t crr_worklist_bytes(unsigned long long n) {
-    return ((size_t)(n + 1) * sizeof(unsigned int) + 255) & ~(size_t)255;
+    return ((size_t)n * sizeof(unsigned int) + 255) & ~(size_t)255;
 }
 static int crr_reserve_worklists(unsigned long long n) {
-    return arena_reserve(ctx().work, 2 * (2 * crr_worklist_bytes(n) + 256) + 512);  // two slots of {list, list, counters}
+    return arena_reserve(ctx().work, 2 * (256 + 2 * crr_worklist_bytes(n)) + 512);  // two slots of {header, list, list}
 }
 
 // `slot` (0 or 1) selects the work-list scratch: launches that may be in flight together (the two
@@ -1121,8 +1143,8 @@ static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st, int sl
     Context& c = ctx();
     CrrArgs a = a_in;
     a.todo_only = 0;
-    a.wl_in = nullptr;
-    a.wl_out = nullptr;
+    a.wl_in = a.wl_in_n = nullptr;
+    a.wl_out = a.wl_out_n = nullptr;
     a.decl_count = nullptr;
     a.cta_scratch = nullptr;
     if (a.n == 0) return 0;
@@ -1140,25 +1162,28 @@ static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st, int sl
             }
         }
         unsigned int* wl[2] = {nullptr, nullptr};
+        unsigned int* hdr = nullptr;
         if (G >= 1) {
             if (int e = crr_reserve_worklists(a.n)) return e;
             const size_t list_bytes = crr_worklist_bytes(a.n);
             char* base = (char*)c.work.p + (size_t)slot * ((c.work.cap / 2) & ~(size_t)255);
-            wl[0] = (unsigned int*)base;
-            wl[1] = (unsigned int*)(base + list_bytes);
-            a.decl_count = (unsigned int*)(base + 2 * list_bytes);
-            OPTP_CUDA(cudaMemsetAsync(wl[0], 0, sizeof(unsigned int), st));
-            OPTP_CUDA(cudaMemsetAsync(wl[1], 0, sizeof(unsigned int), st));
-            OPTP_CUDA(cudaMemsetAsync(a.decl_count, 0, 2 * sizeof(unsigned int), st));
-            if (G >= 2) a.wl_out = wl[0];
+            // header {list 0 count, list 1 count, contracts left at status 2, at status 3}, then the two lists
+            hdr = (unsigned int*)base;
+            wl[0] = (unsigned int*)(base + 256);
+            wl[1] = (unsigned int*)(base + 256 + list_bytes);
+            a.decl_count = hdr + 2;
+            OPTP_CUDA(cudaMemsetAsync(hdr, 0, 4 * sizeof(unsigned int), st));
+            if (G >= 2) {
+                a.wl_out = wl[0];
+                a.wl_out_n = hdr;
+            }
         }
         const void* fn = (G == 4)   ? (const void*)crr_zone_kernel<4>
                          : (G == 2) ? (const void*)crr_zone_kernel<2>
                          : (G == 1) ? (const void*)crr_zone_kernel<1>
                                     : (const void*)crr_band_kernel;
         static_assert(kBandWarps == kZoneWarps, "one grid computation for both banded kernels");
-        OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kZoneWarps * 32, 0));
-        if (per_sm < 1) per_sm = 1;
+        if (int e = occupancy_cached(fn, kZoneWarps * 32, &per_sm)) return e;
         const unsigned long long per_warp = (G > 0) ? (unsigned long long)G : 1ull;
         const unsigned long long want = (a.n + kBandWarps * per_warp - 1) / (kBandWarps * per_warp);
         const unsigned long long cap = (unsigned long long)c.n_sm * per_sm;
@@ -1175,13 +1200,14 @@ static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st, int sl
         OPTP_CUDA(cudaGetLastError());
         // contracts whose band was too wide for G options per warp were appended to wl[0]: walk that
         // list two per warp, then what is too wide even so (wl[1]) one per warp
-        const unsigned int* wl_in = a.wl_out;
-        for (int g2 = G / 2; g2 >= 1; g2 /= 2) {
-            a.wl_in = wl_in;
+        int list = 0;
+        for (int g2 = G / 2; g2 >= 1; g2 /= 2, ++list) {
+            a.wl_in = wl[list];
+            a.wl_in_n = hdr + list;
             a.wl_out = (g2 == 2) ? wl[1] : nullptr;
+            a.wl_out_n = (g2 == 2) ? hdr + 1 : nullptr;
             const void* fn2 = (g2 == 2) ? (const void*)crr_zone_kernel<2> : (const void*)crr_zone_kernel<1>;
-            OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn2, kZoneWarps * 32, 0));
-            if (per_sm < 1) per_sm = 1;
+            if (int e = occupancy_cached(fn2, kZoneWarps * 32, &per_sm)) return e;
             const unsigned long long want2 = (a.n + kZoneWarps * g2 - 1) / (kZoneWarps * g2);
             const unsigned long long cap2 = (unsigned long long)c.n_sm * per_sm;
             const unsigned int grid2 = (unsigned int)(want2 < cap2 ? want2 : cap2);
@@ -1191,10 +1217,9 @@ static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st, int sl
                 crr_zone_kernel<1><<<grid2, kZoneWarps * 32, 0, st>>>(a);
             c.launches++;
             OPTP_CUDA(cudaGetLastError());
-            wl_in = a.wl_out;
         }
-        a.wl_in = nullptr;
-        a.wl_out = nullptr;
+        a.wl_in = a.wl_in_n = nullptr;
+        a.wl_out = a.wl_out_n = nullptr;
         a.todo_only = 0;
         if (c.crr_band_only) return 0;  // diagnostics: leave the declined contracts unpriced
         if (G > 0) {  // two-zone kernel: never-exercised calls were marked 3 -> European recursion
@@ -1241,6 +1266,27 @@ extern "C" int optp_crr_batch(const double* S0, const double* K, const double* T
     char* in = (char*)c.in0.p;
     char* out = (char*)c.out0.p;
     const double* src[6] = {S0, K, T, r, q, sigma};
+    // Small batches (a scalar crr() is a batch of one): the seven columns are packed into pinned memory and
+    // travel in ONE copy each way -- the call is latency-bound, and a copy costs ~5 us whatever its size.
+    if (n <= 8192) {
+        if (int e = host_arena_reserve(c.pin_in, 6 * colp + n)) return e;
+        if (int e = host_arena_reserve(c.pin_out, colp + n)) return e;
+        char* hin = (char*)c.pin_in.p;
+        char* hout = (char*)c.pin_out.p;
+        for (int i = 0; i < 6; ++i) memcpy(hin + i * colp, src[i], col);
+        memcpy(hin + 6 * colp, is_call, n);
+        OPTP_CUDA(cudaMemcpyAsync(in, hin, 6 * colp + n, cudaMemcpyHostToDevice, c.stream));
+        CrrArgs a{(const double*)(in), (const double*)(in + colp), (const double*)(in + 2 * colp),
+                  (const double*)(in + 3 * colp), (const double*)(in + 4 * colp), (const double*)(in + 5 * colp),
+                  (const uint8_t*)(in + 6 * colp), (unsigned long long)n, (int)N, (double*)out,
+                  (uint8_t*)(out + colp), 0};
+        if (int e = launch_crr(a, american, c.stream, 0)) return e;
+        OPTP_CUDA(cudaMemcpyAsync(hout, out, colp + n, cudaMemcpyDeviceToHost, c.stream));
+        OPTP_CUDA(cudaStreamSynchronize(c.stream));
+        memcpy(price_out, hout, col);
+        memcpy(status_out, hout + colp, n);
+        return 0;
+    }
     // Large batches are walked in slices on two streams, so the host->device copy of slice i+1 and
     // the device->host copy of slice i-1 overlap the kernel of slice i.  A contract's price does not
     // depend on the slice it is in (every kernel prices a contract from its own columns only).

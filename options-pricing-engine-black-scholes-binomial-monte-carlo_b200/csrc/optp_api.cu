@@ -45,6 +45,20 @@ int arena_reserve(Arena& a, size_t bytes) {
     return 0;
 }
 
+int host_arena_reserve(Arena& a, size_t bytes) {
+    if (bytes <= a.cap) return 0;
+    if (a.p) {
+        OPTP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+        OPTP_CUDA(cudaFreeHost(a.p));
+        a.p = nullptr;
+        a.cap = 0;
+    }
+    size_t want = 2 * bytes + 4096;
+    OPTP_CUDA(cudaHostAlloc(&a.p, want, cudaHostAllocDefault));
+    a.cap = want;
+    return 0;
+}
+
 int require_ready() {
     if (!g_ctx.ready) return set_error(OPTP_E_NOINIT, "optp_init() has not been called");
     return 0;
@@ -104,6 +118,10 @@ static void release_resources(Context& c) {
     arena_free(c.table_f64);
     arena_free(c.work);
     arena_free(c.cta_scratch);
+    if (c.pin_in.p) cudaFreeHost(c.pin_in.p);
+    if (c.pin_out.p) cudaFreeHost(c.pin_out.p);
+    c.pin_in = Arena();
+    c.pin_out = Arena();
     if (c.partials) cudaFree(c.partials);
     if (c.ticket) cudaFree(c.ticket);
     if (c.stats_dev) cudaFree(c.stats_dev);

@@ -28,6 +28,7 @@ struct Context {
     Arena in0, in1, out0, out1, table_f32, table_f64, table_f4;
     Arena work;  // work lists of the two-zone CRR kernel (crr_batch.cu)
     Arena cta_scratch;  // level arrays of the one-option-per-CTA CRR kernel when N > 9685
+    Arena pin_in, pin_out;  // PINNED host staging of small CRR batches (one copy in, one copy out)
     uint32_t table_steps = 0, table_nodes = 0;
     uint64_t launches = 0;
     bool lv_direct = false;      // "lv_direct" = 1: window nodes gathered from global/L1, no smem staging
@@ -46,6 +47,7 @@ Context& ctx();
 int set_error(int code, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 int arena_reserve(Arena& a, size_t bytes);
+int host_arena_reserve(Arena& a, size_t bytes);  // pinned host memory (cudaHostAlloc), grow-only
 int require_ready();
 
 // The library keeps ONE context (stream, reduction scratch, staging arenas): every C-ABI entry point
