@@ -201,7 +201,7 @@ __device__ __forceinline__ void stage(double (&v)[32], const UTab& U, const Latt
 }
 
 template <bool AMER>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 3)
 crr_warp_kernel(CrrArgs a) {
     __shared__ double tiles[kWarpsPerCta][kTileDoubles];
     const int lane = threadIdx.x & 31;
@@ -1287,56 +1287,70 @@ extern "C" int optp_crr_batch(const double* S0, const double* K, const double* T
         memcpy(status_out, hout + colp, n);
         return 0;
     }
-    // Large batches are walked in slices on two streams, so the host->device copy of slice i+1 and
-    // the device->host copy of slice i-1 overlap the kernel of slice i.  A contract's price does not
-    // depend on the slice it is in (every kernel prices a contract from its own columns only).
+    // Large batches are walked in slices of 128k contracts through FOUR streams chained by events: host->device
+    // copies on one, the kernels of even / odd slices on two (so the tail of one slice's persistent grid
+    // overlaps the head of the next), device->host copies (into pinned staging) on the fourth.  The copies
+    // of slices i+1 and i-1 overlap the kernels of slice i, and the host never blocks on a pageable copy: it
+    // moves a slice's results from the staging buffer to the caller's arrays as soon as that slice's event
+    // has fired.  A contract's price does not depend on the slice it is in.
     const uint64_t slice = 1ull << 17;
-    const bool pipelined = n >= 4 * slice;
-    if (pipelined && !c.stream2)
-        OPTP_CUDA(cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking));
-    const uint64_t step = pipelined ? slice : n;
-    // scratch of both pipeline slots is reserved before anything is in flight (an arena never grows
-    // under a running kernel)
+    const uint64_t step = (n >= 4 * slice) ? slice : n;
+    constexpr uint64_t kGroupSlices = kMaxEvents / 3;  // slices in flight per group (bounds staging and events)
+    if (!c.stream2) OPTP_CUDA(cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking));
+    if (!c.stream3) OPTP_CUDA(cudaStreamCreateWithFlags(&c.stream3, cudaStreamNonBlocking));
+    if (!c.stream4) OPTP_CUDA(cudaStreamCreateWithFlags(&c.stream4, cudaStreamNonBlocking));
+    while (c.n_events < kMaxEvents) {
+        OPTP_CUDA(cudaEventCreateWithFlags(&c.events[c.n_events], cudaEventDisableTiming));
+        c.n_events++;
+    }
+    // scratch is reserved before anything is in flight (an arena never grows under a running kernel)
     if (american)
         if (int e = crr_reserve_worklists(step)) return e;
-    // The device->host copy of a slice is issued AFTER the next slice has been queued: a copy into
-    // pageable host memory blocks the calling thread until it is done.
-    auto copy_back = [&](uint64_t lo, uint64_t m, cudaStream_t st) -> int {
-        OPTP_CUDA(cudaMemcpyAsync(price_out + lo, (double*)out + lo, m * sizeof(double), cudaMemcpyDeviceToHost, st));
-        OPTP_CUDA(cudaMemcpyAsync(status_out + lo, out + colp + lo, m, cudaMemcpyDeviceToHost, st));
-        return 0;
-    };
-    int which = 0;
-    uint64_t prev_lo = 0, prev_m = 0;
-    cudaStream_t prev_st = nullptr;
-    for (uint64_t lo = 0; lo < n; lo += step, which ^= 1) {
-        const uint64_t m = (n - lo < step) ? (n - lo) : step;
-        cudaStream_t st = (pipelined && which) ? c.stream2 : c.stream;
-        for (int i = 0; i < 6; ++i)
-            OPTP_CUDA(cudaMemcpyAsync(in + i * colp + lo * sizeof(double), src[i] + lo, m * sizeof(double),
-                                      cudaMemcpyHostToDevice, st));
-        OPTP_CUDA(cudaMemcpyAsync(in + 6 * colp + lo, is_call + lo, m, cudaMemcpyHostToDevice, st));
-        CrrArgs a{(const double*)(in) + lo,
-                  (const double*)(in + colp) + lo,
-                  (const double*)(in + 2 * colp) + lo,
-                  (const double*)(in + 3 * colp) + lo,
-                  (const double*)(in + 4 * colp) + lo,
-                  (const double*)(in + 5 * colp) + lo,
-                  (const uint8_t*)(in + 6 * colp) + lo,
-                  (unsigned long long)m,
-                  (int)N,
-                  (double*)out + lo,
-                  (uint8_t*)(out + colp) + lo,
-                  0};
-        if (int e = launch_crr(a, american, st, (pipelined && which) ? 1 : 0)) return e;
-        if (prev_m)
-            if (int e = copy_back(prev_lo, prev_m, prev_st)) return e;
-        prev_lo = lo;
-        prev_m = m;
-        prev_st = st;
+    const uint64_t group = step * kGroupSlices;
+    const size_t gcol = (((size_t)(n < group ? n : group) * sizeof(double)) + 255) & ~(size_t)255;
+    if (int e = host_arena_reserve(c.pin_out, gcol + (size_t)(n < group ? n : group))) return e;
+    char* hout = (char*)c.pin_out.p;
+    for (uint64_t g0 = 0; g0 < n; g0 += group) {
+        const uint64_t g1 = (n - g0 < group) ? n : g0 + group;
+        int s_idx = 0;
+        for (uint64_t lo = g0; lo < g1; lo += step, ++s_idx) {
+            const uint64_t m = (g1 - lo < step) ? (g1 - lo) : step;
+            cudaEvent_t ev_in = c.events[3 * s_idx], ev_k = c.events[3 * s_idx + 1], ev_out = c.events[3 * s_idx + 2];
+            for (int i = 0; i < 6; ++i)
+                OPTP_CUDA(cudaMemcpyAsync(in + i * colp + lo * sizeof(double), src[i] + lo, m * sizeof(double),
+                                          cudaMemcpyHostToDevice, c.stream2));
+            OPTP_CUDA(cudaMemcpyAsync(in + 6 * colp + lo, is_call + lo, m, cudaMemcpyHostToDevice, c.stream2));
+            OPTP_CUDA(cudaEventRecord(ev_in, c.stream2));
+            cudaStream_t sc = (s_idx & 1) ? c.stream4 : c.stream;
+            OPTP_CUDA(cudaStreamWaitEvent(sc, ev_in, 0));
+            CrrArgs a{(const double*)(in) + lo,
+                      (const double*)(in + colp) + lo,
+                      (const double*)(in + 2 * colp) + lo,
+                      (const double*)(in + 3 * colp) + lo,
+                      (const double*)(in + 4 * colp) + lo,
+                      (const double*)(in + 5 * colp) + lo,
+                      (const uint8_t*)(in + 6 * colp) + lo,
+                      (unsigned long long)m,
+                      (int)N,
+                      (double*)out + lo,
+                      (uint8_t*)(out + colp) + lo,
+                      0};
+            if (int e = launch_crr(a, american, sc, s_idx & 1)) return e;
+            OPTP_CUDA(cudaEventRecord(ev_k, sc));
+            OPTP_CUDA(cudaStreamWaitEvent(c.stream3, ev_k, 0));
+            OPTP_CUDA(cudaMemcpyAsync(hout + (lo - g0) * sizeof(double), (double*)out + lo, m * sizeof(double),
+                                      cudaMemcpyDeviceToHost, c.stream3));
+            OPTP_CUDA(cudaMemcpyAsync(hout + gcol + (lo - g0), out + colp + lo, m, cudaMemcpyDeviceToHost, c.stream3));
+            OPTP_CUDA(cudaEventRecord(ev_out, c.stream3));
+        }
+        s_idx = 0;
+        for (uint64_t lo = g0; lo < g1; lo += step, ++s_idx) {
+            const uint64_t m = (g1 - lo < step) ? (g1 - lo) : step;
+            OPTP_CUDA(cudaEventSynchronize(c.events[3 * s_idx + 2]));
+            memcpy(price_out + lo, hout + (lo - g0) * sizeof(double), m * sizeof(double));
+            memcpy(status_out + lo, hout + gcol + (lo - g0), m);
+        }
     }
-    if (int e = copy_back(prev_lo, prev_m, prev_st)) return e;
     OPTP_CUDA(cudaStreamSynchronize(c.stream));
-    if (pipelined) OPTP_CUDA(cudaStreamSynchronize(c.stream2));
     return 0;
 }

@@ -128,6 +128,9 @@ static void release_resources(Context& c) {
     if (c.stats_host) cudaFreeHost(c.stats_host);
     if (c.stream) cudaStreamDestroy(c.stream);
     if (c.stream2) cudaStreamDestroy(c.stream2);
+    if (c.stream3) cudaStreamDestroy(c.stream3);
+    if (c.stream4) cudaStreamDestroy(c.stream4);
+    for (int i = 0; i < c.n_events; ++i) cudaEventDestroy(c.events[i]);
     cudaGetLastError();
     c = Context();
 }
@@ -163,6 +166,8 @@ int optp_shutdown(void) {
     cudaSetDevice(c.device);
     cudaStreamSynchronize(c.stream);
     if (c.stream2) cudaStreamSynchronize(c.stream2);
+    if (c.stream3) cudaStreamSynchronize(c.stream3);
+    if (c.stream4) cudaStreamSynchronize(c.stream4);
     release_resources(c);
     return 0;
 }

@@ -20,7 +20,11 @@ struct Context {
     bool ready = false;
     int n_sm = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr;  // second stream of the sliced CRR batch pipeline (created on demand)
+    cudaStream_t stream2 = nullptr;  // host->device copies of the sliced CRR batch pipeline (created on demand)
+    cudaStream_t stream3 = nullptr;  // its device->host copies
+    cudaStream_t stream4 = nullptr;  // the kernels of its odd slices (even slices: `stream`)
+    cudaEvent_t events[384] = {};    // its per-slice events (copy-in done, kernels done, copy-out done)
+    int n_events = 0;
     double* partials = nullptr;   // [kMaxBlocks][kMaxVals]
     unsigned int* ticket = nullptr;
     double* stats_dev = nullptr;  // kMaxPayoffs * OPTP_NSTATS
@@ -39,6 +43,7 @@ struct Context {
     int crr_zone_group = 0;    // two-zone kernel: options per warp (1, 2, 4); 0 = by batch size
 };
 
+constexpr int kMaxEvents = 384;
 constexpr int kMaxPayoffs = 16;
 constexpr int kMaxBlocks = 148 * 16;
 constexpr int kMaxVals = 3 * kMaxPayoffs + 4;
