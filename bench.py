@@ -614,7 +614,7 @@ def main():
             "roofline": {"bound": "fp32_pipe", "achieved": mc_kernel_rate * OPS_PER_PATH_STEP["gbm_barrier"] / 1e12,
                          "peak": p32 / 1e12, "unit": "T lane-ops/s",
                          "frac": mc_kernel_rate * OPS_PER_PATH_STEP["gbm_barrier"] / p32,
-                         "traffic": 106496,  # ncu --set full of THIS launch (profiles/r1_ncu_full_bench_gbm.md): dram read 106 KB, write 0
+                         "traffic": 105984,  # ncu --set full of THIS launch (profiles/r1_ncu_full_bench_gbm.md): dram read 106 KB, write 0
                          # the same figure against the nominal issue rate: 148 SMs x 128 FP32 lanes x the SM clock
                          # sampled during the timed region (the measured FFMA rate above is ~91 % of it)
                          "peak_nominal": 148 * 128 * (clocks or {}).get("sm_mhz", 1965.0) * 1e6 / 1e12
@@ -637,8 +637,8 @@ def main():
                              "peak": peaks["smem_lds64_bytes"] / 1e9, "unit": "GB/s",
                              "frac": crr_rate_gpu * CRR_SMEM_BYTES_PER_OPTION / peaks["smem_lds64_bytes"],
                              # ncu --set full of this launch at 1M contracts (profiles/r1_ncu_full_bench_zone.md):
-                             # dram read 49.60 MB + write 0.46 MB (the 57 MB of contract columns and results)
-                             "traffic": 50_058_752 if n_c == 1_000_000 else None,
+                             # dram read 49.47 MB + write 0.48 MB (the 57 MB of contract columns and results)
+                             "traffic": 49_949_440 if n_c == 1_000_000 else None,
                              "ncu_pipe_pct": {"fp64": 48.9, "issue_slots": 58.3, "smem_wavefronts": 29.9,
                                               "source": "profiles/r1_ncu_full_bench_zone.md"},
                              "bytes_per_option": CRR_SMEM_BYTES_PER_OPTION,
