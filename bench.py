@@ -621,6 +621,8 @@ def main():
                          if (clocks or {}).get("sm_mhz") else 148 * 128 * 1965.0e6 / 1e12,
                          "frac_nominal": mc_kernel_rate * OPS_PER_PATH_STEP["gbm_barrier"]
                          / (148 * 128 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6),
+                         # secondary bound: one MUFU per effective path-step against the measured MUFU.EX2 rate
+                         "mufu_frac": mc_kernel_rate * 1.0 / peaks["mufu_ex2_ops"],
                          "ops_per_path_step": OPS_PER_PATH_STEP["gbm_barrier"], "kernel_ms": mc_kernel_ms,
                          "path_steps_per_s_per_gpu": mc_kernel_rate,
                          "peak_source": "optp_microbench FFMA issue rate measured in this run (MEASURED_PEAKS.json "
