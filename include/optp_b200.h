@@ -216,7 +216,8 @@ int optp_mc_book(const optp_book_item* items, uint64_t n_items, const optp_payof
  * Replaces crr (binomial.py:7-38) looped over a heterogeneous contract batch, and
  * crr_vec (binomial.py:44-109) when S0,T,r,q,sigma are constant across the batch.
  *   status_out[i] = 1 and price_out[i] = NaN when the risk-neutral p is outside (0,1)
- *   (binomial.py:16-17); N <= 0 is an argument error (binomial.py:9-10). */
+ *   (binomial.py:16-17) or the spot / strike is not finite (the reference returns NaN there);
+ *   N <= 0 is an argument error (binomial.py:9-10).  A bad contract never affects the others. */
 int optp_crr_batch(const double* S0, const double* K, const double* T, const double* r,
                    const double* q, const double* sigma, const uint8_t* is_call,
                    uint64_t n, uint32_t N, int american, double* price_out,

@@ -66,7 +66,9 @@ __device__ __forceinline__ Lattice make_lattice_of(double S0, double K, double T
     const double d = 1.0 / L.u;
     const double disc = exp(-r * dt);
     const double p = (exp((r - q) * dt) - d) / (L.u - d);
-    L.ok = (p > 0.0) && (p < 1.0);
+    // (a non-finite spot or strike also counts as a bad contract: it would otherwise come out as 0 from the
+    // max(., 0) selects, where the reference's np.maximum propagates the NaN)
+    L.ok = (p > 0.0) && (p < 1.0) && isfinite(S0) && isfinite(K);
     L.pu = disc * p;
     L.pd = disc * (1.0 - p);
     L.S0 = S0;
@@ -723,11 +725,8 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             const double d = 1.0 / L.u;
             const double p = (exp((r_in - q_in) * dt) - d) / (L.u - d);
             L.ok = L.ok && (p > 0.0) && (p < 1.0);
-            if (!((p > 0.0) && (p < 1.0)) && wanted && gl == 0) {
-                a.price[o] = nan("");
-                a.status[o] = 1;
-            }
-        } else if (wanted && !L.ok && gl == 0) {
+        }
+        if (wanted && !L.ok && gl == 0) {
             a.price[o] = nan("");
             a.status[o] = 1;
         }

@@ -196,6 +196,29 @@ def test_crr_ragged_sizes_against_oracle(op, N):
         assert np.all(np.isnan(got[~ok]))
 
 
+def test_crr_bad_contracts_do_not_disturb_their_warp_mates(op):
+    """Four options share a warp in the two-zone kernel: a NaN / non-positive / p-out-of-range contract in
+    the middle of a batch gets NaN + status 1 and every other contract keeps, bit for bit, the price it has
+    in a clean batch."""
+    g = np.random.default_rng(8)
+    n = 40_000                                     # large enough for four options per warp
+    S0 = g.uniform(50, 150, n); K = S0 * g.uniform(0.8, 1.2, n); T = g.uniform(0.1, 2.0, n)
+    sig = g.uniform(0.1, 0.6, n); r = np.full(n, 0.03); q = g.choice([0.0, 0.01, 0.05], n)
+    is_call = (g.random(n) < 0.3).astype(np.uint8)
+    clean = op.crr_batch(S0, K, T, r, q, sig, is_call, 400, american=True)
+    bad = np.arange(n) % 7 == 3
+    S0b, sigb, Tb, rb = S0.copy(), sig.copy(), T.copy(), r.copy()
+    kinds = np.arange(n) % 4
+    S0b[bad & (kinds == 0)] = np.nan
+    sigb[bad & (kinds == 1)] = 1e-6                # p outside (0, 1)
+    Tb[bad & (kinds == 2)] = np.inf
+    rb[bad & (kinds == 3)] = 40.0                  # p outside (0, 1)
+    got, st = op.crr_batch(S0b, K, Tb, rb, q, sigb, is_call, 400, american=True, return_status=True)
+    assert np.all(st[bad] == 1) and np.all(np.isnan(got[bad]))
+    assert np.all(st[~bad] == 0)
+    np.testing.assert_array_equal(got[~bad], clean[~bad])
+
+
 def test_crr_never_exercised_contracts_take_the_european_recursion(op):
     """American calls with q <= 0 < r and American puts with r <= 0 <= q are never exercised early
     (binomial.py:30-36 always keeps the continuation value): they are routed to the European kernel and
