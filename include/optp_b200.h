@@ -91,7 +91,8 @@ typedef struct optp_payoff {
 
 /* statistics block written by the Monte Carlo entry points:
  *   [0] n (effective paths)  [1] sum X  [2] sum X^2  [3] sum Y  [4] sum Y^2  [5] sum XY
- *   [6] number of table lookups clamped to the grid edge (LV_* only)  [7] reserved
+ *   [6] number of effective paths with a table lookup outside the tabulated range, i.e. clamped to
+ *       the grid edge (LV_* only; fp64 kernels count the lookups themselves)  [7] reserved
  * X = exp(-r_disc*T_disc)*payoff, Y = exp(-r_disc*T_disc)*S_T  (monte_carlo.py:54-64). */
 #define OPTP_NSTATS 8
 

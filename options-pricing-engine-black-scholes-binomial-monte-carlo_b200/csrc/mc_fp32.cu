@@ -209,6 +209,9 @@ __device__ __forceinline__ PathEnd finish_log(const LogState& s, float S0, float
 
 struct LinState {  // one effective path in linear space (Milstein schemes)
     float S, smax, smin, sum = 0.f, slog = 0.f;
+    // local-vol kernels: extrema of the table position of this path's lookups (two FMNMX per step instead
+    // of a compare + predicated add; the path counts as clamped if it ever left [0, pos_max])
+    float pmin = 0.f, pmax = 0.f;
 };
 
 template <int MASK>
@@ -601,7 +604,7 @@ __global__ void __launch_bounds__(256, (PROC == OPTP_PROC_HESTON_FTE || PROC == 
 // Lookup: pos = (log2 S - x0_2)/h_2 clamped to [0, n-1]; the cell index comes from the
 // round-to-nearest "magic number" add (no F2I on the XU pipe), then one LDS.64 and one FFMA.
 struct LvConst {
-    float inv_h2, c0, pos_max, c_up, c_dn, k_up, k_dn, c1, sdt, hdt;
+    float inv_h2, c0, pos_max, c_up, c_dn, k_up, k_dn, c1, sdt, hdt, bm_dt;
     float e_sdt2, e_mhalf2, e_rq2;  // log-Euler variant
 };
 
@@ -616,9 +619,10 @@ __device__ __forceinline__ float table_sigma32(const float2* row, float pos, flo
 
 template <int PROC, int MASK>
 __device__ __forceinline__ void lv_step(LinState& s, const float2* row, const LvConst& k, float zs,
-                                        float zzh, float z, unsigned int& clamps) {
+                                        float zzh) {
     const float pos = fmaf(mufu_lg2(s.S), k.inv_h2, k.c0);
-    clamps += (pos < 0.f || pos > k.pos_max) ? 1u : 0u;
+    s.pmin = fminf(s.pmin, pos);
+    s.pmax = fmaxf(s.pmax, pos);
     float sig = table_sigma32(row, pos, k.pos_max);
     if (PROC == OPTP_PROC_LV_MILSTEIN) {
         // processes.py:361-379.  s_up = S(1+b), s_dn = S(1-b): the bumped lookups are constant
@@ -631,7 +635,7 @@ __device__ __forceinline__ void lv_step(LinState& s, const float2* row, const Lv
         s.S = fmaxf(fmaf(av, fmaf(da, zzh, zs), fmaf(s.S, k.c1, s.S)), 1e-10f);
     } else {  // LV_EULER, processes.py:253-256
         sig = fmaxf(sig, 0.f);
-        const float ex = fmaf(sig * z, k.e_sdt2, fmaf(sig * sig, k.e_mhalf2, k.e_rq2));
+        const float ex = fmaf(sig * zs, 1.4426950408889634f, fmaf(sig * sig, k.e_mhalf2, k.e_rq2));  // zs = sqrt(dt) Z
         s.S = s.S * mufu_ex2(ex);
     }
     observe_lin<MASK>(s);
@@ -644,13 +648,13 @@ __device__ __forceinline__ void lv_step(LinState& s, const float2* row, const Lv
 // clamped to [-1, n]; that reproduces the per-lookup clamping of the (value, slope) path exactly.
 template <int MASK, bool LDG = false>
 __device__ __forceinline__ void lvm_step_win(LinState& s, const float4* row, const LvConst& k, float zs,
-                                             float zzh, unsigned int& clamps) {
+                                             float zzh) {
     // Issue-cost model of sm_100a (profiles/r1_pipe_model.md): FFMA/FADD/FMNMX cost one issue
     // cycle, FSETP/IADD/LOP3/LEA two.  The piecewise-linear evaluations are therefore written with
     // min/max instead of compare + select, and the clamp counter costs one compare.
     const float pos = fmaf(mufu_lg2(s.S), k.inv_h2, k.c0);
-    const float pc0 = fminf(fmaxf(pos, 0.0f), k.pos_max);
-    clamps += (pc0 != pos) ? 1u : 0u;                      // lookups outside the tabulated range
+    s.pmin = fminf(s.pmin, pos);                          // lookups outside the tabulated range are counted
+    s.pmax = fmaxf(s.pmax, pos);                          // per path, from these extrema
     const float pc = fminf(fmaxf(pos, -1.0f), k.pos_max + 1.0f);
     const float t = __fadd_rd(pc, 12582912.0f);           // floor(pc) + 1.5*2^23, one FADD.RM
     const int j = __float_as_int(t) - 0x4B400000;         // floor(pc) in [-1, n]
@@ -733,6 +737,7 @@ __global__ void __launch_bounds__(kLvThreads, 4) lv_fp32_kernel(PathArgs a, int 
     k.c1 = (float)((a.r - a.q) * dt);  // S*(1+c1) is evaluated as fma(S, c1, S)
     k.sdt = (float)sdt;
     k.hdt = (float)(0.5 * dt);
+    k.bm_dt = (float)(-1.3862943611198906 * dt);
     k.e_sdt2 = (float)(sdt * L2E);
     k.e_mhalf2 = (float)(-0.5 * dt * L2E);
     k.e_rq2 = (float)((a.r - a.q) * dt * L2E);
@@ -786,7 +791,7 @@ __global__ void __launch_bounds__(kLvThreads, 4) lv_fp32_kernel(PathArgs a, int 
         LinState p, m;
         p.S = p.smax = p.smin = S0;
         m = p;
-        unsigned int clamps = 0;
+        p.pmin = p.pmax = m.pmin = m.pmax = 0.5f * k.pos_max;
         // the Philox words of the next 4-step block are always requested one block ahead, across
         // chunk boundaries too (chunks are multiples of 4 rows)
         uint4 w = philox_words(a.seed, gpath, 0u, 0u);
@@ -808,20 +813,20 @@ __global__ void __launch_bounds__(kLvThreads, 4) lv_fp32_kernel(PathArgs a, int 
                 for (unsigned int r = 0; r < nr; r += 4) {
                     float z[4];
                     const uint4 wn = philox_words(a.seed, gpath, ((t0 + r) >> 2) + 1, 0u);
-                    normals_from_words(w, z);
+                    normals_from_words_scaled(w, k.bm_dt, z);  // z = sqrt(dt) Z (the scale rides in the radius)
                     w = wn;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         if (r + j < nr) {
                             const Node* row = buf + (size_t)(r + j) * n_ld;
-                            const float zs = k.sdt * z[j];
-                            const float zzh = k.hdt * fmaf(z[j], z[j], -1.0f);
+                            const float zs = z[j];
+                            const float zzh = fmaf(0.5f * zs, zs, -k.hdt);  // (Z^2 - 1) dt / 2
                             if constexpr (WIN) {
-                                lvm_step_win<MASK>(p, row, k, zs, zzh, clamps);
-                                if (ANTI) lvm_step_win<MASK>(m, row, k, -zs, zzh, clamps);
+                                lvm_step_win<MASK>(p, row, k, zs, zzh);
+                                if (ANTI) lvm_step_win<MASK>(m, row, k, -zs, zzh);
                             } else {
-                                lv_step<PROC, MASK>(p, row, k, zs, zzh, z[j], clamps);
-                                if (ANTI) lv_step<PROC, MASK>(m, row, k, -zs, zzh, -z[j], clamps);
+                                lv_step<PROC, MASK>(p, row, k, zs, zzh);
+                                if (ANTI) lv_step<PROC, MASK>(m, row, k, -zs, zzh);
                             }
                         }
                     }
@@ -833,7 +838,9 @@ __global__ void __launch_bounds__(kLvThreads, 4) lv_fp32_kernel(PathArgs a, int 
             }
         }
         if (active) {
-            acc_add(acc, 2, (double)clamps);
+            const int left_p = (p.pmin < 0.f || p.pmax > k.pos_max) ? 1 : 0;
+            const int left_m = (ANTI && (m.pmin < 0.f || m.pmax > k.pos_max)) ? 1 : 0;
+            acc_add(acc, 2, (double)(left_p + left_m));
             path_epilogue(a, finish_lin<MASK>(p, inv_n), df, b, n_eff, acc);
             if (ANTI) path_epilogue(a, finish_lin<MASK>(m, inv_n), df, a.n_base + b, n_eff, acc);
         }
@@ -865,6 +872,7 @@ __global__ void __launch_bounds__(256, 4) lvm_direct_kernel(PathArgs a) {
     k.c1 = (float)((a.r - a.q) * dt);
     k.sdt = (float)sqrt(dt);
     k.hdt = (float)(0.5 * dt);
+    k.bm_dt = (float)(-1.3862943611198906 * dt);
     const float S0 = (float)a.S0;
     const float inv_n = (float)(1.0 / (double)n_steps);
     const float df = (float)exp(-a.pay[0].r_disc * a.pay[0].T_disc);
@@ -878,33 +886,37 @@ __global__ void __launch_bounds__(256, 4) lvm_direct_kernel(PathArgs a) {
         LinState p, m;
         p.S = p.smax = p.smin = S0;
         m = p;
-        unsigned int clamps = 0;
+        p.pmin = p.pmax = m.pmin = m.pmax = 0.5f * k.pos_max;
         float z[4];
         uint4 w = philox_words(a.seed, gpath, 0u, 0u);
         const float4* row = a.table4;
 #pragma unroll 1
         for (unsigned int c = 0; c < n_full; ++c) {
             const uint4 wn = philox_words(a.seed, gpath, c + 1, 0u);
-            normals_from_words(w, z);
+            normals_from_words_scaled(w, k.bm_dt, z);
             w = wn;
 #pragma unroll
             for (int j = 0; j < 4; ++j, row += n_ld) {
-                const float zs = k.sdt * z[j];
-                const float zzh = k.hdt * fmaf(z[j], z[j], -1.0f);
-                lvm_step_win<MASK, true>(p, row, k, zs, zzh, clamps);
-                if (ANTI) lvm_step_win<MASK, true>(m, row, k, -zs, zzh, clamps);
+                const float zs = z[j];
+                const float zzh = fmaf(0.5f * zs, zs, -k.hdt);
+                lvm_step_win<MASK, true>(p, row, k, zs, zzh);
+                if (ANTI) lvm_step_win<MASK, true>(m, row, k, -zs, zzh);
             }
         }
         if (n_tail) {
-            normals_from_words(w, z);
+            normals_from_words_scaled(w, k.bm_dt, z);
             for (unsigned int j = 0; j < n_tail; ++j, row += n_ld) {
-                const float zs = k.sdt * z[j];
-                const float zzh = k.hdt * fmaf(z[j], z[j], -1.0f);
-                lvm_step_win<MASK, true>(p, row, k, zs, zzh, clamps);
-                if (ANTI) lvm_step_win<MASK, true>(m, row, k, -zs, zzh, clamps);
+                const float zs = z[j];
+                const float zzh = fmaf(0.5f * zs, zs, -k.hdt);
+                lvm_step_win<MASK, true>(p, row, k, zs, zzh);
+                if (ANTI) lvm_step_win<MASK, true>(m, row, k, -zs, zzh);
             }
         }
-        acc_add(acc, 2, (double)clamps);
+        {
+            const int left_p = (p.pmin < 0.f || p.pmax > k.pos_max) ? 1 : 0;
+            const int left_m = (ANTI && (m.pmin < 0.f || m.pmax > k.pos_max)) ? 1 : 0;
+            acc_add(acc, 2, (double)(left_p + left_m));
+        }
         path_epilogue(a, finish_lin<MASK>(p, inv_n), df, b, n_eff, acc);
         if (ANTI) path_epilogue(a, finish_lin<MASK>(m, inv_n), df, a.n_base + b, n_eff, acc);
     }
