@@ -394,8 +394,9 @@ __global__ void __launch_bounds__(256, (PROC == OPTP_PROC_HESTON_FTE || PROC == 
     k.h_kt = (float)(a.kappa * a.theta * dt);
     k.h_xs = (float)(a.xi * sdt);
     {
-        // xi < 0 is xi > 0 with Z0 -> -Z0, rho -> -rho (the antithetic pair swaps its two members); xi = 0
-        // keeps a representable scale (the variance shock then is 1e-15 * Z0)
+        // xi < 0 is the same process as xi > 0 with rho -> -rho once Z0 is relabelled -Z0 (statistically
+        // identical; not path-identical to the fp64 kernel for xi < 0); xi = 0 keeps a representable scale
+        // (the variance shock then is 1e-15 * Z0)
         const double s = fmax(fabs(a.xi) * sdt, 1e-15);
         const double rho_eff = (a.xi < 0.0) ? -a.rho : a.rho;
         k.h_bm = (float)(-1.3862943611198906 * s * s);

@@ -568,6 +568,31 @@ def test_fp32_tracks_fp64_on_same_philox_draws(op, gen):
         assert rel(sa, sb) < 2e-3
 
 
+def test_heston_fp32_scaled_normals_cover_negative_and_zero_vol_of_vol(op):
+    """The fp32 Heston kernel takes its normals pre-scaled by |xi| sqrt(dt): xi < 0 runs as (-xi, -rho) -- the
+    same process with Z2 relabelled -Z2, so it must reproduce the (-xi, -rho) run exactly and agree with the
+    fp64 kernel (processes.py:153-160 literally, a different but equally valid sample) statistically; xi = 0
+    keeps a representable scale and stays path-identical to the fp64 kernel."""
+    from optpricer_b200 import exotics as ex, processes as pr
+    n = 200_000
+    specs = [ex.asian_spec(100.0, "call"), ex.barrier_spec(100.0, "put", 85.0, "down-and-in"), ex.vanilla_spec(100.0, "call")]
+
+    def run(xi, rho, mode):
+        lp = pr.heston_paths(100.0, 0.05, 0.0, 0.04, 2.0, 0.04, xi, rho, 1.0, 100, n, seed=5, mode=mode)
+        return ex.price_payoffs(lp, specs, 0.05, 1.0)
+
+    neg, pos = run(-0.3, 0.7, "fp32"), run(0.3, -0.7, "fp32")
+    for (a, sa), (b, sb) in zip(neg, pos):
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(b)) and abs(sa - sb) <= 1e-6 * sb
+    neg64 = run(-0.3, 0.7, "fp64")
+    for (a, sa), (b, sb) in zip(neg, neg64):
+        assert abs(a - b) <= 4.0 * math.hypot(sa, sb), (a, b, sa, sb)
+        assert rel(sa, sb) < 2e-2
+    zero, zero64 = run(0.0, -0.7, "fp32"), run(0.0, -0.7, "fp64")
+    for (a, sa), (b, sb) in zip(zero, zero64):
+        assert abs(a - b) <= 0.05 * sb and rel(sa, sb) < 2e-3
+
+
 def test_size_independent_properties_at_scale(op):
     """BASELINE-scale path counts: identities that hold path by path, whatever the size."""
     from optpricer_b200 import exotics as ex, processes as pr
