@@ -157,6 +157,7 @@ extern "C" int optp_dupire_table(const double* expiries, const double* svi, uint
         return e;
     c.table_steps = n_steps;
     c.table_nodes = n_nodes;
+    c.table_in_clip = true;  // the tabulation clips to [0.01, 5] (calibration.py:355)
     if (table_out)
         OPTP_CUDA(cudaMemcpyAsync(table_out, c.table_f64.p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     OPTP_CUDA(cudaStreamSynchronize(c.stream));

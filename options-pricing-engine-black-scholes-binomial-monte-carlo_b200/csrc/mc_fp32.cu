@@ -647,7 +647,7 @@ __device__ __forceinline__ void lv_step(LinState& s, const float2* row, const Lv
 // the bump is smaller than a cell (|c_up|, |c_dn| < 1): the bumped points are in the same cell or in
 // the neighbouring one.  Rows carry two replicated nodes on each side (flat extrapolation), pos is
 // clamped to [-1, n]; that reproduces the per-lookup clamping of the (value, slope) path exactly.
-template <int MASK, bool LDG = false>
+template <int MASK, bool LDG = false, bool CLIP = true>
 __device__ __forceinline__ void lvm_step_win(LinState& s, const float4* row, const LvConst& k, float zs,
                                              float zzh) {
     // Issue-cost model of sm_100a (profiles/r1_pipe_model.md): FFMA/FADD/FMNMX cost one issue
@@ -668,7 +668,9 @@ __device__ __forceinline__ void lvm_step_win(LinState& s, const float4* row, con
     // sigma at x + c_dn (c_dn in (-1,0)): v_j + max(td,0) s_j + min(td,0) s_{j-1}
     const float td = f + k.c_dn;
     const float sig_dn = fmaf(fminf(td, 0.0f), e.w, fmaf(fmaxf(td, 0.0f), e.y, e.x));
-    sig = fminf(fmaxf(sig, 1e-8f), 10.0f);
+    // processes.py:361-362 clips sigma to [1e-8, 10]; a table whose nodes all lie inside that range (every
+    // Dupire table: calibration.py:355 clips to [0.01, 5]) cannot leave it by linear interpolation
+    if (CLIP) sig = fminf(fmaxf(sig, 1e-8f), 10.0f);
     const float da = fmaf(sig_up, k.k_up, -(sig_dn * k.k_dn));
     const float av = sig * s.S;
     s.S = fmaxf(fmaf(av, fmaf(da, zzh, zs), fmaf(s.S, k.c1, s.S)), 1e-10f);
@@ -712,8 +714,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-template <int PROC, int MASK, bool ANTI, bool WIN>
+// WINMODE: 0 = (value, slope) table, three lookups; 1 = window table, one load; 2 = window table whose nodes
+// all lie inside the reference's clip range [1e-8, 10] (no per-step clip)
+template <int PROC, int MASK, bool ANTI, int WINMODE>
 __global__ void __launch_bounds__(kLvThreads, 4) lv_fp32_kernel(PathArgs a, int rows_per_chunk) {
+    constexpr bool WIN = WINMODE != 0;
     using Node = typename std::conditional<WIN, float4, float2>::type;
     extern __shared__ double dyn[];
     __shared__ double blockvals[kMaxVals];
@@ -823,8 +828,8 @@ __global__ void __launch_bounds__(kLvThreads, 4) lv_fp32_kernel(PathArgs a, int 
                             const float zs = z[j];
                             const float zzh = fmaf(0.5f * zs, zs, -k.hdt);  // (Z^2 - 1) dt / 2
                             if constexpr (WIN) {
-                                lvm_step_win<MASK>(p, row, k, zs, zzh);
-                                if (ANTI) lvm_step_win<MASK>(m, row, k, -zs, zzh);
+                                lvm_step_win<MASK, false, WINMODE != 2>(p, row, k, zs, zzh);
+                                if (ANTI) lvm_step_win<MASK, false, WINMODE != 2>(m, row, k, -zs, zzh);
                             } else {
                                 lv_step<PROC, MASK>(p, row, k, zs, zzh);
                                 if (ANTI) lv_step<PROC, MASK>(m, row, k, -zs, zzh);
@@ -1013,8 +1018,9 @@ static int launch_generic(const PathArgs& a, cudaStream_t st) {
     return 0;
 }
 
-template <int PROC, int MASK, bool ANTI, bool WIN>
+template <int PROC, int MASK, bool ANTI, int WINMODE>
 static int launch_lv_impl(const PathArgs& a, cudaStream_t st) {
+    constexpr bool WIN = WINMODE != 0;
     const size_t acc_bytes = sizeof(double) * (3 + 3 * a.n_pay) * kLvThreads;
     const size_t row_bytes = WIN ? sizeof(float4) * (size_t)(a.n_nodes + 4)
                                  : sizeof(float2) * (size_t)((a.n_nodes + 1) & ~1);
@@ -1029,7 +1035,7 @@ static int launch_lv_impl(const PathArgs& a, cudaStream_t st) {
     if (smem > 200 * 1024)
         return set_error(OPTP_E_TOO_LARGE, "sigma table rows of %d nodes do not fit shared memory",
                          a.n_nodes);
-    auto kern = lv_fp32_kernel<PROC, MASK, ANTI, WIN>;
+    auto kern = lv_fp32_kernel<PROC, MASK, ANTI, WINMODE>;
     if (smem > 48 * 1024)
         OPTP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -1056,10 +1062,11 @@ static int launch_lv(const PathArgs& a, cudaStream_t st) {
         const double cu = log1p(a.bump) / a.h, cd = -log1p(-fmin(a.bump, 0.999999)) / a.h;
         if (cu < 1.0 && cd < 1.0 && !ctx().lv_no_window) {
             if (ctx().lv_direct) return launch_lvm_direct<MASK, ANTI>(a, st);
-            return launch_lv_impl<PROC, MASK, ANTI, true>(a, st);
+            return ctx().table_in_clip ? launch_lv_impl<PROC, MASK, ANTI, 2>(a, st)
+                                       : launch_lv_impl<PROC, MASK, ANTI, 1>(a, st);
         }
     }
-    return launch_lv_impl<PROC, MASK, ANTI, false>(a, st);
+    return launch_lv_impl<PROC, MASK, ANTI, 0>(a, st);
 }
 
 template <int PROC, int MASK>

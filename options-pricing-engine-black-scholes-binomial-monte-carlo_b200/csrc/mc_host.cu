@@ -87,6 +87,9 @@ static int upload_table(const double* table, uint32_t n_steps, uint32_t n_nodes)
         return e;
     c.table_steps = n_steps;
     c.table_nodes = n_nodes;
+    bool in_clip = true;  // NaNs fail the comparison and keep the per-step clip
+    for (size_t i = 0; i < n && in_clip; ++i) in_clip = (table[i] >= 1e-8) && (table[i] <= 10.0);
+    c.table_in_clip = in_clip;
     return 0;
 }
 

@@ -34,6 +34,7 @@ struct Context {
     Arena cta_scratch;  // level arrays of the one-option-per-CTA CRR kernel when N > 9685
     Arena pin_in, pin_out;  // PINNED host staging of small CRR batches (one copy in, one copy out)
     uint32_t table_steps = 0, table_nodes = 0;
+    bool table_in_clip = false;  // every node of the staged sigma table lies in [1e-8, 10] (processes.py:361-362)
     uint64_t launches = 0;
     bool lv_direct = false;      // "lv_direct" = 1: window nodes gathered from global/L1, no smem staging
     bool lv_no_window = false;   // "lv_window" = 0: three-lookup (value, slope) path for LV Milstein
