@@ -142,3 +142,36 @@ def test_lazy_paths_shape_protocol(native):
     z = pr.heston_paths(100, .05, 0, .04, 2, .04, .3, -.7, 1, 3, 4, seed=5, rng="numpy").host_normals()
     g = np.random.default_rng(5)
     assert np.array_equal(z[0], g.standard_normal((3, 4))) and np.array_equal(z[1], g.standard_normal((3, 4)))
+
+
+def test_signatures_mirror_reference(native):
+    """Every parameter of every mirrored reference function -- name, kind (positional / keyword-only) and
+    default -- in the reference's order; the B200 package may only APPEND keyword-only options.  Golden:
+    tests/golden/signatures.json, recorded from the unmodified reference (make_golden_signatures.py)."""
+    import importlib
+    import inspect
+    import json
+    import numpy as np
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "golden", "signatures.json")) as f:
+        golden = json.load(f)
+
+    def enc(v):
+        if v is inspect.Parameter.empty:
+            return "<required>"
+        if v is np.float64:
+            return "np.float64"
+        if isinstance(v, (int, float, str, bool)) or v is None:
+            return v
+        if isinstance(v, (list, tuple)):
+            return [enc(x) for x in v]
+        return repr(v)
+
+    assert len(golden) == 19
+    for key, ref in golden.items():
+        mod, name = key.split(".")
+        fn = getattr(importlib.import_module("optpricer_b200." + mod), name)
+        mine = [[p.name, p.kind.name, enc(p.default)] for p in inspect.signature(fn).parameters.values()]
+        assert mine[:len(ref)] == ref, (key, ref, mine)
+        for extra in mine[len(ref):]:
+            assert extra[1] == "KEYWORD_ONLY" and extra[2] != "<required>", (key, extra)
