@@ -175,3 +175,25 @@ def test_signatures_mirror_reference(native):
         assert mine[:len(ref)] == ref, (key, ref, mine)
         for extra in mine[len(ref):]:
             assert extra[1] == "KEYWORD_ONLY" and extra[2] != "<required>", (key, extra)
+
+
+def test_argument_errors_mirror_reference(native):
+    """Invalid arguments raise the reference's exception type and text BEFORE any native code runs (no GPU is
+    needed to get the error).  Golden: tests/golden/errors.json, recorded by replaying golden_io.error_cases
+    against the unmodified reference (make_golden_errors.py)."""
+    import json
+    import optpricer_b200
+    from golden_io import error_cases
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "golden", "errors.json")) as f:
+        golden = json.load(f)
+
+    def norm(msg):  # the reference prints a set of allowed values: its order changes from process to process
+        return re.sub(r"\{([^}]*)\}", lambda m: "{" + ", ".join(sorted(x.strip() for x in m.group(1).split(","))) + "}", msg)
+
+    cases = error_cases(optpricer_b200)
+    assert {n for n, _ in cases} == set(golden) and all(v is not None for v in golden.values())
+    for name, call in cases:
+        with pytest.raises(Exception) as info:
+            call()
+        assert [type(info.value).__name__, norm(str(info.value))] == [golden[name][0], norm(golden[name][1])], name
