@@ -8,6 +8,7 @@ All three run the same CUDA kernel (csrc/crr_batch.cu) through optp_crr_batch.
 """
 from __future__ import annotations
 
+import ctypes as C
 from math import exp, sqrt
 
 import numpy as np
@@ -61,9 +62,15 @@ def crr(opt, kind=CALL, N=500, *, american=False):
 
     As in the reference, any `kind` other than "call" prices a put (binomial.py:22-25)."""
     _check_lattice(opt.T, opt.r, opt.q, opt.sigma, N)
-    v = crr_batch([opt.S0], [opt.K], [opt.T], [opt.r], [opt.q], [opt.sigma],
-                  [1 if kind == "call" else 0], N, american=american)
-    return float(v[0])
+    # a batch of one, without the array plumbing of crr_batch: the six "columns" are consecutive doubles
+    cols = np.array([opt.S0, opt.K, opt.T, opt.r, opt.q, opt.sigma, 0.0], dtype=np.float64)
+    call = np.array([1 if kind == "call" else 0], dtype=np.uint8)
+    status = np.zeros(1, dtype=np.uint8)
+    base = cols.ctypes.data
+    lib = nv.init()
+    nv.check(lib.optp_crr_batch(*[C.c_void_p(base + 8 * i) for i in range(6)], nv.ptr(call), 1, int(N),
+                                1 if american else 0, C.c_void_p(base + 48), nv.ptr(status)), "optp_crr_batch")
+    return float(cols[6])
 
 
 def crr_vec(S0, K, T, r, q, sigma, kind, N=500, *, american=False):
