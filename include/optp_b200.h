@@ -116,6 +116,9 @@ uint64_t optp_launch_count(void);
  *   "crr_band_kernel" 2 = two-zone banded kernel (default), 1 = the earlier single-zone banded kernel
  *   "crr_zone_group"  options per warp of the two-zone kernel: 1, 2, 4, or 0 = by batch size (default);
  *                   prices are bit-identical for every setting
+ *   "crr_euro_sum"  1 = European trees (and American contracts that are never exercised early) with
+ *                   N <= 20000 are priced as the discounted binomial expectation of the terminal payoff,
+ *                   O(N) per option (default); 0 = backward induction for every N
  * Returns OPTP_E_ARG for an unknown key. */
 int optp_set_option(const char* key, long value);
 /* Pinned host staging memory for callers that want DMA-able buffers. */

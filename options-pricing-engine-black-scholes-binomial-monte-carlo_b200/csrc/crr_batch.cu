@@ -1054,6 +1054,65 @@ __global__ void __launch_bounds__(256) crr_cta_kernel(CrrArgs a) {
     }
 }
 
+// ---------------------------------------------------------------- European: the level-0 value in O(N)
+// Without an exercise test the backward induction of binomial.py:28-29 is linear, and its level-0 value is
+// the discounted binomial expectation of the terminal payoff,
+//     V0 = e^{-rT} * sum_j C(N,j) p^j (1-p)^(N-j) * max(+-(S0 u^(2j-N) - K), 0),
+// which is what N(N+1)/2 node updates compute in another order.  One warp per option: lane l takes a
+// contiguous chunk of nodes, starts from the weight exp(lgamma(N+1) - lgamma(j+1) - lgamma(N-j+1) +
+// j ln p + (N-j) ln(1-p)) and from S0 u^(2j-N) = S0 exp(ln u (2j-N)), and walks its chunk with the exact
+// ratios w_{j+1}/w_j = (N-j)/(j+1) * p/(1-p) and S_{j+1}/S_j = u^2.  Rounding: |ln w| <= ~7 N, so the weights
+// carry ~7 N eps (8e-13 at N = 1000) -- the same order as the tree's own N roundings per path; used for
+// N <= 20000 (2e-11), deeper trees keep the recursion.  `optp_set_option("crr_euro_sum", 0)` restores the
+// recursion for every N (A/B tests).
+constexpr int kEuroSumMaxN = 20000;
+__global__ void __launch_bounds__(128) crr_euro_sum_kernel(CrrArgs a) {
+    if (a.todo_only && a.decl_count && a.decl_count[a.todo_only - 2] == 0) return;  // nothing was left for this pass
+    const int lane = threadIdx.x & 31;
+    const unsigned long long warp0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    const int N = a.N;
+    const int chunk = (N + 1 + 31) / 32;
+    const double lgN = lgamma((double)N + 1.0);
+    for (unsigned long long o = warp0; o < a.n; o += nwarps) {
+        if (a.todo_only && a.status[o] != a.todo_only) continue;
+        const double S0 = a.S0[o], K = a.K[o], T = a.T[o], r = a.r[o], q = a.q[o], sg = a.sigma[o];
+        const double sgn = a.is_call[o] ? 1.0 : -1.0;
+        const double dt = T / (double)N;
+        const double ln_u = sg * sqrt(dt);
+        const double u = exp(ln_u), d = 1.0 / u;
+        const double p = (exp((r - q) * dt) - d) / (u - d);  // binomial.py:15
+        if (!((p > 0.0) && (p < 1.0) && isfinite(S0) && isfinite(K))) {
+            if (lane == 0) {
+                a.price[o] = nan("");
+                a.status[o] = 1;
+            }
+            continue;
+        }
+        const int j0 = lane * chunk;
+        const int j1 = min(j0 + chunk, N + 1);
+        double acc = 0.0;
+        if (j0 < j1) {
+            const double lp = log(p), lq = log1p(-p);
+            double w = exp(lgN - lgamma((double)j0 + 1.0) - lgamma((double)(N - j0) + 1.0) + (double)j0 * lp +
+                           (double)(N - j0) * lq);
+            double S = S0 * exp(ln_u * (double)(2 * j0 - N));
+            const double odds = p / (1.0 - p), u2 = u * u;
+            for (int j = j0; j < j1; ++j) {
+                const double pay = sgn * (S - K);
+                acc = fma(w, pay > 0.0 ? pay : 0.0, acc);
+                w *= odds * ((double)(N - j) / (double)(j + 1));
+                S *= u2;
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            a.price[o] = exp(-r * T) * acc;
+            a.status[o] = 0;
+        }
+    }
+}
+
 // cudaOccupancyMaxActiveBlocksPerMultiprocessor costs microseconds per call and its answer never changes for
 // a (kernel, block size, dynamic shared memory = 0) triple: remember it (calls are serialised by the API lock).
 static int occupancy_cached(const void* fn, int threads, int* per_sm) {
@@ -1097,8 +1156,16 @@ static int launch_full_warp(const CrrArgs& a, int american, cudaStream_t st) {
 
 // Full-width pass (honours a.todo_only): one option per warp up to N = 1023, one per CTA beyond.
 static int launch_full(const CrrArgs& a_in, int american, cudaStream_t st, int slot) {
-    if (a_in.N <= 1023) return launch_full_warp(a_in, american, st);
     Context& c = ctx();
+    if (!american && a_in.N <= kEuroSumMaxN && !c.crr_no_euro_sum) {
+        const unsigned long long want = (a_in.n + 3) / 4;  // four warps (options in flight) per CTA
+        const unsigned long long cap = (unsigned long long)c.n_sm * 16;
+        crr_euro_sum_kernel<<<(unsigned int)(want < cap ? want : cap), 128, 0, st>>>(a_in);
+        c.launches++;
+        OPTP_CUDA(cudaGetLastError());
+        return 0;
+    }
+    if (a_in.N <= 1023) return launch_full_warp(a_in, american, st);
     CrrArgs a = a_in;
     size_t smem = sizeof(double) * 3 * (size_t)(a.N + 2);
     const unsigned long long cap = (unsigned long long)c.n_sm * 8;

@@ -200,6 +200,10 @@ int optp_set_option(const char* key, long value) {
         g_ctx.lv_no_window = (value == 0);
         return 0;
     }
+    if (!strcmp(key, "crr_euro_sum")) {
+        g_ctx.crr_no_euro_sum = (value == 0);
+        return 0;
+    }
     if (!strcmp(key, "crr_band_only")) {
         g_ctx.crr_band_only = (value != 0);
         return 0;

@@ -40,6 +40,7 @@ struct Context {
     bool lv_no_window = false;   // "lv_window" = 0: three-lookup (value, slope) path for LV Milstein
     bool crr_band_only = false;  // OPTP_CRR_BAND_ONLY=1: skip the fallback pass (diagnostics)
     bool crr_no_band = false;  // OPTP_CRR_NO_BAND=1: full-width CRR kernels only (A/B testing)
+    bool crr_no_euro_sum = false;  // "crr_euro_sum" = 0: European trees by backward induction for every N
     int crr_band_kernel = 2;   // 2 = two-zone banded kernel (default), 1 = single-zone banded kernel
     int crr_zone_group = 0;    // two-zone kernel: options per warp (1, 2, 4); 0 = by batch size
 };

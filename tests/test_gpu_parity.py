@@ -219,6 +219,39 @@ def test_crr_bad_contracts_do_not_disturb_their_warp_mates(op):
     np.testing.assert_array_equal(got[~bad], clean[~bad])
 
 
+def test_crr_european_expectation_kernel_equals_backward_induction(op):
+    """European trees are priced as the discounted binomial expectation of the terminal payoff (O(N) per
+    option); `crr_euro_sum = 0` restores the backward induction.  Both against each other over the corners of
+    parameter space and several depths, and against the C restatement of binomial.py:7-38 (1e-10)."""
+    from oracle import crr_c
+    from optpricer_b200 import _native as nv
+    g = np.random.default_rng(17)
+    n = 20_000
+    S0 = g.uniform(20, 300, n); K = S0 * np.exp(g.uniform(-1.2, 1.2, n)); T = np.exp(g.uniform(np.log(0.01), np.log(5.0), n))
+    sig = g.uniform(0.05, 0.9, n); r = g.uniform(-0.01, 0.12, n); q = np.where(g.random(n) < 0.5, 0.0, g.uniform(0.0, 0.1, n))
+    is_call = (g.random(n) < 0.5).astype(np.uint8)
+    worst = 0.0
+    for N in (1, 2, 5, 64, 257, 1000, 1023, 1024, 4000):
+        m = n if N <= 1024 else 400
+        cols = [c[:m] for c in (S0, K, T, r, q, sig, is_call)]
+        fast, st_f = op.crr_batch(*cols, N, return_status=True)
+        nv.set_option("crr_euro_sum", 0)
+        try:
+            tree, st_t = op.crr_batch(*cols, N, return_status=True)
+        finally:
+            nv.set_option("crr_euro_sum", 1)
+        np.testing.assert_array_equal(st_f, st_t)
+        ok = st_t == 0
+        np.testing.assert_allclose(fast[ok], tree[ok], rtol=REL_CRR, atol=REL_CRR)
+        assert np.all(np.isnan(fast[~ok]))
+        worst = max(worst, float(np.max(np.abs(fast[ok] - tree[ok]) / np.maximum(1.0, np.abs(tree[ok])))))
+    assert worst < 2e-11, worst
+    want, st_w = crr_c.crr_loop_ref(S0[:256], K[:256], T[:256], r[:256], q[:256], sig[:256], is_call[:256], 500, False)
+    got, st_g = op.crr_batch(S0[:256], K[:256], T[:256], r[:256], q[:256], sig[:256], is_call[:256], 500, return_status=True)
+    np.testing.assert_array_equal(st_g, st_w)
+    np.testing.assert_allclose(got[st_w == 0], want[st_w == 0], rtol=REL_CRR, atol=REL_CRR)
+
+
 def test_crr_never_exercised_contracts_take_the_european_recursion(op):
     """American calls with q <= 0 < r and American puts with r <= 0 <= q are never exercised early
     (binomial.py:30-36 always keeps the continuation value): they are routed to the European kernel and
