@@ -306,11 +306,19 @@ __device__ __forceinline__ void heston_qe_one(LogState& s, float& v, float z0, f
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_1b2) : "f"(1.0f + b2));
         const float bz = mufu_sqrt(b2) + z0;
         vn = (m * inv_1b2) * (bz * bz);
-    } else {  // exponential branch (small variance): rare, full-precision library calls
-        const float psi = 2.0f / tt;
-        const float p = (psi - 1.0f) / (psi + 1.0f);
-        const float u = normcdff(z0), omu = normcdff(-z0);
-        vn = (u <= p) ? 0.0f : logf((1.0f - p) / omu) * m / (1.0f - p);
+    } else {  // exponential branch (small variance, psi = 2/tt > 1.5): v' = 0 with probability p, else exponential
+        // p = (psi - 1)/(psi + 1) = (2 - tt)/(2 + tt), 1 - p = 2 tt/(2 + tt), v' = ln((1 - p)/(1 - u)) m/(1 - p)
+        // with u = Phi(z0); u <= p  <=>  1 - u >= 1 - p.  Reciprocals and the log are single MUFU ops here
+        // (a divergent warp pays for this branch in full, so it must be short); one normcdff, not two.
+        float inv_2ptt, inv_tt;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_2ptt) : "f"(2.0f + tt));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_tt) : "f"(tt));
+        const float omp = (tt + tt) * inv_2ptt;               // 1 - p
+        const float omu = normcdff(-z0);                      // 1 - u
+        float inv_omu;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_omu) : "f"(omu));
+        const float scale = 0.5f * m * (2.0f + tt) * inv_tt;  // m / (1 - p)
+        vn = (omu >= omp) ? 0.0f : (0.6931471805599453f * mufu_lg2(omp * inv_omu)) * scale;
     }
     const float vol = mufu_sqrt(fmaxf(k.q_K3 * (v + vn), 0.0f));
     s.x = fmaf(vol, z1, fmaf(k.q_K2, vn, fmaf(k.q_K1, v, s.x + k.q_K0)));
