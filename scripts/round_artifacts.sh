@@ -24,7 +24,7 @@ ncu)
   ncu --set full --clock-control none --import-source on -k crr_zone_kernel -s 9 -c 1 -f -o $O/prof_${TAG}_bench_zone \
       python bench.py --steps 1 --warmup 3 --skip-cpu --skip-extra > $O/ncu_full_zone_$TAG.log 2>&1
   # every production kernel at a size ncu replays quickly (third repetition of scripts/profile_target.py)
-  ncu --set full --clock-control none -k regex:"path_fp32|lv_fp32|terminal_fp32|crr_warp|crr_zone" -s 20 -c 10 -f \
+  ncu --set full --clock-control none -k regex:"path_fp32|lv_fp32|terminal_fp32|crr_warp|crr_zone|crr_euro_sum" -s 20 -c 10 -f \
       -o /tmp/prof_${TAG}_all python scripts/profile_target.py > $O/ncu_full_all_$TAG.log 2>&1
   python scripts/ncu_summary.py /tmp/prof_${TAG}_all.ncu-rep > $O/ncu_full_all_$TAG.md 2>> $O/ncu_full_all_$TAG.log
   for r in bench_gbm bench_zone; do
