@@ -168,10 +168,11 @@ def _cpu_extra_task(args):
     return units, time.perf_counter() - t0
 
 
-def cpu_step(pool, workers, mc_base, crr_per_worker, step):
-    """One bounded sample of each workload on `workers` host processes; returns units and seconds."""
+def cpu_step(pool, workers, mc_base, crr_per_worker, step, mc_calls=1):
+    """One bounded sample of each workload on `workers` host processes (`mc_calls` calls of mc_base base paths
+    per process, the way the reference would chunk a larger run); returns units and seconds."""
     t0 = time.perf_counter()
-    mc = list(pool.map(_cpu_mc_task, [(1000 * step + w, MC_STEPS, mc_base) for w in range(workers)]))
+    mc = list(pool.map(_cpu_mc_task, [(1000 * step + w, MC_STEPS, mc_base) for w in range(workers * mc_calls)]))
     t_mc = time.perf_counter() - t0
     t0 = time.perf_counter()
     cr = list(pool.map(_cpu_crr_task, [(w * crr_per_worker, (w + 1) * crr_per_worker) for w in range(workers)]))
@@ -209,13 +210,13 @@ def reference_arm(args):
         return 0
     import concurrent.futures as cf
     workers = os.cpu_count() or 1
-    mc_base, crr_per = 20_000, 8
+    mc_base, mc_calls, crr_per = 20_000, 3, 24   # ~1.2 s of work on every core per step
     with cf.ProcessPoolExecutor(max_workers=workers) as pool:
         for s in range(args.warmup):
             cpu_step(pool, workers, mc_base // 4, 2, s)
         u_mc = t_mc = u_crr = t_crr = 0.0
         for s in range(args.steps):
-            a, b, c, d = cpu_step(pool, workers, mc_base, crr_per, 100 + s)
+            a, b, c, d = cpu_step(pool, workers, mc_base, crr_per, 100 + s, mc_calls)
             u_mc += a; t_mc += b; u_crr += c; t_crr += d
         try:
             t0 = time.perf_counter()
@@ -236,7 +237,8 @@ def reference_arm(args):
             except Exception as e:
                 extra.append({"workload": label, "unavailable": str(e)[:200]})
     mc_v, crr_v = u_mc / t_mc, u_crr / t_crr
-    sample_mc = f"{workers} processes x (252 steps x {mc_base} base paths + mirrors) per step, oracle numpy port"
+    sample_mc = (f"{workers} processes x {mc_calls} calls of (252 steps x {mc_base} base paths + mirrors) per step, "
+                 "oracle numpy port")
     sample_crr = f"{workers} processes x {crr_per} config-2 contracts per step, oracle numpy port"
     line = {
         "impl": "reference", "metric": "mc_path_steps_per_sec", "value": mc_v, "unit": "path-steps/s",
