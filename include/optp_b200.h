@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define OPTP_ABI_VERSION 6
+#define OPTP_ABI_VERSION 7
 
 /* argument errors */
 #define OPTP_E_ARG 1        /* bad scalar argument / null pointer            */
@@ -116,11 +116,22 @@ uint64_t optp_launch_count(void);
  *   "crr_band_kernel" 2 = two-zone banded kernel (default), 1 = the earlier single-zone banded kernel
  *   "crr_zone_group"  options per warp of the two-zone kernel: 1, 2, 4, or 0 = by batch size (default);
  *                   prices are bit-identical for every setting
+ *   "rng_mode"      generator mode of the fp32 GBM path kernel: 0 = Philox4x32-10, two Box-Muller pairs of
+ *                   (32-bit radius, 32-bit angle) per call (default; every parity statement is made for it),
+ *                   1 = Philox4x32-7, same mapping, 2 = Philox4x32-10 with three Box-Muller pairs of
+ *                   (26-bit radius, 16/16/18-bit angle) per call (6 normals; tails end at 6.1 sigma).
+ *                   Modes 1 and 2 trade generator margin for speed and are opt-in; see optp_normal_stats
  *   "crr_euro_sum"  1 = European trees (and American contracts that are never exercised early) with
  *                   N <= 20000 are priced as the discounted binomial expectation of the terminal payoff,
  *                   O(N) per option (default); 0 = backward induction for every N
+ *   "crr_count_ops" 1 = the two-zone CRR kernel counts the work its level loops execute (diagnostic build of
+ *                   the same kernel; setting it also resets the counters), 0 = production kernels (default)
  * Returns OPTP_E_ARG for an unknown key. */
 int optp_set_option(const char* key, long value);
+/* Diagnostics counters (bench.py's physical roofline figure): "crr_fp64_lane_ops" = FP64-pipe lane-instructions
+ * (DFMA, DMUL, DSETP) executed inside the level loops of the two-zone CRR kernel since "crr_count_ops" was
+ * set, "crr_node_updates" = node updates executed there.  Synchronises the device. */
+int optp_get_counter(const char* key, uint64_t* value_out);
 /* Pinned host staging memory for callers that want DMA-able buffers. */
 int optp_host_alloc(void** p, uint64_t bytes);
 int optp_host_free(void* p);
@@ -166,6 +177,11 @@ int optp_mc_path_dev(const optp_process* proc, const optp_payoff* payoffs, uint3
                      void* stream);
 /* Stage a sigma(S,t) table (n_steps x n_nodes fp64, host) in HBM for later _dev calls. */
 int optp_sigma_table_upload(const double* table, uint32_t n_steps, uint32_t n_nodes);
+/* Handle-based staging, so that ONE optp_mc_book call can carry local-vol items with different tables
+ * (bumped surfaces of a risk run; the desk workflow's barrier + vanilla legs share one).  Handles are small
+ * positive integers owned by the context; at most 63 are live at a time. */
+int optp_sigma_table_create(const double* table, uint32_t n_steps, uint32_t n_nodes, int32_t* handle_out);
+int optp_sigma_table_destroy(int32_t handle);
 /* Tabulate the Dupire local volatility of a raw-SVI surface ON THE DEVICE and stage it like
  * optp_sigma_table_upload does: row i = step time i*T/n_steps, node j at ln S = x0 + h*j.
  * Replaces the host loop over the reference's callable dupire_local_vol_func(surface, r, q)
@@ -200,8 +216,10 @@ int optp_payoff_from_paths(const double* paths, uint64_t n_rows, uint64_t n_cols
  * <generator> + <payoff(s)> pair; all items are launched back to back on the context's stream
  * and the statistics blocks come back in ONE device-to-host copy.
  *   stats_out: for every item, in order, n_payoffs blocks of OPTP_NSTATS doubles
- *   (terminal_only items: one block).  Local-vol processes are not accepted here (one sigma
- *   table per context).  path_offset shards the base paths of an item across GPUs. */
+ *   (terminal_only items: one block).  Local-vol items (milstein_local_vol_paths + payoffs, the desk
+ *   workflow scripts/desk_workflow_localvol_barrier.py:136-148) name their table by handle
+ *   (optp_sigma_table_create); proc.sigma_table is ignored.  path_offset shards the base paths of an item
+ *   across GPUs. */
 typedef struct optp_book_item {
     int32_t terminal_only;  /* 1: optp_mc_terminal semantics, uses proc.{S0,r,q,T,sigma}, K, is_call */
     int32_t n_payoffs;      /* payoffs[first_payoff .. first_payoff + n_payoffs), ignored if terminal_only */
@@ -209,7 +227,8 @@ typedef struct optp_book_item {
     uint32_t n_steps;
     uint64_t n_base, seed, path_offset;
     int32_t antithetic, mode;
-    int32_t is_call, reserved;
+    int32_t is_call;
+    int32_t table_handle;   /* LV_* items: handle of the staged sigma table (>= 1); else ignored */
     double K;
     optp_process proc;
 } optp_book_item;
@@ -231,13 +250,48 @@ int optp_crr_batch_dev(const double* S0, const double* K, const double* T, const
                        uint64_t n, uint32_t N, int american, double* price_out,
                        uint8_t* status_out, void* stream);
 
+/* ---- multi-GPU reduction (one process per GPU) -------------------------------------
+ * Replaces _aggregate_stats over the reference's worker processes (monte_carlo.py:67-74, filled by the
+ * ProcessPoolExecutor of monte_carlo.py:126-139): the statistics blocks are additive, so ONE sum over the
+ * ranks gives the whole run.  The library owns one NCCL communicator per context (libnccl.so.2 is resolved
+ * at run time with dlopen -- the copy already loaded in the process, e.g. torch's, is preferred).
+ *   optp_comm_unique_id: rank 0 creates the 128-byte id; the caller ships it to the other ranks by any
+ *                        means it has (torch.distributed broadcast, MPI, a file).
+ *   optp_comm_init:      collective over the `world` ranks; binds to the device of optp_init.
+ *   optp_allreduce_stats:     HOST buffer, in place (staged through pinned memory; synchronous).
+ *   optp_allreduce_stats_dev: DEVICE buffer, in place, asynchronous on `stream` -- queue it behind the
+ *                        *_dev kernel launches that produced the blocks and no host round trip is paid.
+ * Without a communicator (world of one) both reductions are the identity and return 0. */
+#define OPTP_COMM_ID_BYTES 128
+int optp_comm_unique_id(char id_out[OPTP_COMM_ID_BYTES]);
+int optp_comm_init(int rank, int world, const char id[OPTP_COMM_ID_BYTES]);
+int optp_comm_destroy(void);
+int optp_comm_info(int* rank_out, int* world_out);
+int optp_allreduce_stats(double* stats, uint64_t n_doubles);
+int optp_allreduce_stats_dev(double* stats_dev, uint64_t n_doubles, void* stream);
+
+/* ---- generator self-checks ----------------------------------------------------------
+ * optp_philox4x32_10: HOST-only evaluation of the library's Philox4x32-10 (the function the kernels inline)
+ *   for known-answer tests against the Random123 vectors; needs neither a device nor optp_init.
+ * optp_normal_stats: draws normals on the device exactly as the fused path kernels do (counter = (path,
+ *   block, stream 0), key = seed; n_paths x n_blocks Philox calls, 4 or 6 normals each) and returns
+ *   [0] n  [1..4] sum z, z^2, z^3, z^4  [5..8] counts of |z| > 3, 4, 5, 6  [9] sum of products of the two
+ *   normals of a Box-Muller pair  [10] sum of products of the first normals of different pairs of a call
+ *   [11] sum of (last normal of block c) x (first normal of block c+1) along a path  [12] max |z|
+ *   [13], [14], [15] the number of products behind [9], [10], [11].
+ * The reference draws with numpy's PCG64 ziggurat (processes.py:24,48); these checks are what stands behind
+ * replacing it with a counter-based generator. */
+int optp_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+int optp_normal_stats(uint64_t seed, uint64_t path_offset, uint64_t n_paths, uint32_t n_blocks, int rng_mode,
+                      double stats_out[16]);
+
 /* ---- roofline microbenchmarks (bench.py only) ---------------------------------
  * Measure the peaks MEASURED_PEAKS.json lacks, on the device, with CUDA events:
  *   which = 0 FP32 FFMA lane-ops/s, 1 MUFU.EX2 ops/s, 2 FP64 DFMA lane-ops/s,
  *           3 shared-memory bytes/s (LDS.64 conflict-free), 4 IMAD.WIDE+LOP3 pairs/s,
  *           5..14 single-opcode probes used to build the pipe model in profiles/ (IMAD.WIDE,
  *           IMAD.HI, IMAD, LOP3, I2FP, MUFU.SIN, MUFU.LG2, MUFU.SQRT, FMNMX, FADD lane-ops/s). */
-int optp_microbench(int which, double* per_second_out, double* sm_clock_mhz_out);
+int optp_microbench(int which, double* per_second_out, double* cta_cycles_out /* may be NULL */);
 
 #ifdef __cplusplus
 }

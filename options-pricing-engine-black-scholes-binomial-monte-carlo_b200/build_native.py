@@ -34,6 +34,8 @@ UNITS = {
     "crr_batch.cu": [],
     "dupire_table.cu": ["-fmad=false"],
     "microbench.cu": [],
+    "rng_check.cu": [],
+    "comm.cu": [],
 }
 HEADERS = ["optp_common.cuh", "mc_kernels.cuh", os.path.join("..", "..", "include", "optp_b200.h")]
 
@@ -82,7 +84,7 @@ def build(force=False, verbose=False):
         list(ex.map(lambda ue: _compile(nvcc, ue[0], ue[1], verbose), todo))
     objs = [os.path.join(OBJ_DIR, u.replace(".cu", ".o")) for u in UNITS]
     if todo or force or _stale(LIB, objs):
-        cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fPIC"]
+        cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fPIC", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)

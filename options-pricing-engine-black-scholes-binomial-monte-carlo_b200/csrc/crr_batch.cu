@@ -48,6 +48,9 @@ struct CrrArgs {
     // one-option-per-CTA kernel: level arrays in global memory (3*(N+2) doubles per CTA) when they do not
     // fit in shared memory, else null
     double* cta_scratch;
+    // diagnostics ("crr_count_ops" = 1): {FP64-pipe lane-instructions, node updates} executed inside the level
+    // loops of the two-zone kernel, summed over the batch (two atomics per warp and option group), or null
+    unsigned long long* op_count;
 };
 
 struct Lattice {
@@ -687,7 +690,7 @@ __device__ __forceinline__ unsigned int zone_segment(double (&z)[G], double (&c)
     return mask;
 }
 
-template <int G>
+template <int G, bool COUNT = false>
 __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_kernel(CrrArgs a) {
     constexpr int LG = 32 / G, BZ = G, BCMAX = kZoneLaneC, kMaxM = zone_max_m(G), kGroupTile = zone_group_tile(G);
     __shared__ double tiles[kZoneWarps][G * kGroupTile];
@@ -866,6 +869,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             if (w0 > 0 && jlo <= w0) fail = true;
         };
         measure_band();
+        unsigned int cnt_fp64 = 0, cnt_nodes = 0;  // per lane; COUNT builds only
         int width_old = 32;  // M = 0 at level N
         if (k > 0 && __reduce_or_sync(0xffffffffu, (j1 <= N + 1 && !fail) ? 1u : 0u) != 0u) {
             // q > r (see `jump`): from level N-1 on the boundary is the first node above S1, far below
@@ -979,9 +983,18 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             const int top_ex = __shfl_sync(0xffffffffu, n_exT, gb + LG - 1);
             if (w0 > 0 && bottom_ex != nlev) fail = true;
             if (top_ex != 0) fail = true;
+            if (COUNT) {
+                // per lane and level: Z nodes 2 DFMA + 1 DSETP each, C nodes 1 DFMA each, 2 scaling DMULs
+                cnt_fp64 += (unsigned int)(nlev * (3 * G + G * M + 2));
+                cnt_nodes += (unsigned int)(nlev * (G + G * M));
+            }
             k -= nlev;
             measure_band();
             width_old = 32 * (1 + M);
+        }
+        if (COUNT && lane == 0 && a.op_count) {
+            atomicAdd(&a.op_count[0], 32ull * cnt_fp64);
+            atomicAdd(&a.op_count[1], 32ull * cnt_nodes);
         }
         // level 0: node 0 is in the window (w0 == 0) or below it (then it is an exercise node)
         const double v0 = __shfl_sync(0xffffffffu, z[0], gb);
@@ -1203,6 +1216,26 @@ static int crr_reserve_worklists(unsigned long long n) {
     return arena_reserve(ctx().work, 2 * (256 + 2 * crr_worklist_bytes(n)) + 512);  // two slots of {header, list, list}
 }
 
+// the two-zone kernel for G options per warp; COUNT = with the executed-work counters (diagnostics)
+static const void* zone_fn(int G, bool count) {
+    if (count) return (G == 4) ? (const void*)crr_zone_kernel<4, true> : (G == 2) ? (const void*)crr_zone_kernel<2, true>
+                                                                               : (const void*)crr_zone_kernel<1, true>;
+    return (G == 4) ? (const void*)crr_zone_kernel<4> : (G == 2) ? (const void*)crr_zone_kernel<2>
+                                                                 : (const void*)crr_zone_kernel<1>;
+}
+static void zone_launch(int G, bool count, unsigned int grid, const CrrArgs& a, cudaStream_t st) {
+    const dim3 blk(kZoneWarps * 32);
+    if (count) {
+        if (G == 4) crr_zone_kernel<4, true><<<grid, blk, 0, st>>>(a);
+        else if (G == 2) crr_zone_kernel<2, true><<<grid, blk, 0, st>>>(a);
+        else crr_zone_kernel<1, true><<<grid, blk, 0, st>>>(a);
+    } else {
+        if (G == 4) crr_zone_kernel<4><<<grid, blk, 0, st>>>(a);
+        else if (G == 2) crr_zone_kernel<2><<<grid, blk, 0, st>>>(a);
+        else crr_zone_kernel<1><<<grid, blk, 0, st>>>(a);
+    }
+}
+
 // `slot` (0 or 1) selects the work-list scratch: launches that may be in flight together (the two
 // streams of the sliced host pipeline) must use different slots.
 static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st, int slot = 0) {
@@ -1213,6 +1246,7 @@ static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st, int sl
     a.wl_out = a.wl_out_n = nullptr;
     a.decl_count = nullptr;
     a.cta_scratch = nullptr;
+    a.op_count = nullptr;
     if (a.n == 0) return 0;
     if (a.n >= (1ull << 32)) return set_error(OPTP_E_TOO_LARGE, "a CRR batch holds at most 2^32 - 1 contracts");
     if (american && !c.crr_no_band) {
@@ -1244,22 +1278,23 @@ static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st, int sl
                 a.wl_out_n = hdr;
             }
         }
-        const void* fn = (G == 4)   ? (const void*)crr_zone_kernel<4>
-                         : (G == 2) ? (const void*)crr_zone_kernel<2>
-                         : (G == 1) ? (const void*)crr_zone_kernel<1>
-                                    : (const void*)crr_band_kernel;
+        const bool count = c.crr_count_ops && G >= 1;
+        if (count) {
+            if (!c.crr_op_count) {
+                OPTP_CUDA(cudaMalloc(&c.crr_op_count, 2 * sizeof(unsigned long long)));
+                OPTP_CUDA(cudaMemsetAsync(c.crr_op_count, 0, 2 * sizeof(unsigned long long), st));
+            }
+            a.op_count = c.crr_op_count;
+        }
+        const void* fn = (G >= 1) ? zone_fn(G, count) : (const void*)crr_band_kernel;
         static_assert(kBandWarps == kZoneWarps, "one grid computation for both banded kernels");
         if (int e = occupancy_cached(fn, kZoneWarps * 32, &per_sm)) return e;
         const unsigned long long per_warp = (G > 0) ? (unsigned long long)G : 1ull;
         const unsigned long long want = (a.n + kBandWarps * per_warp - 1) / (kBandWarps * per_warp);
         const unsigned long long cap = (unsigned long long)c.n_sm * per_sm;
         const unsigned int grid = (unsigned int)(want < cap ? want : cap);
-        if (G == 4)
-            crr_zone_kernel<4><<<grid, kZoneWarps * 32, 0, st>>>(a);
-        else if (G == 2)
-            crr_zone_kernel<2><<<grid, kZoneWarps * 32, 0, st>>>(a);
-        else if (G == 1)
-            crr_zone_kernel<1><<<grid, kZoneWarps * 32, 0, st>>>(a);
+        if (G >= 1)
+            zone_launch(G, count, grid, a, st);
         else
             crr_band_kernel<<<grid, kBandWarps * 32, 0, st>>>(a);
         c.launches++;
@@ -1272,15 +1307,11 @@ static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st, int sl
             a.wl_in_n = hdr + list;
             a.wl_out = (g2 == 2) ? wl[1] : nullptr;
             a.wl_out_n = (g2 == 2) ? hdr + 1 : nullptr;
-            const void* fn2 = (g2 == 2) ? (const void*)crr_zone_kernel<2> : (const void*)crr_zone_kernel<1>;
-            if (int e = occupancy_cached(fn2, kZoneWarps * 32, &per_sm)) return e;
+            if (int e = occupancy_cached(zone_fn(g2, count), kZoneWarps * 32, &per_sm)) return e;
             const unsigned long long want2 = (a.n + kZoneWarps * g2 - 1) / (kZoneWarps * g2);
             const unsigned long long cap2 = (unsigned long long)c.n_sm * per_sm;
             const unsigned int grid2 = (unsigned int)(want2 < cap2 ? want2 : cap2);
-            if (g2 == 2)
-                crr_zone_kernel<2><<<grid2, kZoneWarps * 32, 0, st>>>(a);
-            else
-                crr_zone_kernel<1><<<grid2, kZoneWarps * 32, 0, st>>>(a);
+            zone_launch(g2, count, grid2, a, st);
             c.launches++;
             OPTP_CUDA(cudaGetLastError());
         }

@@ -125,9 +125,9 @@ extern "C" int optp_dupire_table(const double* expiries, const double* svi, uint
     // surface description: expiries | svi | fwd_T | fwd_F in one staging arena
     const size_t n_in = (size_t)n_exp * 6 + (size_t)n_fwd * 2;
     if (int e = arena_reserve(c.in1, n_in * sizeof(double))) return e;
-    if (int e = arena_reserve(c.table_f64, n * sizeof(double))) return e;
-    if (int e = arena_reserve(c.table_f32, (size_t)n_steps * n_ld * sizeof(float2))) return e;
-    if (int e = arena_reserve(c.table_f4, (size_t)n_steps * (n_nodes + 4) * sizeof(float4))) return e;
+    if (int e = arena_reserve(c.tables[0].f64, n * sizeof(double))) return e;
+    if (int e = arena_reserve(c.tables[0].f32, (size_t)n_steps * n_ld * sizeof(float2))) return e;
+    if (int e = arena_reserve(c.tables[0].f4, (size_t)n_steps * (n_nodes + 4) * sizeof(float4))) return e;
     double* in = (double*)c.in1.p;
     OPTP_CUDA(cudaMemcpyAsync(in, expiries, n_exp * sizeof(double), cudaMemcpyHostToDevice, c.stream));
     OPTP_CUDA(cudaMemcpyAsync(in + n_exp, svi, 5 * (size_t)n_exp * sizeof(double), cudaMemcpyHostToDevice, c.stream));
@@ -146,20 +146,20 @@ extern "C" int optp_dupire_table(const double* expiries, const double* svi, uint
     a.dT = dT;
     a.n_steps = n_steps;
     a.n_nodes = n_nodes;
-    a.table = (double*)c.table_f64.p;
+    a.table = (double*)c.tables[0].f64.p;
     const unsigned int grid = (unsigned int)((n + 255) / 256 < (size_t)c.n_sm * 8 ? (n + 255) / 256 : (size_t)c.n_sm * 8);
     dupire_table_kernel<<<grid, 256, 0, c.stream>>>(a);
     c.launches++;
     OPTP_CUDA(cudaGetLastError());
     // the fp32 (value, slope) and window tables the production kernels read
-    if (int e = launch_table_convert((const double*)c.table_f64.p, (float2*)c.table_f32.p,
-                                     (float4*)c.table_f4.p, n_steps, (int)n_nodes, c.stream))
+    if (int e = launch_table_convert((const double*)c.tables[0].f64.p, (float2*)c.tables[0].f32.p,
+                                     (float4*)c.tables[0].f4.p, n_steps, (int)n_nodes, c.stream))
         return e;
-    c.table_steps = n_steps;
-    c.table_nodes = n_nodes;
-    c.table_in_clip = true;  // the tabulation clips to [0.01, 5] (calibration.py:355)
+    c.tables[0].steps = n_steps;
+    c.tables[0].nodes = n_nodes;
+    c.tables[0].in_clip = true;  // the tabulation clips to [0.01, 5] (calibration.py:355)
     if (table_out)
-        OPTP_CUDA(cudaMemcpyAsync(table_out, c.table_f64.p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        OPTP_CUDA(cudaMemcpyAsync(table_out, c.tables[0].f64.p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     OPTP_CUDA(cudaStreamSynchronize(c.stream));
     return 0;
 }

@@ -379,7 +379,7 @@ __device__ __forceinline__ void sabr_step_lin(LinState& p, LinState& m, float& l
     }
 }
 
-template <int PROC, int MASK, bool ANTI>
+template <int PROC, int MASK, bool ANTI, int RNG = RNG_PHILOX10>
 __global__ void __launch_bounds__(256, (PROC == OPTP_PROC_HESTON_FTE || PROC == OPTP_PROC_HESTON_QE) ? 4 : 5) path_fp32_kernel(PathArgs a) {
     extern __shared__ double dyn[];
     __shared__ double blockvals[kMaxVals];
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(256, (PROC == OPTP_PROC_HESTON_FTE || PROC == 
     const unsigned long long n_eff = ANTI ? 2 * a.n_base : a.n_base;
     constexpr int kDims =
         (PROC == OPTP_PROC_HESTON_FTE || PROC == OPTP_PROC_HESTON_QE || PROC == OPTP_PROC_SABR) ? 2 : 1;
-    constexpr int kPerCall = 4 / kDims;  // steps served by one Philox call
+    constexpr int kPerCall = RngTraits<RNG>::normals / kDims;  // steps served by one Philox call
     const unsigned int n_full = n_steps / kPerCall, n_tail = n_steps % kPerCall;
 
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
@@ -457,20 +457,21 @@ __global__ void __launch_bounds__(256, (PROC == OPTP_PROC_HESTON_FTE || PROC == 
          b < a.n_base; b += stride) {
         const unsigned long long gpath = a.path_offset + b;
         PathEnd ep, em;
-        float z[4];
+        float z[RngTraits<RNG>::normals];
         if (PROC == OPTP_PROC_GBM) {
+            // (RNG = 0 is bit-identical to normals_from_words: same words, same radius constant)
             LogState p, m;
-            uint4 w = philox_words(a.seed, gpath, 0u, 0u);
+            uint4 w = philox_words_m<RNG>(a.seed, gpath, 0u, 0u);
 #pragma unroll 1
             for (unsigned int c = 0; c < n_full; ++c) {
-                const uint4 wn = philox_words(a.seed, gpath, c + 1, 0u);  // software pipeline
-                normals_from_words(w, z);
+                const uint4 wn = philox_words_m<RNG>(a.seed, gpath, c + 1, 0u);  // software pipeline
+                normals_from_words_m<RNG>(w, -1.3862943611198906f, z);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) gbm_step<MASK, ANTI>(p, m, z[j], k);
+                for (int j = 0; j < kPerCall; ++j) gbm_step<MASK, ANTI>(p, m, z[j], k);
                 w = wn;
             }
             if (n_tail) {
-                normals_from_words(w, z);
+                normals_from_words_m<RNG>(w, -1.3862943611198906f, z);
                 for (unsigned int j = 0; j < n_tail; ++j) gbm_step<MASK, ANTI>(p, m, z[j], k);
             }
             ep = finish_log<MASK>(p, S0, inv_n);
@@ -1004,23 +1005,27 @@ bool path_fp32_supported(int proc) {
            proc == OPTP_PROC_LV_MILSTEIN || proc == OPTP_PROC_LV_EULER;
 }
 
-template <int PROC, int MASK, bool ANTI>
+template <int PROC, int MASK, bool ANTI, int RNG = RNG_PHILOX10>
 static int launch_generic(const PathArgs& a, cudaStream_t st) {
     const int threads = 256;
     const size_t smem = sizeof(double) * (3 + 3 * a.n_pay) * threads;
+    if constexpr (PROC == OPTP_PROC_GBM && RNG == RNG_PHILOX10) {  // opt-in generator modes (GBM only)
+        if (a.rng_mode == RNG_PHILOX7) return launch_generic<PROC, MASK, ANTI, RNG_PHILOX7>(a, st);
+        if (a.rng_mode == RNG_PHILOX10_X6) return launch_generic<PROC, MASK, ANTI, RNG_PHILOX10_X6>(a, st);
+    }
     if (smem > 48 * 1024)
-        OPTP_CUDA(cudaFuncSetAttribute(path_fp32_kernel<PROC, MASK, ANTI>,
+        OPTP_CUDA(cudaFuncSetAttribute(path_fp32_kernel<PROC, MASK, ANTI, RNG>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     OPTP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &per_sm, path_fp32_kernel<PROC, MASK, ANTI>, threads, smem));
+        &per_sm, path_fp32_kernel<PROC, MASK, ANTI, RNG>, threads, smem));
     if (per_sm < 1) per_sm = 1;
     unsigned long long blocks = (a.n_base + threads - 1) / threads;
     unsigned long long cap = (unsigned long long)ctx().n_sm * per_sm;
     if (cap > kMaxBlocks) cap = kMaxBlocks;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    path_fp32_kernel<PROC, MASK, ANTI><<<(unsigned int)blocks, threads, smem, st>>>(a);
+    path_fp32_kernel<PROC, MASK, ANTI, RNG><<<(unsigned int)blocks, threads, smem, st>>>(a);
     ctx().launches++;
     OPTP_CUDA(cudaGetLastError());
     return 0;
@@ -1070,7 +1075,7 @@ static int launch_lv(const PathArgs& a, cudaStream_t st) {
         const double cu = log1p(a.bump) / a.h, cd = -log1p(-fmin(a.bump, 0.999999)) / a.h;
         if (cu < 1.0 && cd < 1.0 && !ctx().lv_no_window) {
             if (ctx().lv_direct) return launch_lvm_direct<MASK, ANTI>(a, st);
-            return ctx().table_in_clip ? launch_lv_impl<PROC, MASK, ANTI, 2>(a, st)
+            return a.table_in_clip ? launch_lv_impl<PROC, MASK, ANTI, 2>(a, st)
                                        : launch_lv_impl<PROC, MASK, ANTI, 1>(a, st);
         }
     }

@@ -47,21 +47,24 @@ static bool is_lv(int kind) { return kind == OPTP_PROC_LV_MILSTEIN || kind == OP
 
 static void fill_args(PathArgs& a, const optp_process* pr, const optp_payoff* pay, uint32_t n_pay,
                       uint32_t n_steps, uint64_t n_base, int anti, int mode, uint64_t seed,
-                      uint64_t path_offset) {
+                      uint64_t path_offset, int table_slot = 0) {
     Context& c = ctx();
+    const SigmaTableDev& tb = c.tables[table_slot];
     memset(&a, 0, sizeof(a));
     a.proc = pr->kind;
     a.n_nodes = pr->n_nodes;
     a.S0 = pr->S0; a.r = pr->r; a.q = pr->q; a.T = pr->T; a.sigma = pr->sigma;
     a.v0 = pr->v0; a.kappa = pr->kappa; a.theta = pr->theta; a.xi = pr->xi; a.rho = pr->rho;
     a.bump = pr->dS_bump; a.x0 = pr->x0; a.h = pr->h;
-    a.table32 = (const float2*)c.table_f32.p;
-    a.table4 = (const float4*)c.table_f4.p;
-    a.table64 = (const double*)c.table_f64.p;
+    a.table32 = (const float2*)tb.f32.p;
+    a.table4 = (const float4*)tb.f4.p;
+    a.table64 = (const double*)tb.f64.p;
+    a.table_in_clip = tb.in_clip ? 1 : 0;
     a.n_steps = n_steps;
     a.n_base = n_base;
     a.anti = anti ? 1 : 0;
     a.use_philox = (mode != OPTP_MODE_FP64_HOSTZ);
+    a.rng_mode = c.rng_mode;
     a.seed = seed;
     a.path_offset = path_offset;
     a.n_pay = (int)n_pay;
@@ -70,26 +73,36 @@ static void fill_args(PathArgs& a, const optp_process* pr, const optp_payoff* pa
     a.ticket = c.ticket;
 }
 
-static int upload_table(const double* table, uint32_t n_steps, uint32_t n_nodes) {
+static int upload_table(const double* table, uint32_t n_steps, uint32_t n_nodes, int slot = 0) {
     Context& c = ctx();
+    SigmaTableDev& tb = c.tables[slot];
     if (!table || n_steps == 0 || n_nodes < 2)
         return set_error(OPTP_E_ARG, "sigma table must be n_steps x n_nodes with n_nodes >= 2");
     const size_t n = (size_t)n_steps * n_nodes;
     const size_t n_ld = (n_nodes + 1) & ~1u;
-    if (int e = arena_reserve(c.table_f64, n * sizeof(double))) return e;
-    if (int e = arena_reserve(c.table_f32, (size_t)n_steps * n_ld * sizeof(float2))) return e;
-    if (int e = arena_reserve(c.table_f4, (size_t)n_steps * (n_nodes + 4) * sizeof(float4))) return e;
-    OPTP_CUDA(cudaMemcpyAsync(c.table_f64.p, table, n * sizeof(double), cudaMemcpyHostToDevice,
-                              c.stream));
-    if (int e = launch_table_convert((const double*)c.table_f64.p, (float2*)c.table_f32.p,
-                                     (float4*)c.table_f4.p, n_steps,
+    if (int e = arena_reserve(tb.f64, n * sizeof(double))) return e;
+    if (int e = arena_reserve(tb.f32, (size_t)n_steps * n_ld * sizeof(float2))) return e;
+    if (int e = arena_reserve(tb.f4, (size_t)n_steps * (n_nodes + 4) * sizeof(float4))) return e;
+    OPTP_CUDA(cudaMemcpyAsync(tb.f64.p, table, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    if (int e = launch_table_convert((const double*)tb.f64.p, (float2*)tb.f32.p, (float4*)tb.f4.p, n_steps,
                                      (int)n_nodes, c.stream))
         return e;
-    c.table_steps = n_steps;
-    c.table_nodes = n_nodes;
+    tb.steps = n_steps;
+    tb.nodes = n_nodes;
     bool in_clip = true;  // NaNs fail the comparison and keep the per-step clip
     for (size_t i = 0; i < n && in_clip; ++i) in_clip = (table[i] >= 1e-8) && (table[i] <= 10.0);
-    c.table_in_clip = in_clip;
+    tb.in_clip = in_clip;
+    return 0;
+}
+
+static int check_table_slot(int slot, uint32_t n_steps, int n_nodes) {
+    Context& c = ctx();
+    if (slot < 0 || slot >= kMaxTables || (slot > 0 && !c.tables[slot].used))
+        return set_error(OPTP_E_ARG, "sigma table handle %d is not live", slot);
+    const SigmaTableDev& tb = c.tables[slot];
+    if (tb.steps < n_steps || tb.nodes != (uint32_t)n_nodes || !tb.f64.p)
+        return set_error(OPTP_E_ARG, "no sigma table of %u x %d staged (optp_sigma_table_upload / _create)", n_steps,
+                         n_nodes);
     return 0;
 }
 
@@ -117,6 +130,39 @@ int optp_sigma_table_upload(const double* table, uint32_t n_steps, uint32_t n_no
     OPTP_CUDA(cudaSetDevice(ctx().device));
     if (int e = upload_table(table, n_steps, n_nodes)) return e;
     OPTP_CUDA(cudaStreamSynchronize(ctx().stream));
+    return 0;
+}
+
+int optp_sigma_table_create(const double* table, uint32_t n_steps, uint32_t n_nodes, int32_t* handle_out) {
+    OPTP_ENTER();
+    if (!handle_out) return set_error(OPTP_E_ARG, "null handle pointer");
+    Context& c = ctx();
+    OPTP_CUDA(cudaSetDevice(c.device));
+    int slot = 0;
+    for (int i = 1; i < kMaxTables && !slot; ++i)
+        if (!c.tables[i].used) slot = i;
+    if (!slot) return set_error(OPTP_E_TOO_LARGE, "all %d sigma table handles are in use", kMaxTables - 1);
+    if (int e = upload_table(table, n_steps, n_nodes, slot)) return e;
+    OPTP_CUDA(cudaStreamSynchronize(c.stream));
+    c.tables[slot].used = true;
+    *handle_out = slot;
+    return 0;
+}
+
+int optp_sigma_table_destroy(int32_t handle) {
+    OPTP_ENTER();
+    Context& c = ctx();
+    if (handle < 1 || handle >= kMaxTables || !c.tables[handle].used)
+        return set_error(OPTP_E_ARG, "sigma table handle %d is not live", (int)handle);
+    OPTP_CUDA(cudaSetDevice(c.device));
+    OPTP_CUDA(cudaStreamSynchronize(c.stream));
+    SigmaTableDev& tb = c.tables[handle];
+    for (Arena* a : {&tb.f64, &tb.f32, &tb.f4}) {
+        if (a->p) cudaFree(a->p);
+        a->p = nullptr;
+        a->cap = 0;
+    }
+    tb = SigmaTableDev();
     return 0;
 }
 
@@ -180,28 +226,33 @@ int optp_mc_terminal(double S0, double K, double T, double r, double q, double s
 }
 
 // ------------------------------------------------------------------ fused paths + payoffs
-int optp_mc_path_dev(const optp_process* proc, const optp_payoff* payoffs, uint32_t n_payoffs,
-                     uint32_t n_steps, uint64_t n_base, int antithetic, int mode, uint64_t seed,
-                     uint64_t path_offset, const double* z_dev, double* payoff_out_dev,
-                     double* terminal_out_dev, double* stats_dev, void* stream) {
-    OPTP_ENTER();
+static int mc_path_dev_slot(const optp_process* proc, const optp_payoff* payoffs, uint32_t n_payoffs,
+                            uint32_t n_steps, uint64_t n_base, int antithetic, int mode, uint64_t seed,
+                            uint64_t path_offset, const double* z_dev, double* payoff_out_dev,
+                            double* terminal_out_dev, double* stats_dev, void* stream, int table_slot) {
     if (int e = check_process(proc, n_steps, n_base)) return e;
     if (int e = check_payoffs(payoffs, n_payoffs)) return e;
     if (!stats_dev) return set_error(OPTP_E_ARG, "null stats pointer");
     if (mode == OPTP_MODE_FP64_HOSTZ && !z_dev)
         return set_error(OPTP_E_ARG, "HOSTZ mode needs the normal draws");
-    Context& c = ctx();
-    if (is_lv(proc->kind) &&
-        (c.table_steps < n_steps || c.table_nodes != (uint32_t)proc->n_nodes || !c.table_f64.p))
-        return set_error(OPTP_E_ARG, "no sigma table of %u x %d staged (optp_sigma_table_upload)",
-                         n_steps, proc->n_nodes);
+    if (is_lv(proc->kind))
+        if (int e = check_table_slot(table_slot, n_steps, proc->n_nodes)) return e;
     PathArgs a;
-    fill_args(a, proc, payoffs, n_payoffs, n_steps, n_base, antithetic, mode, seed, path_offset);
+    fill_args(a, proc, payoffs, n_payoffs, n_steps, n_base, antithetic, mode, seed, path_offset, table_slot);
     a.z = z_dev;
     a.payoff_out = payoff_out_dev;
     a.terminal_out = terminal_out_dev;
     a.stats = stats_dev;
     return dispatch_path(a, mode, (cudaStream_t)stream);
+}
+
+int optp_mc_path_dev(const optp_process* proc, const optp_payoff* payoffs, uint32_t n_payoffs,
+                     uint32_t n_steps, uint64_t n_base, int antithetic, int mode, uint64_t seed,
+                     uint64_t path_offset, const double* z_dev, double* payoff_out_dev,
+                     double* terminal_out_dev, double* stats_dev, void* stream) {
+    OPTP_ENTER();
+    return mc_path_dev_slot(proc, payoffs, n_payoffs, n_steps, n_base, antithetic, mode, seed, path_offset, z_dev,
+                            payoff_out_dev, terminal_out_dev, stats_dev, stream, 0);
 }
 
 int optp_mc_path(const optp_process* proc, const optp_payoff* payoffs, uint32_t n_payoffs,
@@ -271,9 +322,12 @@ int optp_mc_book(const optp_book_item* items, uint64_t n_items, const optp_payof
                 return set_error(OPTP_E_ARG, "item %llu: a book has no host normals", (unsigned long long)i);
             n_blocks += 1;
         } else {
-            if (is_lv(it.proc.kind))
-                return set_error(OPTP_E_KIND, "item %llu: local-vol processes are not accepted in a book",
-                                 (unsigned long long)i);
+            if (is_lv(it.proc.kind)) {  // local-vol items name a staged table (optp_sigma_table_create)
+                if (it.table_handle < 1)
+                    return set_error(OPTP_E_ARG, "item %llu: a local-vol item needs a table handle (optp_sigma_table_create)",
+                                     (unsigned long long)i);
+                if (int e = check_table_slot(it.table_handle, it.n_steps, it.proc.n_nodes)) return e;
+            }
             if (it.mode == OPTP_MODE_FP64_HOSTZ)
                 return set_error(OPTP_E_ARG, "item %llu: a book has no host normals", (unsigned long long)i);
             if (int e = check_process(&it.proc, it.n_steps, it.n_base)) return e;
@@ -297,9 +351,9 @@ int optp_mc_book(const optp_book_item* items, uint64_t n_items, const optp_payof
                 return e;
             blk += 1;
         } else {
-            if (int e = optp_mc_path_dev(&it.proc, payoffs + it.first_payoff, (uint32_t)it.n_payoffs,
-                                         it.n_steps, it.n_base, it.antithetic, it.mode, it.seed,
-                                         it.path_offset, nullptr, nullptr, nullptr, dst, c.stream))
+            if (int e = mc_path_dev_slot(&it.proc, payoffs + it.first_payoff, (uint32_t)it.n_payoffs, it.n_steps,
+                                         it.n_base, it.antithetic, it.mode, it.seed, it.path_offset, nullptr, nullptr,
+                                         nullptr, dst, c.stream, is_lv(it.proc.kind) ? it.table_handle : 0))
                 return e;
             blk += (uint64_t)it.n_payoffs;
         }

@@ -27,10 +27,12 @@ struct PathArgs {
     const float2* table32;  // (value, next-value minus value) per node, n_steps rows
     const float4* table4;   // window nodes (v_j, s_j, s_{j+1}, s_{j-1}), n_nodes + 4 per row
     const double* table64;  // n_steps x n_nodes
+    int table_in_clip;      // every node of the table lies in the reference's clip range [1e-8, 10]
     unsigned int n_steps;
     unsigned long long n_base;
     int anti;
     int use_philox;
+    int rng_mode;  // RNG_* (optp_common.cuh); honoured by the fp32 GBM path kernel only
     unsigned long long seed, path_offset;
     const double* z;  // device, n_streams x n_steps x n_base (HOSTZ mode)
     int n_pay;

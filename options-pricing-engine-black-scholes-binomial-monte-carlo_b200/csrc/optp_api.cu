@@ -7,6 +7,8 @@
 
 namespace optp {
 
+void comm_release();  // comm.cu
+
 static Context g_ctx;
 static thread_local char g_err[512] = "";
 
@@ -93,9 +95,15 @@ static int init_resources(Context& c, int device) {
     OPTP_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     OPTP_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10)
+    // the library carries sm_100a SASS only (arch-specific, no forward-compatible PTX): any other part --
+    // sm_103, sm_12x included -- would pass init and fail at the first launch with "no kernel image"
+    if (prop.major != 10 || prop.minor != 0)
         return set_error(OPTP_E_ARG, "device %d is sm_%d%d; this library is built for sm_100a only",
                          device, prop.major, prop.minor);
+    // grids are sized as n_sm x (<= 16 resident CTAs) and must fit the block-partial buffer
+    if (prop.multiProcessorCount * 16 > kMaxBlocks)
+        return set_error(OPTP_E_TOO_LARGE, "device %d has %d SMs; the reduction scratch is sized for %d",
+                         device, prop.multiProcessorCount, kMaxBlocks / 16);
     c.device = device;
     c.n_sm = prop.multiProcessorCount;
     OPTP_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
@@ -113,9 +121,11 @@ static void release_resources(Context& c) {
     arena_free(c.in1);
     arena_free(c.out0);
     arena_free(c.out1);
-    arena_free(c.table_f32);
-    arena_free(c.table_f4);
-    arena_free(c.table_f64);
+    for (int i = 0; i < kMaxTables; ++i) {
+        arena_free(c.tables[i].f32);
+        arena_free(c.tables[i].f4);
+        arena_free(c.tables[i].f64);
+    }
     arena_free(c.work);
     arena_free(c.cta_scratch);
     if (c.pin_in.p) cudaFreeHost(c.pin_in.p);
@@ -125,6 +135,7 @@ static void release_resources(Context& c) {
     if (c.partials) cudaFree(c.partials);
     if (c.ticket) cudaFree(c.ticket);
     if (c.stats_dev) cudaFree(c.stats_dev);
+    if (c.crr_op_count) cudaFree(c.crr_op_count);
     if (c.stats_host) cudaFreeHost(c.stats_host);
     if (c.stream) cudaStreamDestroy(c.stream);
     if (c.stream2) cudaStreamDestroy(c.stream2);
@@ -168,6 +179,7 @@ int optp_shutdown(void) {
     if (c.stream2) cudaStreamSynchronize(c.stream2);
     if (c.stream3) cudaStreamSynchronize(c.stream3);
     if (c.stream4) cudaStreamSynchronize(c.stream4);
+    comm_release();
     release_resources(c);
     return 0;
 }
@@ -204,11 +216,40 @@ int optp_set_option(const char* key, long value) {
         g_ctx.crr_no_euro_sum = (value == 0);
         return 0;
     }
+    if (!strcmp(key, "crr_count_ops")) {  // 1 = count (and reset the counters), 0 = production kernels
+        g_ctx.crr_count_ops = (value != 0);
+        if (g_ctx.crr_op_count) {
+            OPTP_CUDA(cudaSetDevice(g_ctx.device));
+            OPTP_CUDA(cudaDeviceSynchronize());
+            OPTP_CUDA(cudaMemset(g_ctx.crr_op_count, 0, 2 * sizeof(unsigned long long)));
+        }
+        return 0;
+    }
+    if (!strcmp(key, "rng_mode")) {
+        if (value < 0 || value >= RNG_MODES) return set_error(OPTP_E_ARG, "rng_mode must be 0, 1 or 2");
+        g_ctx.rng_mode = (int)value;
+        return 0;
+    }
     if (!strcmp(key, "crr_band_only")) {
         g_ctx.crr_band_only = (value != 0);
         return 0;
     }
     return set_error(OPTP_E_ARG, "unknown option '%s'", key);
+}
+
+int optp_get_counter(const char* key, uint64_t* value_out) {
+    ApiLock lock;
+    if (!key || !value_out) return set_error(OPTP_E_ARG, "null pointer argument");
+    const bool fp64 = !strcmp(key, "crr_fp64_lane_ops"), nodes = !strcmp(key, "crr_node_updates");
+    if (!fp64 && !nodes) return set_error(OPTP_E_ARG, "unknown counter '%s'", key);
+    *value_out = 0;
+    if (!g_ctx.ready || !g_ctx.crr_op_count) return 0;
+    OPTP_CUDA(cudaSetDevice(g_ctx.device));
+    OPTP_CUDA(cudaDeviceSynchronize());
+    unsigned long long v[2] = {0, 0};
+    OPTP_CUDA(cudaMemcpy(v, g_ctx.crr_op_count, sizeof(v), cudaMemcpyDeviceToHost));
+    *value_out = fp64 ? v[0] : v[1];
+    return 0;
 }
 
 int optp_host_alloc(void** p, uint64_t bytes) {

@@ -15,6 +15,15 @@ struct Arena {          // grow-only device scratch
     size_t cap = 0;
 };
 
+// A sigma(S,t) table staged in HBM: the fp64 values, the (value, slope) fp32 pairs and the window nodes.
+struct SigmaTableDev {
+    Arena f64, f32, f4;
+    uint32_t steps = 0, nodes = 0;
+    bool in_clip = false;  // every node lies in [1e-8, 10] (processes.py:361-362): no per-step clip needed
+    bool used = false;     // slots 1.. are handed out by optp_sigma_table_create
+};
+constexpr int kMaxTables = 64;
+
 struct Context {
     int device = -1;
     bool ready = false;
@@ -29,12 +38,12 @@ struct Context {
     unsigned int* ticket = nullptr;
     double* stats_dev = nullptr;  // kMaxPayoffs * OPTP_NSTATS
     double* stats_host = nullptr; // pinned mirror
-    Arena in0, in1, out0, out1, table_f32, table_f64, table_f4;
+    Arena in0, in1, out0, out1;
+    // slot 0: the table of optp_sigma_table_upload / optp_dupire_table / optp_mc_path; slots 1..: handles
+    SigmaTableDev tables[kMaxTables];
     Arena work;  // work lists of the two-zone CRR kernel (crr_batch.cu)
     Arena cta_scratch;  // level arrays of the one-option-per-CTA CRR kernel when N > 9685
     Arena pin_in, pin_out;  // PINNED host staging of small CRR batches (one copy in, one copy out)
-    uint32_t table_steps = 0, table_nodes = 0;
-    bool table_in_clip = false;  // every node of the staged sigma table lies in [1e-8, 10] (processes.py:361-362)
     uint64_t launches = 0;
     bool lv_direct = false;      // "lv_direct" = 1: window nodes gathered from global/L1, no smem staging
     bool lv_no_window = false;   // "lv_window" = 0: three-lookup (value, slope) path for LV Milstein
@@ -43,6 +52,9 @@ struct Context {
     bool crr_no_euro_sum = false;  // "crr_euro_sum" = 0: European trees by backward induction for every N
     int crr_band_kernel = 2;   // 2 = two-zone banded kernel (default), 1 = single-zone banded kernel
     int crr_zone_group = 0;    // two-zone kernel: options per warp (1, 2, 4); 0 = by batch size
+    bool crr_count_ops = false;  // "crr_count_ops": the two-zone kernel counts its executed level-loop work
+    unsigned long long* crr_op_count = nullptr;  // device {FP64 lane-instructions, node updates}
+    int rng_mode = 0;          // "rng_mode": generator mode of the fp32 GBM path kernel (RNG_*), default Philox4x32-10 x 4 normals
 };
 
 constexpr int kMaxEvents = 384;
@@ -109,16 +121,36 @@ __host__ __device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1
     c3 = l0;
 }
 
-__host__ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
-                                                        uint32_t c3, uint32_t k0, uint32_t k1) {
+template <int ROUNDS>
+__host__ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                     uint32_t k0, uint32_t k1) {
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
+    for (int i = 0; i < ROUNDS; ++i) {
         philox_round(c0, c1, c2, c3, k0, k1);
         k0 += 0x9E3779B9u;
         k1 += 0xBB67AE85u;
     }
     return make_uint4(c0, c1, c2, c3);
 }
+
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                        uint32_t c3, uint32_t k0, uint32_t k1) {
+    return philox4x32<10>(c0, c1, c2, c3, k0, k1);
+}
+
+// Opt-in generator modes of the fused GBM kernel (optp_set_option("rng_mode", m)); the default is 0 and
+// every parity statement in DESIGN.md is made for it.
+//   0  Philox4x32-10, two Box-Muller pairs of (32-bit radius, 32-bit angle) per call  -> 4 normals
+//   1  Philox4x32-7 (the smallest round count Salmon et al. report as Crush-resistant), same mapping
+//   2  Philox4x32-10, THREE Box-Muller pairs per call: radii from the top 26 bits of words 0..2, angles
+//      from the two halves of word 3 (16 bits each) and from the low 6 bits of words 0..2 (18 bits)
+//      -> 6 normals; tails reach 6.1 sigma instead of 6.7, 65 536 / 262 144 directions per pair
+enum : int { RNG_PHILOX10 = 0, RNG_PHILOX7 = 1, RNG_PHILOX10_X6 = 2, RNG_MODES = 3 };
+template <int RNG>
+struct RngTraits {
+    static constexpr int rounds = (RNG == RNG_PHILOX7) ? 7 : 10;
+    static constexpr int normals = (RNG == RNG_PHILOX10_X6) ? 6 : 4;
+};
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------ uniforms / normals
@@ -199,6 +231,40 @@ __device__ __forceinline__ void normals_from_words_scaled(const uint4& w, float 
 __device__ __forceinline__ void philox_normals4(uint64_t seed, uint64_t path, uint32_t block,
                                                 uint32_t stream, float z[4]) {
     normals_from_words(philox_words(seed, path, block, stream), z);
+}
+
+// The same two halves for the generator modes above: words of one call, and the 4 (or 6) normals they map
+// to, scaled by s when the caller passes c = -2 ln2 * s^2 (c = -2 ln2 for plain N(0,1)).
+template <int RNG>
+__device__ __forceinline__ uint4 philox_words_m(uint64_t seed, uint64_t path, uint32_t block, uint32_t stream) {
+    return philox4x32<RngTraits<RNG>::rounds>((uint32_t)path, (uint32_t)(path >> 32), block, stream,
+                                              (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+__device__ __forceinline__ void bm_pair(float u, float a, float c, float& z0, float& z1) {
+    const float r = mufu_sqrt(c * mufu_lg2(u));
+    z0 = r * mufu_cos(a);
+    z1 = r * mufu_sin(a);
+}
+
+template <int RNG>
+__device__ __forceinline__ void normals_from_words_m(const uint4& w, float c, float* z) {
+    if (RNG == RNG_PHILOX10_X6) {
+        // radius: u = ((w >> 6) + 1/2) 2^-26 in (0, 1); angle: (k + 1/2) 2 pi / 2^bits
+        const float ux = fmaf(__uint2float_rn(w.x & 0xFFFFFFC0u), 2.3283064365386963e-10f, 7.450580596923828e-9f);
+        const float uy = fmaf(__uint2float_rn(w.y & 0xFFFFFFC0u), 2.3283064365386963e-10f, 7.450580596923828e-9f);
+        const float uz = fmaf(__uint2float_rn(w.z & 0xFFFFFFC0u), 2.3283064365386963e-10f, 7.450580596923828e-9f);
+        const float a0 = fmaf(__uint2float_rn(w.w >> 16), 9.587379924285257e-5f, 4.7936899621426287e-5f);
+        const float a1 = fmaf(__uint2float_rn(w.w & 0xFFFFu), 9.587379924285257e-5f, 4.7936899621426287e-5f);
+        const uint32_t k2 = ((w.x & 63u) << 12) | ((w.y & 63u) << 6) | (w.z & 63u);
+        const float a2 = fmaf(__uint2float_rn(k2), 2.3968449810713143e-5f, 1.1984224905356572e-5f);
+        bm_pair(ux, a0, c, z[0], z[1]);
+        bm_pair(uy, a1, c, z[2], z[3]);
+        bm_pair(uz, a2, c, z[4], z[5]);
+    } else {
+        box_muller_scaled(w.x, w.y, c, z[0], z[1]);
+        box_muller_scaled(w.z, w.w, c, z[2], z[3]);
+    }
 }
 
 // Poisson(mu) count by CDF inversion from one 32-bit word (mu = lambda*dt is small: the loop

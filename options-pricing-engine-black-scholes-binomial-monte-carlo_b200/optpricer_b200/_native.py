@@ -13,7 +13,7 @@ import threading
 import numpy as np
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "liboptp_b200.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 NSTATS = 8
 MAX_PAYOFFS = 16
 
@@ -26,10 +26,14 @@ MODE_FP32_PHILOX, MODE_FP64_PHILOX, MODE_FP64_HOSTZ = 0, 1, 2
 
 EXPORTS = (
     "optp_abi_version", "optp_init", "optp_shutdown", "optp_last_error", "optp_device_count",
-    "optp_launch_count", "optp_set_option", "optp_host_alloc", "optp_host_free",
+    "optp_launch_count", "optp_set_option", "optp_get_counter", "optp_host_alloc", "optp_host_free",
     "optp_mc_terminal", "optp_mc_terminal_dev", "optp_mc_path", "optp_mc_path_dev", "optp_mc_book",
     "optp_sigma_table_upload", "optp_dupire_table", "optp_paths", "optp_payoff_from_paths",
     "optp_crr_batch", "optp_crr_batch_dev", "optp_microbench",
+    "optp_sigma_table_create", "optp_sigma_table_destroy",
+    "optp_comm_unique_id", "optp_comm_init", "optp_comm_destroy", "optp_comm_info",
+    "optp_allreduce_stats", "optp_allreduce_stats_dev",
+    "optp_philox4x32_10", "optp_normal_stats",
 )
 
 
@@ -58,7 +62,7 @@ class OptpBookItem(C.Structure):
                 ("first_payoff", C.c_uint32), ("n_steps", C.c_uint32),
                 ("n_base", C.c_uint64), ("seed", C.c_uint64), ("path_offset", C.c_uint64),
                 ("antithetic", C.c_int32), ("mode", C.c_int32),
-                ("is_call", C.c_int32), ("reserved", C.c_int32),
+                ("is_call", C.c_int32), ("table_handle", C.c_int32),
                 ("K", C.c_double), ("proc", OptpProcess)]
 
 
@@ -77,6 +81,7 @@ def _declare(lib):
     lib.optp_last_error.restype = C.c_char_p
     lib.optp_launch_count.restype = u64
     lib.optp_set_option.argtypes = [C.c_char_p, C.c_long]
+    lib.optp_get_counter.argtypes = [C.c_char_p, C.POINTER(u64)]
     lib.optp_host_alloc.argtypes = [C.POINTER(vp), u64]
     lib.optp_host_free.argtypes = [vp]
     term = [d, d, d, d, d, d, i, u64, i, i, i, u64, u64, vp, vp]
@@ -94,6 +99,15 @@ def _declare(lib):
     lib.optp_crr_batch.argtypes = crr
     lib.optp_crr_batch_dev.argtypes = crr + [vp]
     lib.optp_microbench.argtypes = [i, _dp, _dp]
+    lib.optp_sigma_table_create.argtypes = [vp, u32, u32, C.POINTER(C.c_int32)]
+    lib.optp_sigma_table_destroy.argtypes = [C.c_int32]
+    lib.optp_comm_unique_id.argtypes = [C.c_char_p]
+    lib.optp_comm_init.argtypes = [i, i, C.c_char_p]
+    lib.optp_comm_info.argtypes = [C.POINTER(i), C.POINTER(i)]
+    lib.optp_allreduce_stats.argtypes = [vp, u64]
+    lib.optp_allreduce_stats_dev.argtypes = [vp, u64, vp]
+    lib.optp_philox4x32_10.argtypes = [C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
+    lib.optp_normal_stats.argtypes = [u64, u64, u64, u32, i, _dp]
     for name in EXPORTS:
         if name not in ("optp_abi_version", "optp_last_error", "optp_launch_count"):
             getattr(lib, name).restype = i
@@ -158,6 +172,12 @@ def set_option(key, value):
     check(load().optp_set_option(key.encode(), int(value)), "optp_set_option")
 
 
+def get_counter(key):
+    v = C.c_uint64()
+    check(load().optp_get_counter(key.encode(), C.byref(v)), "optp_get_counter")
+    return int(v.value)
+
+
 def launch_count():
     return int(load().optp_launch_count())
 
@@ -168,6 +188,25 @@ def ptr(a):
 
 def f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def philox4x32_10(ctr, key):
+    """The library's Philox4x32-10 on the host (known-answer tests); needs no device."""
+    lib = load()
+    c = (C.c_uint32 * 4)(*[int(x) & 0xFFFFFFFF for x in ctr])
+    k = (C.c_uint32 * 2)(*[int(x) & 0xFFFFFFFF for x in key])
+    out = (C.c_uint32 * 4)()
+    check(lib.optp_philox4x32_10(c, k, out), "optp_philox4x32_10")
+    return tuple(int(x) for x in out)
+
+
+def normal_stats(seed, n_paths, n_blocks, *, rng_mode=0, path_offset=0):
+    """Moments, tail counts and pair products of the device normals (see include/optp_b200.h)."""
+    lib = init()
+    out = (C.c_double * 16)()
+    check(lib.optp_normal_stats(int(seed), int(path_offset), int(n_paths), int(n_blocks), int(rng_mode), out),
+          "optp_normal_stats")
+    return np.array(out[:], dtype=np.float64)
 
 
 def microbench(which):

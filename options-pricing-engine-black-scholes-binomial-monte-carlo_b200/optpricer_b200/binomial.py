@@ -70,6 +70,8 @@ def crr(opt, kind=CALL, N=500, *, american=False):
     lib = nv.init()
     nv.check(lib.optp_crr_batch(*[C.c_void_p(base + 8 * i) for i in range(6)], nv.ptr(call), 1, int(N),
                                 1 if american else 0, C.c_void_p(base + 48), nv.ptr(status)), "optp_crr_batch")
+    if status[0] != 0:   # the device's own p test disagreed with the host's (binomial.py:16-17): never return its NaN
+        raise ValueError(_P_ERROR)
     return float(cols[6])
 
 

@@ -10,6 +10,10 @@ american.  Methods on the hot path:
             item; rows that share (S0, r, q, sigma, T, n_steps, n_paths) -- the script seeds every
             row with seed=1, i.e. common random numbers -- share ONE simulated path set and are
             evaluated as several payoffs of the same launch (up to 16 per launch)
+            a row may carry `sigma_table` (a processes.SigmaTable; Python rows only): it is then simulated
+            with milstein_local_vol_paths(..., seed=1) on that table instead of gbm_paths -- the desk
+            workflow's local-vol barrier + vanilla legs (scripts/desk_workflow_localvol_barrier.py:136-148)
+            and its bumped-surface reprices batch into the same optp_mc_book call, one table handle each
 All Monte Carlo items of the book are launched back to back by optp_mc_book and their statistics
 return in one device-to-host copy; with a torch.distributed process group the items (or, for a book of
 few items, the base paths of every item) are sharded over the ranks and ONE all-reduce sums the whole
@@ -76,9 +80,17 @@ def plan_book(rows, *, tree_steps=500, mc_paths=100_000, exotic_steps=500, exoti
     holds the host-priced / failed rows and the rest are filled in by price_book."""
     results = [None] * len(rows)
     crr_groups = {}      # american flag -> list of (row index, S0, K, T, r, q, sigma, is_call)
+    items = _plan_rows(rows, 0, len(rows), results, crr_groups, tree_steps=tree_steps, mc_paths=mc_paths,
+                       exotic_steps=exotic_steps, exotic_paths=exotic_paths, seed=seed)
+    return results, crr_groups, items
+
+
+def _plan_rows(rows, lo, hi, results, crr_groups, *, tree_steps, mc_paths, exotic_steps, exotic_paths, seed):
+    """plan_book for rows[lo:hi] (row indices stay global); returns the Monte Carlo items of the slice."""
     items = []           # dicts: kind "terminal" | "path", rows [(row index, payoff spec)], params
     path_groups = {}     # (S0, r, q, sigma, T, n_steps, n_paths) -> item (<= 16 payoffs each)
-    for i, row in enumerate(rows):
+    for i in range(lo, hi):
+        row = rows[i]
         rid = row.get("id", "")
         try:
             S0, K, T, r, sigma = (_f(row, k) for k in ("S0", "K", "T", "r", "sigma"))
@@ -101,11 +113,17 @@ def plan_book(rows, *, tree_steps=500, mc_paths=100_000, exotic_steps=500, exoti
                 if n_steps <= 0 or n_paths <= 0:
                     raise ValueError("n_steps and n_paths must be positive.")
                 spec = _exotic_spec(row, K, kind)
-                key = (S0, r, q, sigma, T, n_steps, n_paths)
+                table = row.get("sigma_table")
+                if table is not None and (table.table.shape[0] < n_steps
+                                          or abs(table.dt - T / n_steps) > 1e-12 * table.dt):
+                    raise ValueError("sigma_table does not match T / n_steps of the row")
+                row_seed = int(row["seed"]) if row.get("seed") not in (None, "") else seed   # (the script: always 1)
+                key = (S0, r, q, sigma if table is None else id(table), T, n_steps, n_paths, row_seed)
                 it = path_groups.get(key)
                 if it is None or len(it["rows"]) >= nv.MAX_PAYOFFS:
                     it = dict(kind="path", rows=[], S0=S0, r=r, q=q, sigma=sigma, T=T, n_steps=n_steps,
-                              n_base=n_paths, seed=seed)
+                              n_base=n_paths, seed=row_seed, table=table,
+                              dS_bump=float(row.get("dS_bump", 0.01)))
                     path_groups[key] = it
                     items.append(it)
                 it["rows"].append((i, spec))
@@ -113,10 +131,10 @@ def plan_book(rows, *, tree_steps=500, mc_paths=100_000, exotic_steps=500, exoti
                 raise ValueError(f"Unknown method: {method!r}")
         except Exception as e:  # per-row failure, as scripts/price_book.py:139-145
             results[i] = {"id": rid, "price": None, "error": str(e)}
-    return results, crr_groups, items
+    return items
 
 
-def shard_items(items, rank, world):
+def shard_items(items, rank, world, load=None):
     """This rank's share of every item as a list of base-path ranges [(lo, hi), ...], one per item.
 
     A book with many items (>= 4 per rank) is sharded BY ITEM: each item runs whole on one rank, so a rank
@@ -124,7 +142,10 @@ def shard_items(items, rank, world):
     are dealt out longest-first to the least loaded rank (cost = base paths x steps), identically on every
     rank.  A book with few items is sharded BY PATHS (every item on every rank, disjoint ranges of its base
     paths).  Either way the statistics are additive, so ONE all-reduce over the (n_blocks, 8) array -- blocks
-    a rank did not touch stay zero -- gives the whole book (monte_carlo.py:67-74)."""
+    a rank did not touch stay zero -- gives the whole book (monte_carlo.py:67-74).
+    `load` (a list of `world` running totals, updated in place) carries the ranks' loads from one slice of a
+    book to the next (price_book plans and launches a large book slice by slice)."""
+    import heapq
     from .distributed import shard_range
     if world <= 1:
         return [(0, it["n_base"]) for it in items]
@@ -132,19 +153,24 @@ def shard_items(items, rank, world):
         return [shard_range(it["n_base"], rank, world) for it in items]
     cost = [it["n_base"] * (1 if it["kind"] == "terminal" else it["n_steps"]) for it in items]
     order = sorted(range(len(items)), key=lambda i: (-cost[i], i))
-    load = [0] * world
+    if load is None:
+        load = [0] * world
+    heap = [(load[k], k) for k in range(world)]
+    heapq.heapify(heap)
     owner = [0] * len(items)
     for i in order:
-        r = min(range(world), key=lambda k: (load[k], k))
+        ld, r = heapq.heappop(heap)      # least loaded rank, lowest rank on ties
         owner[i] = r
-        load[r] += cost[i]
+        heapq.heappush(heap, (ld + cost[i], r))
+    for ld, r in heap:
+        load[r] = ld
     return [(0, it["n_base"]) if owner[i] == rank else (0, 0) for i, it in enumerate(items)]
 
 
-def book_stats(items, *, mode="fp32", rank=0, world=1):
+def book_stats(items, *, mode="fp32", rank=0, world=1, load=None):
     """Run this rank's share (shard_items) of all Monte Carlo items through optp_mc_book.
     Returns the (n_blocks, 8) statistics array (item order, payoff order inside an item)."""
-    shards = shard_items(items, rank, world)
+    shards = shard_items(items, rank, world, load)
     n_blocks = sum(len(it["rows"]) for it in items)
     stats = np.zeros((n_blocks, nv.NSTATS), dtype=np.float64)
     if not items:
@@ -153,6 +179,15 @@ def book_stats(items, *, mode="fp32", rank=0, world=1):
     arr = (nv.OptpBookItem * len(items))()
     specs = []
     live = 0
+    handles = {}   # id(SigmaTable) -> device table handle, created once per distinct table of this rank's items
+    try:
+        return _book_stats_run(lib, items, shards, arr, specs, live, handles, stats, mode)
+    finally:
+        for h in handles.values():
+            lib.optp_sigma_table_destroy(h)
+
+
+def _book_stats_run(lib, items, shards, arr, specs, live, handles, stats, mode):
     for it, (lo, hi) in zip(items, shards):
         a = arr[live]
         if hi == lo:
@@ -165,6 +200,16 @@ def book_stats(items, *, mode="fp32", rank=0, world=1):
         a.antithetic, a.mode = 1, mc._MODES[mode]
         a.proc.kind = nv.PROC_GBM
         a.proc.S0, a.proc.r, a.proc.q, a.proc.T, a.proc.sigma = it["S0"], it["r"], it["q"], it["T"], it["sigma"]
+        tb = it.get("table")
+        if tb is not None:
+            if id(tb) not in handles:
+                h = C.c_int32()
+                nv.check(lib.optp_sigma_table_create(nv.ptr(tb.table), tb.table.shape[0], tb.table.shape[1],
+                                                     C.byref(h)), "optp_sigma_table_create")
+                handles[id(tb)] = h.value
+            a.proc.kind = nv.PROC_LV_MILSTEIN
+            a.proc.n_nodes, a.proc.x0, a.proc.h, a.proc.dS_bump = tb.table.shape[1], tb.x0, tb.h, it["dS_bump"]
+            a.table_handle = handles[id(tb)]
         if it["kind"] == "terminal":
             a.K, a.is_call, a.n_steps, a.n_payoffs, a.first_payoff = it["K"], it["is_call"], 1, 1, 0
         else:
@@ -188,43 +233,91 @@ def book_stats(items, *, mode="fp32", rank=0, world=1):
     return stats
 
 
+def estimate_rows(items, stats, control_variate=True):
+    """(price, stderr) of every row of `items` from the (n_blocks, 8) statistics, vectorised: terminal rows with
+    the euro_price_mc estimator (monte_carlo.py:142-167: ddof=0, control variate Y = e^{-rT} S_T), path rows with
+    exotics._price_from_payoff's (exotics.py:22-27: ddof=1).  Same formulas, same operation order as
+    monte_carlo.estimator / exotics.estimate, evaluated on arrays.  Returns (row indices, prices, stderrs)."""
+    idx, term, ey = [], [], []
+    for it in items:
+        t = it["kind"] == "terminal"
+        e = it["S0"] * math.exp(-it["q"] * it["T"]) if t else 0.0
+        for (i, _) in it["rows"]:
+            idx.append(i)
+            term.append(t)
+            ey.append(e)
+    n, sx, sxx, sy, syy, sxy = (stats[:, k] for k in range(6))
+    term = np.array(term, dtype=bool)
+    ey = np.array(ey, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        mean = sx / n
+        # path rows: ddof = 1
+        var1 = np.maximum(0.0, (sxx - n * mean * mean) / (n - 1.0))
+        p_price, p_se = mean, np.where(n > 1, np.sqrt(var1) / np.sqrt(n), 0.0)
+        # terminal rows: ddof = 0 (+ control variate)
+        varX = np.maximum(0.0, sxx / n - mean * mean)
+        if control_variate:
+            meanY = sy / n
+            varY = np.maximum(0.0, syy / n - meanY * meanY)
+            cov = (sxy / n) - mean * meanY
+            c_hat = np.where(varY == 0.0, 0.0, cov / np.where(varY == 0.0, 1.0, varY))
+            t_price = mean - c_hat * (meanY - ey)
+            var_cv = varX - 2.0 * c_hat * cov + (c_hat * c_hat) * varY
+            t_se = np.sqrt(np.maximum(0.0, var_cv) / n)
+        else:
+            t_price, t_se = mean, np.sqrt(np.maximum(0.0, varX) / n)
+    price = np.where(term, t_price, p_price)
+    se = np.where(term, t_se, p_se)
+    empty = n <= 0
+    price = np.where(empty, np.nan, price)
+    se = np.where(empty, np.nan, se)
+    return idx, price, se
+
+
 def price_book(rows, *, tree_steps=500, mc_paths=100_000, exotic_steps=500, exotic_paths=100_000, seed=1,
-               mode="fp32", control_variate=True, sharded=None):
+               mode="fp32", control_variate=True, sharded=None, slice_rows=1024):
     """Price a portfolio (list of dict rows).  Returns one result dict per row, in row order:
     {"id", "price", "stderr"} or {"id", "price": None, "error"}.
 
     `sharded`: None = shard over the default torch.distributed process group when one is initialised.
-    `control_variate` applies to the "mc" rows only (euro_price_mc's default, monte_carlo.py:84)."""
+    `control_variate` applies to the "mc" rows only (euro_price_mc's default, monte_carlo.py:84).
+    A book of more than 2*slice_rows rows is planned and launched slice by slice: a worker thread runs the
+    (blocking, GIL-free) optp_mc_book call of slice k while this thread parses slice k+1, so the device
+    starts after the first slice is parsed and the host work hides behind the kernels."""
+    import concurrent.futures as cf
     from . import distributed as dd
     from .binomial import crr_batch
-    results, crr_groups, items = plan_book(rows, tree_steps=tree_steps, mc_paths=mc_paths,
-                                           exotic_steps=exotic_steps, exotic_paths=exotic_paths, seed=seed)
     rank, world = dd.world() if sharded in (None, True) else (0, 1)
-    # --- trees: one batch per american flag -----------------------------------------------------
-    for american, group in crr_groups.items():
-        cols = [np.array([g[c] for g in group], dtype=np.float64) for c in range(1, 8)]
-        if world > 1:
-            prices = dd.crr_batch(*cols, tree_steps, american=american)
-        else:
-            prices = crr_batch(*cols, tree_steps, american=american)
-        for g, p in zip(group, prices):
-            results[g[0]] = {"id": rows[g[0]].get("id", ""), "price": float(p), "stderr": None}
-    # --- Monte Carlo: every item in one optp_mc_book call, one all-reduce for the whole book -----
-    if items:
-        stats = book_stats(items, mode=mode, rank=rank, world=world)
-        if world > 1:
-            stats = dd.allreduce_sum(stats)
-        blk = 0
-        for it in items:
-            for (i, spec) in it["rows"]:
-                s = stats[blk]
-                blk += 1
-                if it["kind"] == "terminal":
-                    price, se = mc.estimator((int(s[0]), *s[1:6]), S0=it["S0"], q=it["q"], T=it["T"],
-                                             control_variate=control_variate)
-                else:
-                    price, se = ex.estimate(s)
-                results[i] = {"id": rows[i].get("id", ""), "price": price, "stderr": se}
+    n_rows = len(rows)
+    results = [None] * n_rows
+    crr_groups = {}
+    step = n_rows if n_rows <= 2 * slice_rows else int(slice_rows)
+    load = [0] * world
+    slices = []      # (items, future of the slice's statistics)
+    with cf.ThreadPoolExecutor(max_workers=1) as pool:
+        for lo in range(0, n_rows, max(step, 1)):
+            items = _plan_rows(rows, lo, min(lo + step, n_rows), results, crr_groups, tree_steps=tree_steps,
+                               mc_paths=mc_paths, exotic_steps=exotic_steps, exotic_paths=exotic_paths, seed=seed)
+            if items:
+                slices.append((items, pool.submit(book_stats, items, mode=mode, rank=rank, world=world, load=load)))
+        # --- trees: one batch per american flag (queues behind the slices on the device) ---------------
+        for american, group in crr_groups.items():
+            cols = [np.array([g[c] for g in group], dtype=np.float64) for c in range(1, 8)]
+            if world > 1:
+                prices = dd.crr_batch(*cols, tree_steps, american=american)
+            else:
+                prices = crr_batch(*cols, tree_steps, american=american)
+            for g, p in zip(group, prices):
+                results[g[0]] = {"id": rows[g[0]].get("id", ""), "price": float(p), "stderr": None}
+        # --- Monte Carlo: one all-reduce for the whole book, vectorised estimators ------------------------
+        if slices:
+            stats = np.concatenate([f.result() for _, f in slices], axis=0)
+            if world > 1:
+                stats = dd.allreduce_sum(stats)
+            all_items = [it for items, _ in slices for it in items]
+            idx, price, se = estimate_rows(all_items, stats, control_variate)
+            for i, p, e in zip(idx, price.tolist(), se.tolist()):
+                results[i] = {"id": rows[i].get("id", ""), "price": p, "stderr": e}
     return results
 
 

@@ -35,12 +35,45 @@ def shard_range(n, rank, size):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+_comm_world = 1   # size of the library's own NCCL communicator (optp_comm_init), 1 = none
+
+
+def init_comm():
+    """Create the library's NCCL communicator over the ranks of the default process group
+    (optp_comm_unique_id on rank 0 -> broadcast -> optp_comm_init everywhere).  After this the statistics
+    blocks are reduced by optp_allreduce_stats -- pinned staging, ncclAllReduce and the copy back inside ONE
+    C call -- instead of a numpy -> torch -> NCCL -> numpy round trip.  Idempotent; a no-op for a world of
+    one or a CPU (gloo) process group."""
+    global _comm_world
+    rank, size = world()
+    if size == 1 or _comm_world == size:
+        return _comm_world > 1
+    import ctypes as C
+    import torch.distributed as dist
+    if dist.get_backend() != "nccl":
+        return False
+    lib = nv.init()
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        nv.check(lib.optp_comm_unique_id(buf), "optp_comm_unique_id")
+    box = [bytes(buf.raw)]
+    dist.broadcast_object_list(box, src=0)
+    nv.check(lib.optp_comm_init(rank, size, box[0]), "optp_comm_init")
+    _comm_world = size
+    return True
+
+
 def allreduce_sum(block):
-    """Sum a float64 numpy block over all ranks (one collective for the whole block)."""
+    """Sum a float64 numpy block over all ranks (one collective for the whole block): through the C ABI
+    (optp_allreduce_stats) on the GPU box, through torch.distributed (gloo) in the CPU tests."""
     rank, size = world()
     block = np.ascontiguousarray(block, dtype=np.float64)
     if size == 1:
         return block
+    if init_comm():
+        out = block.copy()
+        nv.check(nv.load().optp_allreduce_stats(nv.ptr(out), out.size), "optp_allreduce_stats")
+        return out
     import torch
     import torch.distributed as dist
     t = torch.from_numpy(block.copy())

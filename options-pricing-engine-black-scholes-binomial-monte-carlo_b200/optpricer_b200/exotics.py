@@ -150,7 +150,27 @@ def path_stats(paths, specs, r, T, *, want_payoffs=False, want_terminal=False, n
     nv.check(lib.optp_mc_path(C.byref(p), pay, len(specs), paths.n_steps, nb, int(paths.antithetic),
                               paths.native_mode(), paths.seed, int(path_offset), nv.ptr(z), nv.ptr(pout),
                               nv.ptr(tout), nv.ptr(stats)), "optp_mc_path")
+    _warn_if_clamped(paths, stats)
     return stats, pout, tout
+
+
+CLAMP_WARN_FRACTION = 1e-4
+
+
+def _warn_if_clamped(paths, stats):
+    """Local-vol runs: statistics slot 6 counts the effective paths (fp64 kernels: lookups) that left the
+    tabulated ln S range, where sigma is the edge value instead of the reference's sigma_loc(S_t, t)
+    (processes.py:226,361).  A negligible count is the design; anything else must not pass silently."""
+    if paths.table is None or stats[0][0] <= 0:
+        return
+    frac = float(stats[0][6]) / float(stats[0][0])
+    if frac > CLAMP_WARN_FRACTION:
+        import warnings
+        warnings.warn(f"{frac:.2%} of the paths left the tabulated sigma(S,t) range "
+                      f"[{math.exp(paths.table.x0):.4g}, "
+                      f"{math.exp(paths.table.x0 + paths.table.h * (paths.table.table.shape[1] - 1)):.4g}] and saw the "
+                      "edge volatility there; pass a wider sigma_grid=(n_nodes, half_width)", RuntimeWarning,
+                      stacklevel=3)
 
 
 def array_stats(paths, spec, r, T, *, want_payoffs=False):
@@ -168,9 +188,24 @@ def array_stats(paths, spec, r, T, *, want_payoffs=False):
 
 
 def _expected_y(paths, r, T):
-    """E[e^{-rT} S_T] of the simulated process under the risk-neutral measure (monte_carlo.py:157)."""
+    """E[e^{-rT} S_T] of the DISCRETISED process the kernel simulates (monte_carlo.py:157 has the exact GBM
+    value S0 e^{-qT}).  Exact and log-Euler schemes (GBM, Heston FTE, LV log-Euler, Merton, SABR beta = 1) keep
+    the continuous mean S0 e^{(r-q)T}; the Euler / Milstein schemes in S (gbm_milstein, LV Milstein, SABR
+    beta < 1) have E[S_T] = S0 (1 + (r-q) dt)^n before their floors -- using the continuous mean there would
+    bias the control-variate estimator by c (E_disc[Y] - EY), which does not shrink with the path count.
+    Heston QE without the martingale correction has no closed-form discrete mean: declined."""
     pr = paths.proc
-    return pr["S0"] * math.exp((pr["r"] - pr["q"]) * pr["T"]) * math.exp(-r * T)
+    kind = pr["kind"]
+    rq = pr["r"] - pr["q"]
+    if kind == nv.PROC_HESTON_QE and not pr.get("martingale", False):
+        raise ValueError("control_variate needs E[S_T] of the discretised process; the QE scheme has it only "
+                         "with the martingale correction (heston_paths(..., scheme='qe', martingale_correction=True))")
+    euler_in_S = kind in (nv.PROC_GBM_MILSTEIN, nv.PROC_LV_MILSTEIN) or (kind == nv.PROC_SABR and pr["kappa"] != 1.0)
+    if euler_in_S:
+        growth = (1.0 + rq * pr["T"] / paths.n_steps) ** paths.n_steps
+    else:
+        growth = math.exp(rq * pr["T"])
+    return pr["S0"] * growth * math.exp(-r * T)
 
 
 def price_payoffs(paths, specs, r, T, *, control_variate=False):

@@ -21,7 +21,12 @@ New optional keywords (defaults keep every call a drop-in):
                    drawn on the host exactly as the reference does (processes.py:48,138-139,353)
                    and consumed by the fp64 kernels -> 1e-12 parity with the reference
   mode = "fp32" | "fp64"   arithmetic of the fused kernels with rng="philox"
-  sigma_grid = (n_nodes, half_width)  tabulation of sigma_loc for the local-vol generators
+  sigma_grid = (n_nodes, half_width)  tabulation of sigma_loc for the local-vol generators; the default
+         None means (256, 1.6) around ln S0, widened (same node spacing) when 6 standard deviations of ln S_T
+         at the surface's median volatility would not fit
+The kernels count the effective paths that left the tabulated range (statistics slot 6); exotics.path_stats
+warns when that fraction is not negligible -- outside the table sigma is the edge value, a departure from the
+reference's sigma_loc(S_t, t) (processes.py:226,361).
 """
 from __future__ import annotations
 
@@ -45,6 +50,33 @@ class SigmaTable:
         if self.table.ndim != 2 or self.table.shape[1] < 2:
             raise ValueError("sigma table must be (n_steps, n_nodes>=2)")
         self.x0, self.h, self.dt = float(x0), float(h), float(dt)
+
+    def check_against(self, S0, T, n_steps):
+        """A ready-made table must belong to this run: rows at the step times i*T/n_steps, grid around S0."""
+        if self.table.shape[0] < n_steps:
+            raise ValueError("sigma table has fewer rows than n_steps")
+        dt = T / n_steps
+        if abs(self.dt - dt) > 1e-12 * dt:
+            raise ValueError(f"sigma table was tabulated for dt={self.dt!r}, this run has T/n_steps={dt!r}: "
+                             "its rows would be applied at the wrong times")
+        x = float(np.log(S0))
+        if not (self.x0 < x < self.x0 + self.h * (self.table.shape[1] - 1)):
+            raise ValueError(f"S0={S0!r} lies outside the table's grid "
+                             f"[{float(np.exp(self.x0))!r}, {float(np.exp(self.x0 + self.h * (self.table.shape[1] - 1)))!r}]")
+
+    @staticmethod
+    def auto_grid(sigma_loc, S0, T, n_steps):
+        """(n_nodes, half_width): 256 nodes over ln S0 +- 1.6 (the desk workflow's paths span 19.7-307.6,
+        SURVEY 8d cfg 3), widened at the same node spacing when 6 sigma sqrt(T) at the surface's median
+        at-the-money volatility exceeds 1.6 -- so that long maturities / high volatilities do not run into the
+        flat extrapolation."""
+        dt = T / n_steps
+        probe_t = [i * dt for i in range(0, n_steps, max(1, n_steps // 16))]
+        at = [float(np.asarray(sigma_loc(np.array([float(S0)]), t), dtype=float)[0]) for t in probe_t]
+        med = float(np.median(np.clip(at, 1e-8, 10.0)))
+        half = max(1.6, 6.0 * med * float(np.sqrt(T)))
+        n_nodes = int(np.ceil(255 * half / 1.6)) + 1
+        return min(n_nodes, 2048), half
 
     @classmethod
     def from_callable(cls, sigma_loc, *, S0, T, n_steps, n_nodes=256, half_width=1.6):
@@ -255,16 +287,15 @@ def merton_jump_paths(S0, r, q, sigma, T, n_steps, n_paths, *, lam, mJ, sJ, anti
 
 def _table_for(sigma_loc, S0, T, n_steps, sigma_grid):
     if isinstance(sigma_loc, SigmaTable):
-        if sigma_loc.table.shape[0] < n_steps:
-            raise ValueError("sigma table has fewer rows than n_steps")
+        sigma_loc.check_against(S0, T, n_steps)
         return sigma_loc
-    n_nodes, half_width = sigma_grid
+    n_nodes, half_width = sigma_grid if sigma_grid is not None else SigmaTable.auto_grid(sigma_loc, S0, T, n_steps)
     return SigmaTable.from_callable(sigma_loc, S0=S0, T=T, n_steps=n_steps, n_nodes=n_nodes,
                                     half_width=half_width)
 
 
 def milstein_local_vol_paths(S0, r, q, T, n_steps, n_paths, sigma_loc, *, antithetic=True, seed=None,
-                             dS_bump=0.01, rng="philox", mode="fp32", sigma_grid=(256, 1.6)):
+                             dS_bump=0.01, rng="philox", mode="fp32", sigma_grid=None):
     """Local-vol Milstein (processes.py:311-381).  `sigma_loc` is the reference's callable (it is
     tabulated once on the host at the step times) or a ready SigmaTable."""
     _check_sizes(n_steps, n_paths)
@@ -274,7 +305,7 @@ def milstein_local_vol_paths(S0, r, q, T, n_steps, n_paths, sigma_loc, *, antith
 
 
 def local_vol_paths(S0, r, q, T, n_steps, n_paths, sigma_loc, *, antithetic=True, seed=None,
-                    rng="philox", mode="fp32", sigma_grid=(256, 1.6)):
+                    rng="philox", mode="fp32", sigma_grid=None):
     """Local-vol log-Euler (processes.py:223-258)."""
     _check_sizes(n_steps, n_paths)
     table = _table_for(sigma_loc, S0, T, n_steps, sigma_grid)

@@ -18,7 +18,7 @@ import numpy as np
 
 from . import monte_carlo as mc
 from .binomial import _P_ERROR, crr_batch
-from .core import OptionSpec
+from .core import OptionSpec, validate_contracts
 
 __all__ = ["TreePricer", "McPricer", "numerical_greeks", "scenario_grid", "portfolio_risk"]
 
@@ -32,6 +32,7 @@ class TreePricer:
         self.N, self.american = int(N), bool(american)
 
     def batch(self, S, K, T, r, q, sigma, kind):
+        validate_contracts(S, K, T, sigma)   # the OptionSpec(...) a reference pricer_func builds per point
         is_call = np.array([1 if k == "call" else 0 for k in kind], dtype=np.uint8)   # binomial.py:22-25
         price, status = crr_batch(S, K, T, r, q, sigma, is_call, self.N, american=self.american,
                                   return_status=True)

@@ -16,7 +16,7 @@ from statistics import NormalDist
 import numpy as np
 
 from .binomial import _P_ERROR, crr, crr_batch
-from .core import CALL, PUT
+from .core import CALL, PUT, validate_contracts
 from .monte_carlo import euro_price_mc
 
 __all__ = ["stress_test", "convergence_analysis"]
@@ -57,8 +57,7 @@ def stress_test(opt, kind, spot_shocks, vol_shocks, rate_shocks, *, pricer="bs")
         for idx in np.ndindex(*shape):
             out[idx] = _bs_price(float(S[idx]), opt.K, opt.T, float(r[idx]), opt.q, float(sig[idx]), kind)
         return out
-    if np.any(S <= 0):
-        raise ValueError(f"S0 must be positive, got {float(S[S <= 0][0])}")   # OptionSpec, core.py:27-28
+    validate_contracts(S, opt.K, opt.T, sig)   # OptionSpec(...) per grid point, reference validation.py:223-227 (replace() re-validates)
     price, status = crr_batch(S, opt.K, opt.T, r, opt.q, sig, 1 if kind == "call" else 0, 500,
                               american=False, return_status=True)
     if status.any():

@@ -87,3 +87,61 @@ def test_shard_items_by_item_for_large_books_and_by_paths_for_small_ones():
         assert edges[0][0] == 0 and edges[-1][1] == it["n_base"]
         assert all(edges[r][1] == edges[r + 1][0] for r in range(world - 1))
     assert book.shard_items(items, 0, 1) == [(0, it["n_base"]) for it in items]
+
+
+def test_vectorised_estimators_equal_the_scalar_ones_bit_for_bit():
+    """price_book evaluates the estimators of monte_carlo.py:142-167 / exotics.py:22-27 on arrays; the numbers
+    must be the ones the row-by-row API returns."""
+    import numpy as np
+    from optpricer_b200 import exotics as ex, monte_carlo as mc
+    g = np.random.default_rng(3)
+    items, blocks = [], []
+    for j in range(200):
+        n = float(g.integers(2, 10**7))
+        x = g.uniform(0.0, 20.0)
+        y = g.uniform(50.0, 150.0)
+        sx, sy = n * x, n * y
+        sxx = n * (x * x + g.uniform(0.0, 30.0))
+        syy = n * (y * y + g.uniform(0.0, 400.0))
+        sxy = n * (x * y + g.uniform(-20.0, 60.0))
+        if j % 2:
+            items.append(dict(kind="terminal", rows=[(j, None)], S0=g.uniform(50, 150), q=g.uniform(0, 0.05), T=g.uniform(0.1, 2)))
+        else:
+            items.append(dict(kind="path", rows=[(j, None)], S0=100.0, q=0.0, T=1.0))
+        blocks.append([n, sx, sxx, sy, syy, sxy, 0.0, 0.0])
+    blocks.append([1.0, 3.0, 9.0, 100.0, 1e4, 300.0, 0.0, 0.0])      # n = 1: stderr 0 for a path row
+    items.append(dict(kind="path", rows=[(200, None)], S0=100.0, q=0.0, T=1.0))
+    blocks.append([0.0] * 8)                                          # n = 0: NaN
+    items.append(dict(kind="terminal", rows=[(201, None)], S0=100.0, q=0.0, T=1.0))
+    stats = np.array(blocks)
+    for cv in (True, False):
+        idx, price, se = book.estimate_rows(items, stats, cv)
+        assert idx == list(range(202))
+        for it, s, p, e in zip(items, stats, price, se):
+            if it["kind"] == "terminal":
+                want = mc.estimator((int(s[0]), *s[1:6]), S0=it["S0"], q=it["q"], T=it["T"], control_variate=cv)
+            else:
+                want = ex.estimate(s)
+            assert (p == want[0] or (np.isnan(p) and np.isnan(want[0]))), (it, p, want)
+            assert (e == want[1] or (np.isnan(e) and np.isnan(want[1]))), (it, e, want)
+
+
+def test_item_sharding_carries_the_load_between_slices():
+    items = [dict(kind="path", rows=[(i, None)], n_base=1000 + 10 * (i % 7), n_steps=252) for i in range(64)]
+    whole = [book.shard_items(items, r, 4) for r in range(4)]
+    # every item on exactly one rank
+    for i in range(64):
+        assert sum(1 for r in range(4) if whole[r][i][1] > 0) == 1
+    loads = [sum((hi - lo) * 252 for lo, hi in whole[r]) for r in range(4)]
+    assert max(loads) - min(loads) <= 252 * 1060
+    # two slices with a carried load balance as well as one pass, identically on every rank
+    per_rank = []
+    for r in range(4):
+        load = [0] * 4
+        a = book.shard_items(items[:32], r, 4, load)
+        b = book.shard_items(items[32:], r, 4, load)
+        per_rank.append((a + b, list(load)))
+    assert all(pr[1] == per_rank[0][1] for pr in per_rank)
+    assert max(per_rank[0][1]) - min(per_rank[0][1]) <= 252 * 1060
+    for i in range(64):
+        assert sum(1 for r in range(4) if per_rank[r][0][i][1] > 0) == 1

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(native):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/optp_b200.h but not exported"
     assert sorted(native.EXPORTS) == declared
-    assert lib.optp_abi_version() == native.ABI_VERSION == 6
+    assert lib.optp_abi_version() == native.ABI_VERSION == 7
 
 
 def test_struct_layout_matches_header(native, tmp_path):

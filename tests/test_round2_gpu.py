@@ -1,0 +1,203 @@
+"""GPU tests of the round-2 additions behind the C ABI (run with -m gpu):
+local-vol items in optp_mc_book (table handles), the executed-work counters of the two-zone CRR kernel,
+the collective for a world of one, the sigma-table guards, the per-scheme control-variate mean, and the
+crr_vec many-strikes call the reference times at 220 options/s (binomial.py:44-109)."""
+import ctypes as C
+import math
+import warnings
+
+import numpy as np
+import pytest
+
+from golden_io import dupire_grid_arrays
+from oracle import crr_tree
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def op():
+    import optpricer_b200 as o
+    from optpricer_b200 import _native
+    _native.init()
+    return o
+
+
+def test_book_local_vol_rows_equal_the_single_call_api(op):
+    """scripts/desk_workflow_localvol_barrier.py:136-148 (Milstein local-vol paths, barrier + vanilla legs from
+    the same paths) as rows of ONE optp_mc_book call, next to a bumped-surface reprice and plain GBM rows."""
+    from optpricer_b200 import book as bk, exotics as ex, processes as pr
+    tab = pr.SigmaTable(*dupire_grid_arrays())
+    bumped = pr.SigmaTable(tab.table * 1.01, tab.x0, tab.h, tab.dt)
+    n, steps = 200_000, 252
+    base = dict(S0=100.0, K=100.0, T=1.0, r=0.05, q=0.02, sigma=0.2, kind="call", method="exotic", n_steps=steps,
+                n_paths=n, seed=42)
+    rows = [
+        dict(base, id="lv_barrier", exotic_type="barrier", barrier=130.0, barrier_type="up-and-out", sigma_table=tab),
+        dict(base, id="lv_digital", exotic_type="digital", sigma_table=tab),
+        dict(base, id="lv_barrier_bumped", exotic_type="barrier", barrier=130.0, barrier_type="up-and-out",
+             sigma_table=bumped),
+        dict(base, id="gbm_barrier", exotic_type="barrier", barrier=130.0, barrier_type="up-and-out"),
+        dict(base, id="bad_table", exotic_type="barrier", barrier=130.0, barrier_type="up-and-out", sigma_table=tab,
+             n_steps=100),
+    ]
+    got = bk.price_book(rows)
+    lp = pr.milstein_local_vol_paths(100.0, 0.05, 0.02, 1.0, steps, n, tab, seed=42)
+    want = ex.price_payoffs(lp, [ex.barrier_spec(100.0, "call", 130.0, "up-and-out"), ex.digital_spec(100.0, "call")],
+                            0.05, 1.0)
+    assert (got[0]["price"], got[0]["stderr"]) == want[0]
+    assert (got[1]["price"], got[1]["stderr"]) == want[1]
+    lpb = pr.milstein_local_vol_paths(100.0, 0.05, 0.02, 1.0, steps, n, bumped, seed=42)
+    wantb = ex.barrier_price(lpb, 100.0, 0.05, 1.0, "call", 130.0, "up-and-out")
+    assert (got[2]["price"], got[2]["stderr"]) == wantb and wantb[0] != want[0][0]
+    wantg = ex.barrier_price(pr.gbm_paths(100.0, 0.05, 0.02, 0.2, 1.0, steps, n, seed=42), 100.0, 0.05, 1.0, "call",
+                             130.0, "up-and-out")
+    assert (got[3]["price"], got[3]["stderr"]) == wantg
+    assert got[4]["price"] is None and "sigma_table does not match" in got[4]["error"]
+
+
+def test_sigma_table_handles(op):
+    from optpricer_b200 import _native as nv
+    lib = nv.init()
+    table = np.full((8, 16), 0.2)
+    hs = []
+    for _ in range(3):
+        h = C.c_int32()
+        nv.check(lib.optp_sigma_table_create(nv.ptr(table), 8, 16, C.byref(h)), "create")
+        hs.append(h.value)
+    assert len(set(hs)) == 3 and min(hs) >= 1
+    for h in hs:
+        assert lib.optp_sigma_table_destroy(h) == 0
+    assert lib.optp_sigma_table_destroy(hs[0]) > 0           # already gone: argument error, not a crash
+    assert lib.optp_sigma_table_destroy(0) > 0
+    # a local-vol book item must name a live handle
+    it = (nv.OptpBookItem * 1)()
+    it[0].n_payoffs, it[0].n_steps, it[0].n_base, it[0].antithetic = 1, 8, 1000, 1
+    it[0].proc.kind, it[0].proc.S0, it[0].proc.T, it[0].proc.n_nodes = nv.PROC_LV_MILSTEIN, 100.0, 1.0, 16
+    it[0].proc.x0, it[0].proc.h, it[0].proc.dS_bump = math.log(100.0) - 1.0, 2.0 / 15, 0.01
+    from optpricer_b200 import exotics as ex
+    pay = ex._native_payoffs([ex.vanilla_spec(100.0, "call")], 0.05, 1.0)
+    out = np.zeros(nv.NSTATS)
+    assert lib.optp_mc_book(it, 1, pay, 1, nv.ptr(out)) > 0
+    assert "table handle" in nv.last_error()
+
+
+def test_crr_executed_work_counters(op):
+    """bench.py's physical roofline figure: the counting build of the two-zone kernel prices identically and
+    reports what its level loops executed."""
+    from optpricer_b200 import _native as nv
+    S0, K, T, r, q, sig, is_call = crr_tree.cfg2_contracts(100_000)
+    plain = op.crr_batch(S0, K, T, r, q, sig, is_call, 1000, american=True)
+    nv.set_option("crr_count_ops", 1)
+    try:
+        counted = op.crr_batch(S0, K, T, r, q, sig, is_call, 1000, american=True)
+        fp64 = nv.get_counter("crr_fp64_lane_ops") / S0.size
+        nodes = nv.get_counter("crr_node_updates") / S0.size
+    finally:
+        nv.set_option("crr_count_ops", 0)
+    np.testing.assert_array_equal(counted, plain)
+    assert 60_000 < nodes < 500_500            # the band cuts skip most of the 500 500 node updates ...
+    assert nodes < fp64 < 3.0 * nodes + 2.0 * 1000 * 32   # ... and most executed nodes cost one DFMA
+    nv.set_option("crr_count_ops", 1)          # setting the option resets the counters
+    assert nv.get_counter("crr_node_updates") == 0
+    nv.set_option("crr_count_ops", 0)
+    with pytest.raises(ValueError):
+        nv.get_counter("no_such_counter")
+
+
+def test_collective_for_a_world_of_one(op):
+    from optpricer_b200 import _native as nv
+    lib = nv.init()
+    assert lib.optp_comm_init(0, 1, None) == 0
+    r_, w_ = C.c_int(-1), C.c_int(-1)
+    assert lib.optp_comm_info(C.byref(r_), C.byref(w_)) == 0 and (r_.value, w_.value) == (0, 1)
+    a = np.arange(24, dtype=np.float64)
+    b = a.copy()
+    assert lib.optp_allreduce_stats(nv.ptr(b), b.size) == 0
+    np.testing.assert_array_equal(a, b)
+    assert lib.optp_comm_init(3, 2, None) > 0       # rank outside the world
+    assert lib.optp_comm_destroy() == 0
+
+
+def test_sigma_table_guards_and_clamp_warning(op):
+    from optpricer_b200 import exotics as ex, processes as pr
+    tab = pr.SigmaTable(*dupire_grid_arrays())
+    with pytest.raises(ValueError, match="tabulated for dt"):
+        pr.milstein_local_vol_paths(100.0, 0.05, 0.02, 2.0, 252, 1000, tab, seed=1)        # another T
+    with pytest.raises(ValueError, match="outside the table"):
+        pr.milstein_local_vol_paths(1000.0, 0.05, 0.02, 1.0, 252, 1000, tab, seed=1)       # another S0
+    flat = lambda S, t: 0.6 + 0.0 * S  # noqa: E731
+    # default grid: widened from +-1.6 to 6 sigma sqrt(T) = 5.09 at the same node spacing
+    n_nodes, half = pr.SigmaTable.auto_grid(flat, 100.0, 2.0, 100)
+    assert half == pytest.approx(6 * 0.6 * math.sqrt(2.0)) and n_nodes == math.ceil(255 * half / 1.6) + 1
+    assert pr.SigmaTable.auto_grid(lambda S, t: 0.2 + 0.0 * S, 100.0, 1.0, 252) == (256, 1.6)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        lp = pr.milstein_local_vol_paths(100.0, 0.05, 0.0, 2.0, 100, 200_000, flat, seed=3)
+        wide = ex.barrier_price(lp, 100.0, 0.05, 2.0, "call", 400.0, "up-and-out")          # no warning
+    # a deliberately narrow table: several per cent of the paths leave it -> RuntimeWarning, price moves
+    with pytest.warns(RuntimeWarning, match="left the tabulated"):
+        lpn = pr.milstein_local_vol_paths(100.0, 0.05, 0.0, 2.0, 100, 200_000, flat, seed=3, sigma_grid=(64, 0.8))
+        ex.barrier_price(lpn, 100.0, 0.05, 2.0, "call", 400.0, "up-and-out")
+    assert wide[0] > 0
+
+
+def test_control_variate_uses_the_discrete_mean_of_the_scheme(op):
+    """Milstein / Euler-in-S schemes have E[S_T] = S0 (1 + (r-q) dt)^n, not S0 e^{(r-q)T}; with the
+    continuous mean the CV estimator carries a bias that does not shrink with the path count."""
+    from optpricer_b200 import exotics as ex, processes as pr
+    lp = pr.gbm_milstein_paths(100.0, 0.12, 0.0, 0.2, 1.0, 4, 20_000_000, seed=9)
+    spec = [ex.vanilla_spec(100.0, "call")]
+    stats, _, _ = ex.path_stats(lp, spec, 0.12, 1.0)
+    plain = ex.estimate(stats[0])
+    cv = ex.price_payoffs(lp, spec, 0.12, 1.0, control_variate=True)[0]
+    assert cv[1] < 0.6 * plain[1]
+    assert abs(cv[0] - plain[0]) <= 4.0 * plain[1], (cv, plain)
+    wrong = ex.estimate(stats[0], control_variate=True, expected_y=100.0)      # the continuous-time mean
+    assert abs(wrong[0] - plain[0]) > 10.0 * plain[1], (wrong, plain)
+    assert ex._expected_y(lp, 0.12, 1.0) == pytest.approx(100.0 * 1.03 ** 4 * math.exp(-0.12))
+    qe = pr.heston_paths(100.0, 0.05, 0.0, 0.04, 2.0, 0.04, 0.3, -0.7, 1.0, 8, 1000, seed=1, scheme="qe")
+    with pytest.raises(ValueError, match="martingale correction"):
+        ex.asian_price(qe, 100.0, 0.05, 1.0, "call", control_variate=True)
+
+
+def test_crr_european_sum_at_its_depth_limit_with_extreme_probabilities(op):
+    """N = 20000 is where crr_euro_sum_kernel stops; p close to 0 and to 1 against the backward
+    induction (optp_set_option("crr_euro_sum", 0))."""
+    from optpricer_b200 import _native as nv
+    S0 = np.array([100.0, 100.0, 100.0, 100.0, 50.0, 150.0])
+    K = np.array([100.0, 90.0, 110.0, 100.0, 55.0, 140.0])
+    T = np.array([1.0, 2.0, 0.5, 1.0, 1.0, 1.0])
+    # p = (e^{(r-q)dt} - d)/(u - d): large |r - q| with small sigma pushes p to the ends of (0, 1)
+    r = np.array([0.03, 1.20, -1.00, 0.03, 2.0, 0.0])
+    q = np.array([0.00, 0.00, 0.00, 0.00, 0.0, 1.8])
+    sig = np.array([0.2, 0.02, 0.02, 0.9, 0.03, 0.03])
+    is_call = np.array([1, 1, 0, 0, 1, 0], dtype=np.uint8)
+    fast, st = op.crr_batch(S0, K, T, r, q, sig, is_call, 20000, american=False, return_status=True)
+    nv.set_option("crr_euro_sum", 0)
+    try:
+        slow, st2 = op.crr_batch(S0, K, T, r, q, sig, is_call, 20000, american=False, return_status=True)
+    finally:
+        nv.set_option("crr_euro_sum", 1)
+    np.testing.assert_array_equal(st, st2)
+    ok = st == 0
+    assert ok.sum() >= 4
+    np.testing.assert_allclose(fast[ok], slow[ok], rtol=1e-10, atol=1e-10)
+
+
+def test_crr_vec_many_strikes_on_one_tree(op):
+    """binomial.py:44-109 with 1000 strikes, N = 1000, American (the call bench.py times): every strike against
+    the scalar path, a sample against the oracle's shared-tree restatement."""
+    strikes = np.linspace(60.0, 140.0, 1000)
+    got = op.crr_vec(100.0, strikes, 1.0, 0.03, 0.0, 0.2, "put", N=1000, american=True)
+    assert got.shape == (1000,)
+    pick = [0, 137, 500, 731, 999]
+    want = crr_tree.crr_shared_tree(100.0, strikes[pick], 1.0, 0.03, 0.0, 0.2, "put", N=1000, american=True)
+    np.testing.assert_allclose(got[pick], want, rtol=1e-10, atol=1e-10)
+    assert np.all(np.diff(got) > 0)                      # a put's price rises with the strike
+    one = op.crr(op.OptionSpec(100.0, float(strikes[500]), 1.0, 0.03, 0.2), "put", 1000, american=True)
+    assert one == got[500]
+    kinds = np.where(np.arange(1000) % 2 == 0, "call", "put")
+    mixed = op.crr_vec(100.0, strikes, 1.0, 0.03, 0.01, 0.2, kinds, N=1000, american=True)
+    want = crr_tree.crr_shared_tree(100.0, strikes[pick], 1.0, 0.03, 0.01, 0.2, kinds[pick], N=1000, american=True)
+    np.testing.assert_allclose(mixed[pick], want, rtol=1e-10, atol=1e-10)
