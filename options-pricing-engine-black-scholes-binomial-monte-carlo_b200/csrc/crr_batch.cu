@@ -45,6 +45,10 @@ struct CrrArgs {
     // {number of contracts left at status 2, at status 3} by the two-zone passes, or null: a full-width
     // filter pass with nothing to do returns at once instead of scanning n status bytes
     unsigned int* decl_count;
+    // two-zone kernel: ticket counter of this launch (zeroed by launch_crr).  A warp takes the next group of G
+    // contracts when it has finished its last one, instead of a fixed stride: the walks differ in length (band
+    // width, early all-exercise exits), and with a fixed stride the slowest warp set the kernel's time
+    unsigned int* next_group;
     // one-option-per-CTA kernel: level arrays in global memory (3*(N+2) doubles per CTA) when they do not
     // fit in shared memory, else null
     double* cta_scratch;
@@ -596,14 +600,32 @@ __global__ void __launch_bounds__(kBandWarps * 32, 5) crr_band_kernel(CrrArgs a)
 //      of ITS option.  All options of a warp walk the same levels with the same layout (M = the
 //      widest C zone among them); everything else (lattice constants, window origin, band limits,
 //      failure flags) is per option.
-//  (3) The schedule is FIXED -- segments of kZoneSeg levels counted from level N, rigorous margin --
+//  (3) The schedule is FIXED -- kZoneSeg0 levels from level N, then segments of kZoneSeg levels --
 //      so the arithmetic applied to a contract does not depend on its warp mates or on G: a
 //      contract's price is bit-identical whatever batch it is priced in.
 #ifndef OPTP_ZONE_MINB4
 #define OPTP_ZONE_MINB4 4
 #endif
 constexpr int kZoneWarps = 4;
-constexpr int kZoneSeg = 28;      // levels per segment: Z = [jlo - 30, jlo + 2), margin kZoneSeg + 2 below the boundary
+// Z = [jlo - 30, jlo + 2): 30 nodes below the first continuation node jlo of the segment's first level.
+// RIGOROUSLY the boundary index falls by at most one per level (see above), which would allow segments of 28
+// levels.  Measured (scripts/crr_boundary_drop.py, the exact lattice boundary of config-2-like contracts), it falls
+// by 1/2 + O(1/sqrt(n)) per level n levels from expiry: at most 27 nodes over the FIRST 37 levels, and at most
+// 27 over any later stretch of 46 levels.  The schedule therefore walks kZoneSeg0 levels from level N and
+// kZoneSeg levels per segment after that -- 23 segments per N = 1000 option instead of 36, and the work between
+// segments (tile round trip, band measurement, plan) is a third of the walk.  Exactness does not rest on the
+// measurement: the kernel checks at EVERY level that Z's bottom node chose exercise, and a contract that fails
+// keeps status 2 and is priced by the full-width kernel.
+#ifndef OPTP_ZONE_SEG
+#define OPTP_ZONE_SEG 44
+#endif
+#ifndef OPTP_ZONE_SEG0
+#define OPTP_ZONE_SEG0 32
+#endif
+constexpr int kZoneBelow = 30;                // Z nodes below the first continuation node
+constexpr int kZoneSeg = OPTP_ZONE_SEG;       // levels per segment
+constexpr int kZoneSeg0 = OPTP_ZONE_SEG0;     // levels of the first segment (from level N)
+static_assert(kZoneSeg0 <= kZoneSeg, "the renormalisation bound L.R >= kZoneSeg covers the first segment too");
 // A lane holds at most 24 C nodes: 6 chunks of 32 nodes per option at four options per warp (band up to
 // 224 nodes), 12 at two (416), 24 at one (800).  A contract whose band is too wide for the layout it was
 // tried in keeps status 4 and is walked again by the next narrower-group pass (launch_crr); the
@@ -629,26 +651,45 @@ static_assert(32 * (1 + zone_max_m(4)) + (32 * (1 + zone_max_m(4)) >> 4) <= zone
 static_assert(32 * (1 + zone_max_m(2)) + (32 * (1 + zone_max_m(2)) >> 4) <= zone_group_tile(2), "tile too small");
 static_assert(32 * (1 + zone_max_m(1)) + (32 * (1 + zone_max_m(1)) >> 4) <= zone_group_tile(1), "tile too small");
 
-// nlev levels in layout (BZ = G, BC = G*M).  sb = sgn*S0*u^(2*(w0 + quad) - k): the first node of this
-// lane's quad of Z nodes one level above the segment (ulo holds the lane's factors within the quad).  Returns the exercise mask of this lane's Z nodes at the last
-// level; n_ex0 counts the levels at which the lane's first Z node chose exercise, n_exT the levels
-// t < n_chk at which its last Z node did.
+// One segment in layout (BZ = G, BC = G*M), M a compile-time constant:
+//   * the lane's C nodes are loaded from the node-ordered tile, which holds level k in the PREVIOUS layout
+//     (tile index jr0 + i; nodes outside [0, lim) are above the band and count as 0);
+//   * nlev levels are walked;
+//   * the pd^-nlev scaling is undone (back = pd^nlev) and the lane's C nodes are written back to the tile in THIS
+//     layout.  (The caller loads and stores the Z nodes: with the Z stores in here ptxas no longer proves the warp
+//     converged and guards every shuffle of the walk with a BRA.DIV.)
+// sb = sgn*S0*u^(2*(w0 + quad) - k): the first node of this lane's quad of Z nodes one level above the segment
+// (ulo holds the lane's factors within the quad).  Returns the exercise mask of this lane's Z nodes at the last
+// level; n_ex0 counts the levels at which the lane's first Z node chose exercise, t_exT is the first level at
+// which its last Z node did (INT_MAX: never).
 template <int G, int M>
 __device__ __forceinline__ unsigned int zone_segment(double (&z)[G], double (&c)[kZoneLaneC],
                                                      const double (&ulo)[G], const Lattice& L, int gl,
-                                                     int src, double sb, int nlev, int n_chk, double back,
-                                                     int& n_ex0_out, int& n_exT_out) {
+                                                     int src, double sb, int nlev, double back, double* tile,
+                                                     int jr0, int lim, int& n_ex0_out, int& t_exT_out) {
     constexpr int BZ = G, BC = G * M, LG = 32 / G;
+    constexpr int kMaxM = zone_max_m(G);  // (OPTP_ZP's bound in -DOPTP_ZONE_CHECK builds)
+    (void)kMaxM;
+#pragma unroll
+    for (int i = 0; i < BC; ++i) {
+        const int jr = jr0 + i;
+        c[i] = ((unsigned int)jr < (unsigned int)lim) ? tile[OPTP_ZP(jr)] : 0.0;
+    }
+    __syncwarp();  // every lane has read level k before this segment's stores overwrite the tile
     double sbg = sb, sKg = L.sK;
     const double rho = L.rho;
-    const double rho_top = (gl == LG - 1) ? 0.0 : rho;  // the node above the window counts as 0
-    const double rho_ztop = (BC > 0) ? rho : rho_top;
-    // exercise counters instead of predicate chains: ptxas folds `all = all && (e > c)` into a second
-    // and third DSETP per level, and the FP64 pipe is the one this loop loads most
-    int n_ex0 = 0, n_exT = 0;
-    // lane gl takes lane gl+1's first Z node; the option's last lane takes its first lane's first C
-    // node (the first lane's own first Z node is nobody's neighbour)
-    double nbz = __shfl_sync(0xffffffffu, (BC > 0 && gl == 0) ? c[0] : z[0], src);
+    const bool last = (gl == LG - 1);
+    const double rho_top = last ? 0.0 : rho;  // the node above the window counts as 0
+    // The top Z node of a lane takes the next lane's first Z node; in the option's last lane it takes the first
+    // C node of the option's first lane, which the ring shuffle of c[0] delivers there as nbc.  Both products
+    // are formed and one multiplier is zero (x + 0*y = x exactly for finite y: values are bounded by 2^200 K),
+    // so no 64-bit select sits between the shuffles and the arithmetic: one DFMA instead of two FSELs.
+    const double rz_z = (BC > 0) ? (last ? 0.0 : rho) : rho_top;
+    const double rz_c = (BC > 0 && last) ? rho : 0.0;
+    // a counter and a running minimum instead of predicate chains: ptxas folds `all = all && (e > c)` into a
+    // second and third DSETP per level, and the FP64 pipe is the one this loop loads most
+    int n_ex0 = 0, t_exT = 0x7fffffff;
+    double nbz = __shfl_sync(0xffffffffu, z[0], src);
     double nbc = 0.0;
     if (BC > 0) nbc = __shfl_sync(0xffffffffu, c[0], src);
 #pragma unroll 2
@@ -657,8 +698,11 @@ __device__ __forceinline__ unsigned int zone_segment(double (&z)[G], double (&c)
         sKg *= L.inv_pd;
         double cz[BZ], ez[BZ];
 #pragma unroll
-        for (int i = 0; i < BZ; ++i)
-            cz[i] = (i + 1 < BZ) ? fma(rho, z[i + 1], z[i]) : fma(rho_ztop, nbz, z[i]);
+        for (int i = 0; i < BZ; ++i) {
+            if (i + 1 < BZ) cz[i] = fma(rho, z[i + 1], z[i]);
+            else if (BC > 0) cz[i] = fma(rz_z, nbz, fma(rz_c, nbc, z[i]));
+            else cz[i] = fma(rz_z, nbz, z[i]);
+        }
 #pragma unroll
         for (int i = 0; i < BZ; ++i) ez[i] = fma(sbg, ulo[i], sKg);
         // everything is updated in place, in ascending node order, so no value has to be carried
@@ -670,11 +714,11 @@ __device__ __forceinline__ unsigned int zone_segment(double (&z)[G], double (&c)
         for (int i = 0; i < BZ; ++i) {
             const bool ex = ez[i] > cz[i];
             if (i == 0) n_ex0 += ex ? 1 : 0;
-            if (i == BZ - 1) n_exT += (ex && t < n_chk) ? 1 : 0;
+            if (i == BZ - 1) t_exT = ex ? min(t_exT, t) : t_exT;
             z[i] = ex ? ez[i] : cz[i];
         }
         if (BC > 0) nbc = __shfl_sync(0xffffffffu, c[0], src);
-        nbz = __shfl_sync(0xffffffffu, (BC > 0 && gl == 0) ? c[0] : z[0], src);
+        nbz = __shfl_sync(0xffffffffu, z[0], src);
     }
     // exercise mask of the last level: a node chose exercise iff it holds the exercise value
     unsigned int mask = 0;
@@ -684,9 +728,12 @@ __device__ __forceinline__ unsigned int zone_segment(double (&z)[G], double (&c)
 #pragma unroll
     for (int i = 0; i < BZ; ++i) z[i] *= back;
 #pragma unroll
-    for (int i = 0; i < BC; ++i) c[i] *= back;
+    for (int i = 0; i < BC; ++i) {
+        c[i] *= back;
+        tile[OPTP_ZP(32 + gl * BC + i)] = c[i];
+    }
     n_ex0_out = n_ex0;
-    n_exT_out = n_exT;
+    t_exT_out = t_exT;
     return mask;
 }
 
@@ -706,7 +753,16 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
     const unsigned long long nwarps = (unsigned long long)gridDim.x * kZoneWarps;
     // retry passes walk the compacted list of contracts the previous layout was too narrow for
     const unsigned int n_work = a.wl_in ? *a.wl_in_n : (unsigned int)a.n;  // (launch_crr: n < 2^32)
-    for (unsigned long long o0 = warp0 * G; o0 < n_work; o0 += nwarps * G) {
+    (void)warp0;
+    (void)nwarps;
+    while (true) {
+        // EVERY lane issues the atomic (lane 0 adds one, the others zero): nvcc aggregates it into one ATOMG per
+        // warp, and the REDUX puts the ticket in a uniform register.  With the atomic under `if (lane == 0)` --
+        // or the ticket passed on by a shuffle -- ptxas no longer proves the warp converged and guards every
+        // shuffle of the walk with a BRA.DIV (see the level-loop notes above).
+        const unsigned int ticket = __reduce_min_sync(0xffffffffu, atomicAdd(a.next_group, lane == 0 ? 1u : 0u));
+        const unsigned long long o0 = (unsigned long long)ticket * G;
+        if (o0 >= n_work) break;
         const unsigned long long og = o0 + (unsigned long long)(lane / LG);
         const bool wanted = og < n_work;
         const unsigned long long ow = wanted ? og : (unsigned long long)(n_work - 1);
@@ -823,15 +879,12 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
         // level N here, then after every segment.  (The level-N specials live OUTSIDE the walk loop: the loop
         // body is what the instruction caches have to hold.)
         int jlo = 0, jhi = 0;
+#pragma unroll
+        for (int i = 0; i < BZ; ++i) tile[OPTP_ZP(gl * BZ + i)] = z[i];  // level N (M = 0)
+        __syncwarp();
         auto measure_band = [&]() {
             // ---- level k goes to the tile (node-ordered); measure its band [jlo, jhi) per option -----
             const int BC = G * M;
-#pragma unroll
-            for (int i = 0; i < BZ; ++i) tile[OPTP_ZP(gl * BZ + i)] = z[i];
-#pragma unroll
-            for (int i = 0; i < BCMAX; ++i)
-                if (i < BC) tile[OPTP_ZP(32 + gl * BC + i)] = c[i];
-            __syncwarp();
             // jlo = first node that did not choose exercise
             const unsigned int contm = ~exmask & ((1u << BZ) - 1u);
             const int first_cont = contm ? (__ffs(contm) - 1) : BZ;
@@ -879,7 +932,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             int wl = w0, span = 0;
             if (mine) {
                 jlo = j1;
-                wl = max(0, j1 - (kZoneSeg + 2));
+                wl = max(0, j1 - kZoneBelow);
                 span = w0 + 32 - wl;
                 if (span > 32 * (1 + kMaxM)) fail = too_wide = true;
             }
@@ -910,10 +963,10 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             // puts a BRA.DIV convergence check and a dozen register moves into every level loop below)
             if (k == 0 || __reduce_or_sync(0xffffffffu, fail ? 0u : 1u) == 0u) break;  // nothing left to walk in this warp
             // ---- next segment: levels k-1 ... k-nlev, fixed schedule -------------------------------
-            const int nlev = min(kZoneSeg, k);
+            const int nlev = min(k == N ? kZoneSeg0 : kZoneSeg, k);
             const int top = min(jhi, k + 1);  // exclusive; node `top` of level k is 0 (or dead)
-            // rigorous margin: the boundary index falls by at most one per level
-            int w0n = max(0, jlo - (nlev + 2));
+            // Z's bottom sits kZoneBelow nodes under the boundary (see kZoneSeg)
+            int w0n = max(0, jlo - kZoneBelow);
             int need = 0, n_chk = 0;
             if (top > w0n + 32) {
                 need = (top - (w0n + 32) + 31) >> 5;
@@ -929,7 +982,9 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             const int Mn = __reduce_max_sync(0xffffffffu, need);
             const int BCn = G * Mn;
             // ---- re-pack level k from (w0, M) to (w0n, Mn) ------------------------------------------
-            // this lane's first Z node of the new layout at level k: sgn*S0*u^(2j - k)
+            // this lane's first Z node of the new layout at level k: sgn*S0*u^(2j - k).  (A running product
+            // sb *= (u^2)^m instead of this exp() -- five predicated square-and-multiply steps -- was tried: no
+            // faster (45.5 M against 45.8 M options/s), and it lets the exercise values drift by 3e-14.)
             const double sb = sS0 * exp(ln_u * (double)(2 * (w0n + quad0) - k));
 #pragma unroll
             for (int i = 0; i < BZ; ++i) {
@@ -941,18 +996,11 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
                 else val = tile[OPTP_ZP(jr)];
                 z[i] = val;
             }
-#pragma unroll
-            for (int i = 0; i < BCMAX; ++i) {
-                if (i < BCn) {
-                    const int j = w0n + 32 + gl * BCn + i;
-                    const int jr = j - w0;
-                    c[i] = (jr < 0 || jr >= width_old || j >= top) ? 0.0 : tile[OPTP_ZP(jr)];
-                }
-            }
-            __syncwarp();
+            const int jr0 = w0n + 32 + gl * BCn - w0;
+            const int lim = max(0, min(width_old, top - w0));
             w0 = w0n;
             M = Mn;
-            int n_ex0 = 0, n_exT = 0;
+            int n_ex0 = 0, t_exT = 0x7fffffff;
             double back = back_full;
             if (nlev != kZoneSeg) {  // last, partial segment: pd^nlev by square-and-multiply
                 back = 1.0;
@@ -965,7 +1013,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
 #define OPTP_ZONE_CASE(m)                                                                                          \
     case m:                                                                                                        \
         if constexpr ((m) <= kMaxM)                                                                                \
-            exmask = zone_segment<G, ((m) <= kMaxM ? (m) : 0)>(z, c, ulo, L, gl, src, sb, nlev, n_chk, back, n_ex0, n_exT); \
+            exmask = zone_segment<G, ((m) <= kMaxM ? (m) : 0)>(z, c, ulo, L, gl, src, sb, nlev, back, tile, jr0, lim, n_ex0, t_exT); \
         break;
             switch (M) {
                 OPTP_ZONE_CASE(0) OPTP_ZONE_CASE(1) OPTP_ZONE_CASE(2) OPTP_ZONE_CASE(3) OPTP_ZONE_CASE(4)
@@ -976,13 +1024,16 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
                 default: break;
             }
 #undef OPTP_ZONE_CASE
+#pragma unroll
+            for (int i = 0; i < BZ; ++i) tile[OPTP_ZP(gl * BZ + i)] = z[i];
+            __syncwarp();  // level k - nlev is in the tile
             // everything below the window is an exercise node only while the window's bottom node
             // chose exercise at EVERY level; everything in C is a continuation node only while Z's
             // top node chose continuation at every level it exists
             const int bottom_ex = __shfl_sync(0xffffffffu, n_ex0, gb);
-            const int top_ex = __shfl_sync(0xffffffffu, n_exT, gb + LG - 1);
+            const int top_ex = __shfl_sync(0xffffffffu, t_exT, gb + LG - 1);
             if (w0 > 0 && bottom_ex != nlev) fail = true;
-            if (top_ex != 0) fail = true;
+            if (top_ex < n_chk) fail = true;  // (exercise events while Z's top node is outside the tree do not count)
             if (COUNT) {
                 // per lane and level: Z nodes 2 DFMA + 1 DSETP each, C nodes 1 DFMA each, 2 scaling DMULs
                 cnt_fp64 += (unsigned int)(nlev * (3 * G + G * M + 2));
@@ -1247,6 +1298,7 @@ static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st, int sl
     a.decl_count = nullptr;
     a.cta_scratch = nullptr;
     a.op_count = nullptr;
+    a.next_group = nullptr;
     if (a.n == 0) return 0;
     if (a.n >= (1ull << 32)) return set_error(OPTP_E_TOO_LARGE, "a CRR batch holds at most 2^32 - 1 contracts");
     if (american && !c.crr_no_band) {
@@ -1272,7 +1324,8 @@ static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st, int sl
             wl[0] = (unsigned int*)(base + 256);
             wl[1] = (unsigned int*)(base + 256 + list_bytes);
             a.decl_count = hdr + 2;
-            OPTP_CUDA(cudaMemsetAsync(hdr, 0, 4 * sizeof(unsigned int), st));
+            a.next_group = hdr + 4;   // hdr[4..6]: the ticket counters of the (up to three) two-zone passes
+            OPTP_CUDA(cudaMemsetAsync(hdr, 0, 8 * sizeof(unsigned int), st));
             if (G >= 2) {
                 a.wl_out = wl[0];
                 a.wl_out_n = hdr;
@@ -1305,6 +1358,7 @@ static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st, int sl
         for (int g2 = G / 2; g2 >= 1; g2 /= 2, ++list) {
             a.wl_in = wl[list];
             a.wl_in_n = hdr + list;
+            a.next_group = hdr + 5 + list;
             a.wl_out = (g2 == 2) ? wl[1] : nullptr;
             a.wl_out_n = (g2 == 2) ? hdr + 1 : nullptr;
             if (int e = occupancy_cached(zone_fn(g2, count), kZoneWarps * 32, &per_sm)) return e;

@@ -12,7 +12,9 @@ import threading
 
 import numpy as np
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "liboptp_b200.so")
+# OPTP_LIB: another build of the same library (A/B runs of kernel variants, scripts/crr_ab.py)
+LIB_PATH = os.environ.get("OPTP_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib",
+                                                      "liboptp_b200.so")
 ABI_VERSION = 7
 NSTATS = 8
 MAX_PAYOFFS = 16
