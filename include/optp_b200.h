@@ -46,6 +46,8 @@ extern "C" {
 #define OPTP_PROC_SABR 5         /* sabr_paths                processes.py:168-217 */
 #define OPTP_PROC_HESTON_QE 6    /* Andersen (2008) QE -- no reference code, parity unpinned */
 #define OPTP_PROC_MERTON 7       /* merton_jump_paths         processes.py:62-111  */
+#define OPTP_PROC_HESTON_QE_M 8  /* QE with Andersen's martingale correction K0* (2008, sec. 4.3.2): E[S_T] is exact,
+                                    which the control variate needs -- no reference code, parity unpinned */
 
 /* ---- payoff kinds (reference exotics.py) ---------------------------------- */
 #define OPTP_PAY_VANILLA 0   /* vanilla leg of barrier_price  exotics.py:83-88   */

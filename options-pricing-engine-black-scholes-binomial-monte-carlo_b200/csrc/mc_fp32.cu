@@ -245,6 +245,7 @@ struct StepConst {
     float m_c1, m_ssdt, m_hs2dt;
     // Heston QE (Andersen 2008); x in log2 units
     float q_theta, q_E, q_c1, q_c2, q_K0, q_K1, q_K2, q_K3;
+    float q_A, q_hK3, q_rq2;  // martingale correction: A = K2 + K3/2 (natural units), K3/2 and (r-q) dt in log2 units
     // Merton jumps (log2 units): drift incl. compensator, mJ, sJ, mu = lam*dt, exp(-mu)
     float j_drift2, j_m2, j_s2, j_mu, j_p0;
     // SABR: log2 sigma += s_nu2*Z2 + s_vdr2; beta = 1: log2 S += sigma*zc*s_sdt2 + sigma^2*s_mhdt2 + s_rq2;
@@ -289,7 +290,7 @@ __device__ __forceinline__ void heston_step(LogState& p, LogState& m, float& vp,
 
 // Heston quadratic-exponential step of ONE path (no reference code: Andersen 2008, see
 // oracle/path_schemes.py:heston_qe).  psi <= 1.5  <=>  tt = 2 m^2 / s^2 >= 4/3.
-template <int MASK>
+template <int MASK, bool MART>
 __device__ __forceinline__ void heston_qe_one(LogState& s, float& v, float z0, float z1,
                                               const StepConst& k) {
     const float m = fmaf(v - k.q_theta, k.q_E, k.q_theta);
@@ -299,13 +300,23 @@ __device__ __forceinline__ void heston_qe_one(LogState& s, float& v, float z0, f
     const float m2 = m * m;
     const float tt = (m2 + m2) * inv_s2;
     float vn;
+    // MART: log2 of M = E[exp(A v') | v] (Andersen 2008, eqs. 4.14-4.16); NaN where its regularity condition
+    // fails, which keeps the uncorrected drift below
+    float lg2M = 0.0f;
     if (tt >= 1.3333334f) {
         const float r1 = mufu_sqrt(fmaf(tt, tt, -tt));
         const float b2 = (tt - 1.0f) + r1;
         float inv_1b2;
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_1b2) : "f"(1.0f + b2));
         const float bz = mufu_sqrt(b2) + z0;
-        vn = (m * inv_1b2) * (bz * bz);
+        const float aq = m * inv_1b2;
+        vn = aq * (bz * bz);
+        if (MART) {  // M = exp(A b^2 a / (1 - 2 A a)) / sqrt(1 - 2 A a)
+            const float den = fmaf(-2.0f * k.q_A, aq, 1.0f);
+            float inv_den;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_den) : "f"(den));
+            lg2M = fmaf(1.4426950408889634f * k.q_A * b2 * aq, inv_den, -0.5f * mufu_lg2(den));  // den <= 0 -> NaN
+        }
     } else {  // exponential branch (small variance, psi = 2/tt > 1.5): v' = 0 with probability p, else exponential
         // p = (psi - 1)/(psi + 1) = (2 - tt)/(2 + tt), 1 - p = 2 tt/(2 + tt), v' = ln((1 - p)/(1 - u)) m/(1 - p)
         // with u = Phi(z0); u <= p  <=>  1 - u >= 1 - p.  Reciprocals and the log are single MUFU ops here
@@ -319,9 +330,20 @@ __device__ __forceinline__ void heston_qe_one(LogState& s, float& v, float z0, f
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_omu) : "f"(omu));
         const float scale = 0.5f * m * (2.0f + tt) * inv_tt;  // m / (1 - p)
         vn = (omu >= omp) ? 0.0f : (0.6931471805599453f * mufu_lg2(omp * inv_omu)) * scale;
+        if (MART) {  // M = p + beta (1 - p)/(beta - A), beta = (1 - p)/m  ->  p + (1-p)^2 / ((1-p) - A m)
+            const float den = fmaf(-k.q_A, m, omp);
+            float inv_den;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_den) : "f"(den));
+            lg2M = (den > 0.0f) ? mufu_lg2(fmaf(omp * omp, inv_den, 1.0f - omp)) : __int_as_float(0x7fc00000);
+        }
     }
     const float vol = mufu_sqrt(fmaxf(k.q_K3 * (v + vn), 0.0f));
-    s.x = fmaf(vol, z1, fmaf(k.q_K2, vn, fmaf(k.q_K1, v, s.x + k.q_K0)));
+    float drift = fmaf(k.q_K1, v, s.x + k.q_K0);
+    if (MART) {
+        const float corrected = fmaf(-k.q_hK3, v, (s.x + k.q_rq2) - lg2M);
+        drift = (lg2M == lg2M) ? corrected : drift;
+    }
+    s.x = fmaf(vol, z1, fmaf(k.q_K2, vn, drift));
     v = vn;
     observe_log<MASK>(s);
 }
@@ -421,6 +443,9 @@ __global__ void __launch_bounds__(256, (PROC == OPTP_PROC_HESTON_FTE || PROC == 
         k.q_K1 = (float)((0.5 * dt * (a.kappa * a.rho / a.xi - 0.5) - a.rho / a.xi) * L2E);
         k.q_K2 = (float)((0.5 * dt * (a.kappa * a.rho / a.xi - 0.5) + a.rho / a.xi) * L2E);
         k.q_K3 = (float)(0.5 * dt * (1.0 - a.rho * a.rho) * L2E * L2E);
+        k.q_A = (float)((0.5 * dt * (a.kappa * a.rho / a.xi - 0.5) + a.rho / a.xi) + 0.25 * dt * (1.0 - a.rho * a.rho));
+        k.q_hK3 = (float)(0.25 * dt * (1.0 - a.rho * a.rho) * L2E);
+        k.q_rq2 = (float)((a.r - a.q) * dt * L2E);
     }
     if (PROC == OPTP_PROC_MERTON) {
         const double kj = exp(a.kappa + 0.5 * a.theta * a.theta) - 1.0;
@@ -525,22 +550,27 @@ __global__ void __launch_bounds__(256, (PROC == OPTP_PROC_HESTON_FTE || PROC == 
             LogState p, m;
             float vp = fmaxf((float)a.v0, 0.f), vm = vp;
             uint4 w = philox_words(a.seed, gpath, 0u, 0u);
+            auto qe_steps = [&](auto mart) {
+                constexpr bool MART = decltype(mart)::value;
 #pragma unroll 1
-            for (unsigned int c = 0; c < n_full; ++c) {
-                const uint4 wn = philox_words(a.seed, gpath, c + 1, 0u);
-                normals_from_words(w, z);
+                for (unsigned int c = 0; c < n_full; ++c) {
+                    const uint4 wn = philox_words(a.seed, gpath, c + 1, 0u);
+                    normals_from_words(w, z);
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    heston_qe_one<MASK>(p, vp, z[2 * j], z[2 * j + 1], k);
-                    if (ANTI) heston_qe_one<MASK>(m, vm, -z[2 * j], -z[2 * j + 1], k);
+                    for (int j = 0; j < 2; ++j) {
+                        heston_qe_one<MASK, MART>(p, vp, z[2 * j], z[2 * j + 1], k);
+                        if (ANTI) heston_qe_one<MASK, MART>(m, vm, -z[2 * j], -z[2 * j + 1], k);
+                    }
+                    w = wn;
                 }
-                w = wn;
-            }
-            if (n_tail) {
-                normals_from_words(w, z);
-                heston_qe_one<MASK>(p, vp, z[0], z[1], k);
-                if (ANTI) heston_qe_one<MASK>(m, vm, -z[0], -z[1], k);
-            }
+                if (n_tail) {
+                    normals_from_words(w, z);
+                    heston_qe_one<MASK, MART>(p, vp, z[0], z[1], k);
+                    if (ANTI) heston_qe_one<MASK, MART>(m, vm, -z[0], -z[1], k);
+                }
+            };
+            if (a.qe_martingale) qe_steps(std::true_type{});
+            else qe_steps(std::false_type{});
             ep = finish_log<MASK>(p, S0, inv_n);
             if (ANTI) em = finish_log<MASK>(m, S0, inv_n);
         } else if (PROC == OPTP_PROC_SABR) {

@@ -224,7 +224,23 @@ __global__ void __launch_bounds__(128) path_fp64_kernel(PathArgs a) {
                     const double omu = 0.5 * erfc(z0 * 0.7071067811865476);
                     vn = (u <= p) ? 0.0 : log((1.0 - p) / omu) / beta;
                 }
-                logs = logs + rq * dt + qe_K0 + qe_K1 * v + qe_K2 * vn + sqrt(fmax(qe_K3 * (v + vn), 0.0)) * z1;
+                double k0 = qe_K0 + qe_K1 * v;
+                if (a.qe_martingale) {  // Andersen's K0* (oracle/path_schemes.py:heston_qe, martingale_correction)
+                    const double A = qe_K2 + 0.5 * qe_K3;
+                    if (psi <= 1.5) {
+                        const double tt = 2.0 / psi;
+                        const double b2 = fmax(tt - 1.0 + sqrt(tt) * sqrt(fmax(tt - 1.0, 0.0)), 0.0);
+                        const double aa = m / (1.0 + b2);
+                        const double den = 1.0 - 2.0 * A * aa;
+                        if (den > 0.0) k0 = -(A * b2 * aa / den - 0.5 * log(den)) - 0.5 * qe_K3 * v;
+                    } else {
+                        const double p = (psi - 1.0) / (psi + 1.0);
+                        const double beta = (1.0 - p) / m;
+                        const double den = beta - A;
+                        if (den > 0.0) k0 = -log(p + beta * (1.0 - p) / den) - 0.5 * qe_K3 * v;
+                    }
+                }
+                logs = logs + rq * dt + k0 + qe_K2 * vn + sqrt(fmax(qe_K3 * (v + vn), 0.0)) * z1;
                 v = vn;
                 S = exp(logs);
             } else if (PROC == OPTP_PROC_LV_MILSTEIN) {

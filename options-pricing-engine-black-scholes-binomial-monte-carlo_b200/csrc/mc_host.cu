@@ -24,15 +24,16 @@ static int check_process(const optp_process* pr, uint32_t n_steps, uint64_t n_ba
     if (!pr) return set_error(OPTP_E_ARG, "null process");
     if (n_steps == 0 || n_base == 0)
         return set_error(OPTP_E_ARG, "n_steps and n_paths must be positive.");
-    if (pr->kind < OPTP_PROC_GBM || pr->kind > OPTP_PROC_MERTON)
+    if (pr->kind < OPTP_PROC_GBM || pr->kind > OPTP_PROC_HESTON_QE_M)
         return set_error(OPTP_E_KIND, "unknown process kind %d", pr->kind);
     if ((pr->kind == OPTP_PROC_HESTON_FTE || pr->kind == OPTP_PROC_SABR ||
-         pr->kind == OPTP_PROC_HESTON_QE) &&
+         pr->kind == OPTP_PROC_HESTON_QE || pr->kind == OPTP_PROC_HESTON_QE_M) &&
         !(pr->rho >= -1.0 && pr->rho <= 1.0))
         return set_error(OPTP_E_ARG, "rho must be in [-1, 1].");
     if (pr->kind == OPTP_PROC_MERTON && (pr->v0 < 0.0 || pr->theta < 0.0))
         return set_error(OPTP_E_ARG, "lam and sJ must be non-negative.");
-    if (pr->kind == OPTP_PROC_HESTON_QE && !(pr->xi > 0.0 && pr->kappa > 0.0 && pr->theta > 0.0))
+    if ((pr->kind == OPTP_PROC_HESTON_QE || pr->kind == OPTP_PROC_HESTON_QE_M) &&
+        !(pr->xi > 0.0 && pr->kappa > 0.0 && pr->theta > 0.0))
         return set_error(OPTP_E_ARG, "the QE scheme needs xi > 0, kappa > 0 and theta > 0");
     if (pr->kind == OPTP_PROC_LV_MILSTEIN || pr->kind == OPTP_PROC_LV_EULER) {
         if (pr->n_nodes < 2 || !(pr->h > 0.0))
@@ -51,7 +52,8 @@ static void fill_args(PathArgs& a, const optp_process* pr, const optp_payoff* pa
     Context& c = ctx();
     const SigmaTableDev& tb = c.tables[table_slot];
     memset(&a, 0, sizeof(a));
-    a.proc = pr->kind;
+    a.proc = (pr->kind == OPTP_PROC_HESTON_QE_M) ? OPTP_PROC_HESTON_QE : pr->kind;
+    a.qe_martingale = (pr->kind == OPTP_PROC_HESTON_QE_M) ? 1 : 0;
     a.n_nodes = pr->n_nodes;
     a.S0 = pr->S0; a.r = pr->r; a.q = pr->q; a.T = pr->T; a.sigma = pr->sigma;
     a.v0 = pr->v0; a.kappa = pr->kappa; a.theta = pr->theta; a.xi = pr->xi; a.rho = pr->rho;

@@ -33,6 +33,7 @@ struct PathArgs {
     int anti;
     int use_philox;
     int rng_mode;  // RNG_* (optp_common.cuh); honoured by the fp32 GBM path kernel only
+    int qe_martingale;  // OPTP_PROC_HESTON_QE_M: proc = HESTON_QE with the martingale-corrected K0*
     unsigned long long seed, path_offset;
     const double* z;  // device, n_streams x n_steps x n_base (HOSTZ mode)
     int n_pay;
@@ -70,7 +71,8 @@ __host__ __device__ inline int observer_mask(const optp_payoff* p, int n) {
 
 __host__ __device__ inline int n_streams_of(int proc) {
     if (proc == OPTP_PROC_MERTON) return 3;
-    return (proc == OPTP_PROC_HESTON_FTE || proc == OPTP_PROC_SABR || proc == OPTP_PROC_HESTON_QE) ? 2
+    return (proc == OPTP_PROC_HESTON_FTE || proc == OPTP_PROC_SABR || proc == OPTP_PROC_HESTON_QE ||
+            proc == OPTP_PROC_HESTON_QE_M) ? 2
                                                                                                   : 1;
 }
 

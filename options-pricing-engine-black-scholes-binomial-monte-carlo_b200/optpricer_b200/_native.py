@@ -21,7 +21,7 @@ MAX_PAYOFFS = 16
 
 # process kinds / payoff kinds / flags / modes -- mirror include/optp_b200.h
 (PROC_GBM, PROC_HESTON_FTE, PROC_LV_MILSTEIN, PROC_LV_EULER, PROC_GBM_MILSTEIN, PROC_SABR, PROC_HESTON_QE,
- PROC_MERTON) = range(8)
+ PROC_MERTON, PROC_HESTON_QE_M) = range(9)
 PAY_VANILLA, PAY_DIGITAL, PAY_BARRIER, PAY_ASIAN, PAY_LOOKBACK = range(5)
 F_CALL, F_UP, F_IN, F_GEOMETRIC, F_FLOATING = 1, 2, 4, 8, 16
 MODE_FP32_PHILOX, MODE_FP64_PHILOX, MODE_FP64_HOSTZ = 0, 1, 2

@@ -197,7 +197,7 @@ def _expected_y(paths, r, T):
     pr = paths.proc
     kind = pr["kind"]
     rq = pr["r"] - pr["q"]
-    if kind == nv.PROC_HESTON_QE and not pr.get("martingale", False):
+    if kind == nv.PROC_HESTON_QE:
         raise ValueError("control_variate needs E[S_T] of the discretised process; the QE scheme has it only "
                          "with the martingale correction (heston_paths(..., scheme='qe', martingale_correction=True))")
     euler_in_S = kind in (nv.PROC_GBM_MILSTEIN, nv.PROC_LV_MILSTEIN) or (kind == nv.PROC_SABR and pr["kappa"] != 1.0)

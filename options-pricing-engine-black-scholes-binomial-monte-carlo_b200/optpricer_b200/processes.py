@@ -163,7 +163,8 @@ class LazyPaths:
     def n_streams(self):
         if self.proc["kind"] == nv.PROC_MERTON:
             return 3
-        return 2 if self.proc["kind"] in (nv.PROC_HESTON_FTE, nv.PROC_SABR, nv.PROC_HESTON_QE) else 1
+        return 2 if self.proc["kind"] in (nv.PROC_HESTON_FTE, nv.PROC_SABR, nv.PROC_HESTON_QE,
+                                          nv.PROC_HESTON_QE_M) else 1
 
     def native_process(self):
         p = nv.OptpProcess()
@@ -239,11 +240,14 @@ def gbm_milstein_paths(S0, r, q, sigma, T, n_steps, n_paths, *, antithetic=True,
 
 
 def heston_paths(S0, r, q, v0, kappa, theta, xi, rho, T, n_steps, n_paths, *, antithetic=True,
-                 seed=None, return_variance=False, rng="philox", mode="fp32", scheme="fte"):
+                 seed=None, return_variance=False, rng="philox", mode="fp32", scheme="fte",
+                 martingale_correction=False):
     """Heston paths (processes.py:117-162).  return_variance=True materialises.
     scheme="fte": the reference's full-truncation Euler (default, drop-in).
     scheme="qe":  Andersen's quadratic-exponential scheme -- NEW, the reference has no such code
-                  (parity unpinned; checked against oracle/path_schemes.py:heston_qe)."""
+                  (parity unpinned; checked against oracle/path_schemes.py:heston_qe).
+                  martingale_correction=True uses Andersen's K0* (2008, sec. 4.3.2), which makes
+                  E[S_T] = S0 e^{(r-q)T} exact for the discretised process -- what control_variate=True needs."""
     _check_sizes(n_steps, n_paths)
     if not (-1.0 <= rho <= 1.0):
         raise ValueError("rho must be in [-1, 1].")
@@ -251,7 +255,9 @@ def heston_paths(S0, r, q, v0, kappa, theta, xi, rho, T, n_steps, n_paths, *, an
         raise ValueError("scheme must be 'fte' or 'qe'")
     if scheme == "qe" and not (xi > 0 and kappa > 0 and theta > 0):
         raise ValueError("the QE scheme needs xi > 0, kappa > 0 and theta > 0")
-    kind = nv.PROC_HESTON_FTE if scheme == "fte" else nv.PROC_HESTON_QE
+    if martingale_correction and scheme != "qe":
+        raise ValueError("martingale_correction belongs to scheme='qe'")
+    kind = nv.PROC_HESTON_FTE if scheme == "fte" else (nv.PROC_HESTON_QE_M if martingale_correction else nv.PROC_HESTON_QE)
     proc = dict(kind=kind, S0=S0, r=r, q=q, T=T, v0=v0, kappa=kappa, theta=theta, xi=xi, rho=rho)
     lp = LazyPaths(proc, n_steps, n_paths, antithetic, seed, rng, mode)
     if return_variance:

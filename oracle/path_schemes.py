@@ -71,14 +71,20 @@ def heston_fte(z2_base, zp_base, *, S0, r, q, v0, kappa, theta, xi, rho, T,
 
 
 def heston_qe(z2_base, zp_base, *, S0, r, q, v0, kappa, theta, xi, rho, T, antithetic=True,
-              psi_c=1.5, return_variance=False):
+              psi_c=1.5, return_variance=False, martingale_correction=False):
     """Heston quadratic-exponential scheme -- PARITY UNPINNED: the reference has no QE code
     (processes.py:117-162 is full-truncation Euler only; README.md:42 merely mentions QE).  This
     restates Andersen, "Simple and efficient simulation of the Heston stochastic volatility model"
     (J. Comp. Finance 11(3), 2008), sec. 3.2.4 / 4.2: moment-matched quadratic (psi <= psi_c) or
     exponential (psi > psi_c) variance update, central discretisation gamma1 = gamma2 = 1/2 of the
-    log-price, no martingale correction.  It consumes the same two normal streams as heston_fte
-    (Z2 drives the variance -- its uniform Phi(Z2) feeds the exponential branch -- Zp the price)."""
+    log-price.  It consumes the same two normal streams as heston_fte (Z2 drives the variance -- its uniform
+    Phi(Z2) feeds the exponential branch -- Zp the price).
+    martingale_correction=True replaces K0 by Andersen's K0* (sec. 4.3.2, eqs. 4.14-4.16):
+        K0* = -ln M - (K1 + K3/2) v,   M = E[exp(A v') | v],   A = K2 + K4/2   (K4 = K3 here),
+        quadratic branch:   M = exp(A b^2 a / (1 - 2 A a)) / sqrt(1 - 2 A a)     (needs A < 1/(2a))
+        exponential branch: M = p + beta (1 - p) / (beta - A)                    (needs A < beta)
+    so that E[S' e^{-(r-q) dt} | S, v] = S exactly; where the regularity condition fails (it cannot for
+    rho <= 0) the uncorrected K0 is kept for that path and step."""
     from scipy.special import erfc
     n_steps = z2_base.shape[0]
     dt = T / n_steps
@@ -113,7 +119,19 @@ def heston_qe(z2_base, zp_base, *, S0, r, q, v0, kappa, theta, xi, rho, T, antit
         with np.errstate(divide="ignore", invalid="ignore"):
             ve = np.where(u <= p, 0.0, np.log((1.0 - p) / one_minus_u) / beta)
         vn = np.where(psi <= psi_c, vq, ve)
-        X[i + 1] = X[i] + (r - q) * dt + K0 + K1 * v + K2 * vn + np.sqrt(np.maximum(K3 * (v + vn), 0.0)) * zp[i]
+        k0 = K0 + K1 * v
+        if martingale_correction:
+            A = K2 + 0.5 * K3
+            with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+                den_q = 1.0 - 2.0 * A * a
+                lnM_q = A * b2 * a / den_q - 0.5 * np.log(den_q)
+                den_e = beta - A
+                lnM_e = np.log(p + beta * (1.0 - p) / den_e)
+            quad = psi <= psi_c
+            ok = np.where(quad, den_q > 0.0, den_e > 0.0)
+            lnM = np.where(quad, lnM_q, lnM_e)
+            k0 = np.where(ok, -lnM - 0.5 * K3 * v, k0)
+        X[i + 1] = X[i] + (r - q) * dt + k0 + K2 * vn + np.sqrt(np.maximum(K3 * (v + vn), 0.0)) * zp[i]
         v = vn
         V[i + 1] = v
     S = np.exp(X)

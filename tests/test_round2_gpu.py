@@ -201,3 +201,100 @@ def test_crr_vec_many_strikes_on_one_tree(op):
     mixed = op.crr_vec(100.0, strikes, 1.0, 0.03, 0.01, 0.2, kinds, N=1000, american=True)
     want = crr_tree.crr_shared_tree(100.0, strikes[pick], 1.0, 0.03, 0.01, 0.2, kinds[pick], N=1000, american=True)
     np.testing.assert_allclose(mixed[pick], want, rtol=1e-10, atol=1e-10)
+
+
+# ------------------------------------------------------------------ Heston QE (no reference code: parity unpinned)
+QE_CASES = [dict(S0=100.0, r=0.05, q=0.0, v0=0.04, kappa=2.0, theta=0.04, xi=0.3, rho=-0.7, T=1.0),
+            dict(S0=100.0, r=0.02, q=0.01, v0=0.09, kappa=1.5, theta=0.04, xi=0.9, rho=-0.5, T=0.5)]
+
+
+def _qe_grid():
+    """20 (kappa, theta, xi, v0, dt) points: both branches of the scheme, Feller-satisfying (2 kappa theta >= xi^2)
+    and Feller-violating sets, v0 from far below to far above theta."""
+    g = []
+    for kappa, theta, xi in ((2.0, 0.04, 0.3), (1.5, 0.04, 0.9), (0.5, 0.09, 1.0), (4.0, 0.02, 0.5), (0.3, 0.04, 0.6)):
+        for v0, dt in ((0.25 * theta, 1.0 / 12), (theta, 1.0 / 50), (4.0 * theta, 1.0 / 4), (0.01 * theta, 1.0 / 12)):
+            g.append((kappa, theta, xi, v0, dt))
+    return g
+
+
+@pytest.mark.parametrize("block", [0, 1, 2, 3])
+def test_heston_qe_variance_step_has_the_exact_cir_moments(op, block):
+    """One QE step of the variance from a fixed v0 against the exact conditional mean and variance of the CIR
+    process (Andersen 2008, eqs. 17-18) -- the two moments the scheme is built to match -- over a 20-point grid
+    (5 per block); 4e7 effective paths per point, bar 1e-3 relative (or 4 sampling standard errors if wider)."""
+    from optpricer_b200 import processes as pr
+    n = 20_000_000
+    for kappa, theta, xi, v0, dt in _qe_grid()[5 * block:5 * block + 5]:
+        _, V = pr.heston_paths(100.0, 0.03, 0.0, v0, kappa, theta, xi, -0.5, dt, 1, n, seed=17, scheme="qe",
+                               return_variance=True)
+        v1 = V[1]
+        E = math.exp(-kappa * dt)
+        m = theta + (v0 - theta) * E
+        s2 = v0 * xi * xi * E * (1.0 - E) / kappa + theta * xi * xi * (1.0 - E) ** 2 / (2.0 * kappa)
+        assert (v1 >= 0.0).all()
+        mean = float(v1.mean())
+        d = v1 - mean
+        var = float((d * d).mean())
+        m4 = float((d ** 4).mean())
+        se_mean = math.sqrt(var / v1.size)
+        se_var = math.sqrt(max(m4 - var * var, 0.0) / v1.size)
+        feller = 2.0 * kappa * theta >= xi * xi
+        assert abs(mean - m) <= max(1e-3 * m, 4.0 * se_mean), (kappa, theta, xi, v0, dt, feller, mean, m, se_mean)
+        assert abs(var - s2) <= max(1e-3 * s2, 4.0 * se_var), (kappa, theta, xi, v0, dt, feller, var, s2, se_var)
+        del V, v1, d
+
+
+def test_heston_qe_martingale_correction(op):
+    """K0* (Andersen 2008, sec. 4.3.2): with coarse steps, strong correlation and high vol-of-vol the plain scheme
+    misses E[S_T] by many standard errors; the corrected one does not -- fp64 and fp32 kernels; the fp64 kernel
+    equals the numpy restatement on the same normals; and the control variate becomes available."""
+    from optpricer_b200 import exotics as ex, processes as pr
+    from oracle import path_schemes, payoffs
+    c = dict(S0=100.0, r=0.0, q=0.0, v0=0.04, kappa=0.5, theta=0.04, xi=1.0, rho=-0.9, T=10.0)
+    spec = [ex.vanilla_spec(100.0, "call")]
+
+    def mean_y(mart, mode):
+        lp = pr.heston_paths(n_steps=10, n_paths=4_000_000, seed=2, scheme="qe", martingale_correction=mart, mode=mode, **c)
+        s, _, _ = ex.path_stats(lp, spec, 0.0, c["T"])
+        n, sy, syy = s[0][0], s[0][3], s[0][4]
+        my = sy / n
+        return my, math.sqrt(max(syy / n - my * my, 0.0) / n)
+
+    for mode in ("fp32", "fp64"):
+        plain, se = mean_y(False, mode)
+        fixed, se2 = mean_y(True, mode)
+        assert abs(plain - 100.0) > 10.0 * se, (mode, plain, se)
+        assert abs(fixed - 100.0) <= 4.0 * se2, (mode, fixed, se2)
+    # check mode against the restatement, both branches active
+    for case in (QE_CASES[1], c):
+        lp = pr.heston_paths(n_steps=12, n_paths=3000, seed=5, rng="numpy", scheme="qe", martingale_correction=True, **case)
+        z2, zp = path_schemes.draw_normals(5, 12, 3000, 2)
+        ref = path_schemes.heston_qe(z2, zp, martingale_correction=True, **case)
+        np.testing.assert_allclose(np.asarray(lp), ref, rtol=1e-11)
+        plain = path_schemes.heston_qe(z2, zp, martingale_correction=False, **case)
+        assert np.max(np.abs(ref[-1] / plain[-1] - 1.0)) > 1e-6
+    # fp32 tracks fp64 on the same draws, and the control variate is accepted (and helps)
+    lp32 = pr.heston_paths(n_steps=32, n_paths=400_000, seed=3, scheme="qe", martingale_correction=True, **QE_CASES[1])
+    lp64 = pr.heston_paths(n_steps=32, n_paths=400_000, seed=3, scheme="qe", martingale_correction=True, mode="fp64", **QE_CASES[1])
+    a = ex.price_payoffs(lp32, spec, 0.02, 0.5)[0]
+    b = ex.price_payoffs(lp64, spec, 0.02, 0.5)[0]
+    assert abs(a[0] - b[0]) <= 0.1 * b[1], (a, b)
+    cv = ex.price_payoffs(lp32, spec, 0.02, 0.5, control_variate=True)[0]
+    assert cv[1] < 0.8 * a[1] and abs(cv[0] - a[0]) <= 4.0 * a[1]
+
+
+@pytest.mark.parametrize("case", [0, 1])
+@pytest.mark.parametrize("n_steps", [64, 128])
+def test_heston_qe_against_the_semi_analytic_price_without_an_allowance(op, case, n_steps):
+    """Martingale-corrected QE at 64 / 128 steps, 1.6e7 effective paths: the vanilla call within 4 of the run's own
+    standard errors of the semi-analytic Heston price -- no discretisation allowance (round 1 granted 0.02)."""
+    from optpricer_b200 import exotics as ex, processes as pr
+    from test_oracle_cpu import heston_call_semi_analytic
+    c = QE_CASES[case]
+    exact = heston_call_semi_analytic(c["S0"], 100.0, c["T"], c["r"], c["q"], c["v0"], c["kappa"], c["theta"], c["xi"], c["rho"])
+    lp = pr.heston_paths(n_steps=n_steps, n_paths=8_000_000, seed=11 + n_steps, scheme="qe", martingale_correction=True, **c)
+    plain = ex.price_payoffs(lp, [ex.vanilla_spec(100.0, "call")], c["r"], c["T"])[0]
+    cv = ex.price_payoffs(lp, [ex.vanilla_spec(100.0, "call")], c["r"], c["T"], control_variate=True)[0]
+    assert abs(plain[0] - exact) <= 4.0 * plain[1], (plain, exact)
+    assert abs(cv[0] - exact) <= 4.0 * cv[1] + 1e-3, (cv, exact)
