@@ -653,20 +653,31 @@ def main():
                           "value": rate, "unit": "path-steps/s/GPU", "ms": ms,
                           "fp32_pipe_frac": rate * OPS_PER_PATH_STEP["terminal"] / (N_SM * FP32_LANES * 1965.0e6),
                           "price": pt[0], "stderr": pt[1]})
-        # opt-in generator modes of the headline kernel (default stays Philox4x32-10, 4 normals per call)
+        # opt-in generator modes (default stays Philox4x32-10, 4 normals per call): headline kernel and cfg-4 kernel
+        hout = torch.zeros(nv.NSTATS, dtype=torch.float64, device=dev)
+        hpay = ex._native_payoffs([ex.asian_spec(100.0, "call")], 0.05, 1.0)
+        nbh = 1 << 25
+
+        def heston_step_():
+            nv.check(lib.optp_mc_path_dev(C.byref(hp), hpay, 1, 365, nbh, 1, nv.MODE_FP32_PHILOX, 42, rank * nbh, None, None,
+                                          None, C.c_void_p(hout.data_ptr()), sptr), "optp_mc_path_dev")
         for mode_id, label in ((1, "rng_mode 1: Philox4x32-7"), (2, "rng_mode 2: Philox4x32-10, three Box-Muller pairs "
                                                                     "of (26-bit radius, 16/16/18-bit angle) per call")):
             nv.set_option("rng_mode", mode_id)
             try:
                 msr = timed(lambda: mc_step(3), reps=2)
                 sr = stats_t.cpu().numpy()
+                msh = timed(heston_step_, reps=2)
+                sh = hout.cpu().numpy()
             finally:
                 nv.set_option("rng_mode", 0)
             pr_ = ex.estimate(sr)
-            workloads.append({"workload": f"headline GBM+barrier kernel, OPT-IN {label} (tests/test_production_scale_gpu.py "
-                                          "::test_device_normals_quality holds its statistical price)",
+            ph_ = ex.estimate(sh, control_variate=True, expected_y=100.0)
+            workloads.append({"workload": f"OPT-IN {label}: headline GBM+barrier kernel / cfg4 Heston FTE+Asian kernel "
+                                          "(tests/test_production_scale_gpu.py::test_device_normals_quality holds the statistical price)",
                               "value": 2.0 * n_base * MC_STEPS / (msr * 1e-3), "unit": "path-steps/s/GPU", "ms": msr,
-                              "price": pr_[0], "stderr": pr_[1]})
+                              "price": pr_[0], "stderr": pr_[1],
+                              "heston_value": 2.0 * nbh * 365 / (msh * 1e-3), "heston_price": ph_[0], "heston_stderr": ph_[1]})
         # cfg 5 at BASELINE size: 10k-contract book (1/3 European, 1/3 barrier, 1/3 arithmetic Asian)
         # through price_book, 5e6 base paths (1e7 effective) per contract; items are dealt over the ranks
         from optpricer_b200 import book as bk

@@ -15,8 +15,10 @@
  *   - the library keeps no pointer after a call returns.
  *   - threads: the library owns ONE context per process (stream, reduction scratch, staging
  *     arenas); every entry point takes a process-wide lock, so concurrent calls from several
- *     host threads are serialised, never interleaved.  The _dev variants share the reduction
- *     scratch too: queue them on ONE stream at a time (or order the streams with events).
+ *     host threads are serialised, never interleaved (the lock covers the host side of a call: the
+ *     _dev variants return once their kernels are queued).  Monte Carlo launches take the 8 slots of the
+ *     reduction scratch round-robin, so _dev launches queued on up to 8 different streams overlap on the
+ *     device; the CRR _dev entry point uses one work-list scratch: one stream at a time.
  *   - no CPU fallback exists: without a usable CUDA device every compute entry
  *     point returns a negative status.
  */
@@ -118,7 +120,7 @@ uint64_t optp_launch_count(void);
  *   "crr_band_kernel" 2 = two-zone banded kernel (default), 1 = the earlier single-zone banded kernel
  *   "crr_zone_group"  options per warp of the two-zone kernel: 1, 2, 4, or 0 = by batch size (default);
  *                   prices are bit-identical for every setting
- *   "rng_mode"      generator mode of the fp32 GBM path kernel: 0 = Philox4x32-10, two Box-Muller pairs of
+ *   "rng_mode"      generator mode of the fp32 GBM and Heston (FTE) path kernels: 0 = Philox4x32-10, two Box-Muller pairs of
  *                   (32-bit radius, 32-bit angle) per call (default; every parity statement is made for it),
  *                   1 = Philox4x32-7, same mapping, 2 = Philox4x32-10 with three Box-Muller pairs of
  *                   (26-bit radius, 16/16/18-bit angle) per call (6 normals; tails end at 6.1 sigma).

@@ -188,11 +188,33 @@ struct LogState {  // one effective path in log2 space
     float x = 0.f, xmax = 0.f, xmin = 0.f, sum = 0.f, slog = 0.f;
 };
 
+#ifdef OPTP_POLY_EX2
+// A/B experiment (task 5): 2^x on the FMA pipe instead of MUFU.EX2 -- magic-number rounding, a
+// degree-5 polynomial on [-1/2, 1/2] and an exponent add: 3 FADD + 5 FFMA + SHL + IADD against one MUFU issue.
+// Measured on B200 (scripts/mc_ab.py, Heston FTE + Asian): see DESIGN.md section 4 -- the kernel is bound by the
+// issue rate, not by the XU pipe, so trading one MUFU for ten FMA-pipe instructions makes it slower.
+__device__ __forceinline__ float poly_ex2(float x) {
+    const float t = x + 12582912.0f;
+    const float n = t - 12582912.0f;
+    const float f = x - n;
+    float p = 1.3333558e-3f;
+    p = fmaf(p, f, 9.6181291e-3f);
+    p = fmaf(p, f, 5.5504109e-2f);
+    p = fmaf(p, f, 2.4022651e-1f);
+    p = fmaf(p, f, 6.9314718e-1f);
+    p = fmaf(p, f, 1.0f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+#define OPTP_OBS_EX2(x) poly_ex2(x)
+#else
+#define OPTP_OBS_EX2(x) mufu_ex2(x)
+#endif
+
 template <int MASK>
 __device__ __forceinline__ void observe_log(LogState& s) {
     if (MASK & M_MAX) s.xmax = fmaxf(s.xmax, s.x);
     if (MASK & M_MIN) s.xmin = fminf(s.xmin, s.x);
-    if (MASK & M_SUM) s.sum += mufu_ex2(s.x);
+    if (MASK & M_SUM) s.sum += OPTP_OBS_EX2(s.x);
     if (MASK & M_LOG) s.slog += s.x;
 }
 
@@ -504,18 +526,18 @@ __global__ void __launch_bounds__(256, (PROC == OPTP_PROC_HESTON_FTE || PROC == 
         } else if (PROC == OPTP_PROC_HESTON_FTE) {
             LogState p, m;
             float vp = fmaxf((float)a.v0, 0.f), vm = vp;
-            uint4 w = philox_words(a.seed, gpath, 0u, 0u);
+            uint4 w = philox_words_m<RNG>(a.seed, gpath, 0u, 0u);
 #pragma unroll 1
             for (unsigned int c = 0; c < n_full; ++c) {
-                const uint4 wn = philox_words(a.seed, gpath, c + 1, 0u);
-                normals_from_words_scaled(w, k.h_bm, z);
-                heston_step<MASK, ANTI>(p, m, vp, vm, z[0], z[1], k);
-                heston_step<MASK, ANTI>(p, m, vp, vm, z[2], z[3], k);
+                const uint4 wn = philox_words_m<RNG>(a.seed, gpath, c + 1, 0u);
+                normals_from_words_m<RNG>(w, k.h_bm, z);  // (RNG = 0: the words and normals of normals_from_words_scaled)
+#pragma unroll
+                for (int j = 0; j < kPerCall; ++j) heston_step<MASK, ANTI>(p, m, vp, vm, z[2 * j], z[2 * j + 1], k);
                 w = wn;
             }
             if (n_tail) {
-                normals_from_words_scaled(w, k.h_bm, z);
-                heston_step<MASK, ANTI>(p, m, vp, vm, z[0], z[1], k);
+                normals_from_words_m<RNG>(w, k.h_bm, z);
+                for (unsigned int j = 0; j < n_tail; ++j) heston_step<MASK, ANTI>(p, m, vp, vm, z[2 * j], z[2 * j + 1], k);
             }
             ep = finish_log<MASK>(p, S0, inv_n);
             if (ANTI) em = finish_log<MASK>(m, S0, inv_n);
@@ -702,11 +724,15 @@ __device__ __forceinline__ void lvm_step_win(LinState& s, const float4* row, con
     const float4 e = LDG ? __ldg(row + j + 2) : row[j + 2];
     float sig = fmaf(f, e.y, e.x);
     // sigma at x + c_up (c_up in (0,1)):  v_j + min(tu,1) s_j + max(tu-1,0) s_{j+1}
+    // (max(tu-1, 0) = tu - min(tu, 1) and min(td, 0) = td - max(td, 0), bit for bit: one FMNMX + one FADD per
+    // bumped lookup instead of two FMNMX + one FADD)
     const float tu = f + k.c_up;
-    const float sig_up = fmaf(fmaxf(tu - 1.0f, 0.0f), e.z, fmaf(fminf(tu, 1.0f), e.y, e.x));
+    const float tu1 = fminf(tu, 1.0f);
+    const float sig_up = fmaf(tu - tu1, e.z, fmaf(tu1, e.y, e.x));
     // sigma at x + c_dn (c_dn in (-1,0)): v_j + max(td,0) s_j + min(td,0) s_{j-1}
     const float td = f + k.c_dn;
-    const float sig_dn = fmaf(fminf(td, 0.0f), e.w, fmaf(fmaxf(td, 0.0f), e.y, e.x));
+    const float td0 = fmaxf(td, 0.0f);
+    const float sig_dn = fmaf(td - td0, e.w, fmaf(td0, e.y, e.x));
     // processes.py:361-362 clips sigma to [1e-8, 10]; a table whose nodes all lie inside that range (every
     // Dupire table: calibration.py:355 clips to [0.01, 5]) cannot leave it by linear interpolation
     if (CLIP) sig = fminf(fmaxf(sig, 1e-8f), 10.0f);
@@ -793,13 +819,13 @@ __global__ void __launch_bounds__(kLvThreads, 4) lv_fp32_kernel(PathArgs a, int 
     // row length: (value, slope) table padded to an even node count; window table n + 4 nodes
     const int n_ld = WIN ? a.n_nodes + 4 : ((a.n_nodes + 1) & ~1);
 
-    // Staging of the table rows, selectable at compile time:
-    //   OPTP_LV_TMA=0 (default; measured 8 % faster on B200, 448 vs 412 G path-steps/s on config 3):
-    //     the CTA copies one 32 KB chunk itself between two __syncthreads;
-    //   OPTP_LV_TMA=1: the TMA unit (cp.async.bulk + mbarrier) fills one of two 16 KB buffers while
-    //     the CTA walks the other; a buffer is re-armed by thread 0 after the __syncthreads that ends
-    //     its chunk.  Chunks are numbered globally (across slabs) so the mbarrier phase of buffer b
-    //     is (use count of b) & 1.
+    // Staging of the table rows, selectable at compile time (OPTP_LV_TMA, default 1):
+    //   OPTP_LV_TMA=1 (default): the TMA unit (cp.async.bulk + mbarrier) fills one of two ~36 KB buffers while
+    //     the CTA walks the other; a buffer is re-armed by thread 0 after the __syncthreads that ends its chunk.
+    //     Chunks are numbered globally (across slabs) so the mbarrier phase of buffer b is (use count of b) & 1.
+    //     Measured on B200, config 3: 4.9e11 path-steps/s against 4.5e11 for the copy loop below (no LDG -> STS
+    //     instructions in the issue stream, one barrier per chunk instead of two).
+    //   OPTP_LV_TMA=0: the CTA copies one chunk itself between two __syncthreads (kept for A/B runs).
     __shared__ __align__(8) uint64_t full_bar[2];
     const unsigned int n_chunks = (n_steps + rows_per_chunk - 1) / rows_per_chunk;
     const unsigned int row_bytes = (unsigned int)n_ld * (unsigned int)sizeof(Node);
@@ -1039,7 +1065,7 @@ template <int PROC, int MASK, bool ANTI, int RNG = RNG_PHILOX10>
 static int launch_generic(const PathArgs& a, cudaStream_t st) {
     const int threads = 256;
     const size_t smem = sizeof(double) * (3 + 3 * a.n_pay) * threads;
-    if constexpr (PROC == OPTP_PROC_GBM && RNG == RNG_PHILOX10) {  // opt-in generator modes (GBM only)
+    if constexpr ((PROC == OPTP_PROC_GBM || PROC == OPTP_PROC_HESTON_FTE) && RNG == RNG_PHILOX10) {  // opt-in generator modes
         if (a.rng_mode == RNG_PHILOX7) return launch_generic<PROC, MASK, ANTI, RNG_PHILOX7>(a, st);
         if (a.rng_mode == RNG_PHILOX10_X6) return launch_generic<PROC, MASK, ANTI, RNG_PHILOX10_X6>(a, st);
     }

@@ -388,8 +388,11 @@ int launch_payoff_from_paths(const double* paths, unsigned long long n_rows,
     const unsigned long long cap = (unsigned long long)c.n_sm * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
+    double* partials;
+    unsigned int* ticket;
+    reduction_scratch(&partials, &ticket);
     payoff_from_paths_kernel<<<(unsigned int)blocks, 128, sizeof(double) * 6 * 128, st>>>(
-        paths, n_rows, n_cols, pay, payoff_out, c.partials, c.ticket, stats);
+        paths, n_rows, n_cols, pay, payoff_out, partials, ticket, stats);
     c.launches++;
     OPTP_CUDA(cudaGetLastError());
     return 0;

@@ -71,8 +71,7 @@ static void fill_args(PathArgs& a, const optp_process* pr, const optp_payoff* pa
     a.path_offset = path_offset;
     a.n_pay = (int)n_pay;
     for (uint32_t i = 0; i < n_pay; ++i) a.pay[i] = pay[i];
-    a.partials = c.partials;
-    a.ticket = c.ticket;
+    reduction_scratch(&a.partials, &a.ticket);
 }
 
 static int upload_table(const double* table, uint32_t n_steps, uint32_t n_nodes, int slot = 0) {
@@ -189,8 +188,7 @@ int optp_mc_terminal_dev(double S0, double K, double T, double r, double q, doub
     a.seed = seed;
     a.path_offset = path_offset;
     a.z = z_dev;
-    a.partials = c.partials;
-    a.ticket = c.ticket;
+    reduction_scratch(&a.partials, &a.ticket);
     a.stats = stats_dev;
     if (mode == OPTP_MODE_FP32_PHILOX) return launch_terminal_fp32(a, (cudaStream_t)stream);
     if (mode == OPTP_MODE_FP64_PHILOX || mode == OPTP_MODE_FP64_HOSTZ)

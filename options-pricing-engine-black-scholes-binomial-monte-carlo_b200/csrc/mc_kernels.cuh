@@ -32,7 +32,7 @@ struct PathArgs {
     unsigned long long n_base;
     int anti;
     int use_philox;
-    int rng_mode;  // RNG_* (optp_common.cuh); honoured by the fp32 GBM path kernel only
+    int rng_mode;  // RNG_* (optp_common.cuh); honoured by the fp32 GBM and Heston FTE path kernels
     int qe_martingale;  // OPTP_PROC_HESTON_QE_M: proc = HESTON_QE with the martingale-corrected K0*
     unsigned long long seed, path_offset;
     const double* z;  // device, n_streams x n_steps x n_base (HOSTZ mode)

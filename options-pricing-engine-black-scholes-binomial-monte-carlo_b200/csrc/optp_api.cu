@@ -61,6 +61,12 @@ int host_arena_reserve(Arena& a, size_t bytes) {
     return 0;
 }
 
+void reduction_scratch(double** partials, unsigned int** ticket) {
+    const unsigned int slot = g_ctx.reduce_slot++ % (unsigned int)kReduceSlots;
+    *partials = g_ctx.partials + (size_t)slot * kMaxBlocks * kMaxVals;
+    *ticket = g_ctx.ticket + slot;
+}
+
 int require_ready() {
     if (!g_ctx.ready) return set_error(OPTP_E_NOINIT, "optp_init() has not been called");
     return 0;
@@ -107,9 +113,9 @@ static int init_resources(Context& c, int device) {
     c.device = device;
     c.n_sm = prop.multiProcessorCount;
     OPTP_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-    OPTP_CUDA(cudaMalloc(&c.partials, sizeof(double) * (size_t)kMaxBlocks * kMaxVals));
-    OPTP_CUDA(cudaMalloc(&c.ticket, sizeof(unsigned int)));
-    OPTP_CUDA(cudaMemset(c.ticket, 0, sizeof(unsigned int)));
+    OPTP_CUDA(cudaMalloc(&c.partials, sizeof(double) * (size_t)kReduceSlots * kMaxBlocks * kMaxVals));
+    OPTP_CUDA(cudaMalloc(&c.ticket, sizeof(unsigned int) * kReduceSlots));
+    OPTP_CUDA(cudaMemset(c.ticket, 0, sizeof(unsigned int) * kReduceSlots));
     OPTP_CUDA(cudaMalloc(&c.stats_dev, sizeof(double) * kMaxPayoffs * OPTP_NSTATS));
     OPTP_CUDA(cudaHostAlloc(&c.stats_host, sizeof(double) * kMaxPayoffs * OPTP_NSTATS,
                             cudaHostAllocDefault));

@@ -34,8 +34,9 @@ struct Context {
     cudaStream_t stream4 = nullptr;  // the kernels of its odd slices (even slices: `stream`)
     cudaEvent_t events[384] = {};    // its per-slice events (copy-in done, kernels done, copy-out done)
     int n_events = 0;
-    double* partials = nullptr;   // [kMaxBlocks][kMaxVals]
-    unsigned int* ticket = nullptr;
+    double* partials = nullptr;   // [kReduceSlots][kMaxBlocks][kMaxVals]
+    unsigned int* ticket = nullptr;  // [kReduceSlots]
+    unsigned int reduce_slot = 0;    // next slot of the reduction scratch (reduction_scratch())
     double* stats_dev = nullptr;  // kMaxPayoffs * OPTP_NSTATS
     double* stats_host = nullptr; // pinned mirror
     Arena in0, in1, out0, out1;
@@ -54,13 +55,16 @@ struct Context {
     int crr_zone_group = 0;    // two-zone kernel: options per warp (1, 2, 4); 0 = by batch size
     bool crr_count_ops = false;  // "crr_count_ops": the two-zone kernel counts its executed level-loop work
     unsigned long long* crr_op_count = nullptr;  // device {FP64 lane-instructions, node updates}
-    int rng_mode = 0;          // "rng_mode": generator mode of the fp32 GBM path kernel (RNG_*), default Philox4x32-10 x 4 normals
+    int rng_mode = 0;          // "rng_mode": generator mode of the fp32 GBM / Heston FTE path kernels (RNG_*), default Philox4x32-10 x 4 normals
 };
 
 constexpr int kMaxEvents = 384;
 constexpr int kMaxPayoffs = 16;
 constexpr int kMaxBlocks = 148 * 16;
 constexpr int kMaxVals = 3 * kMaxPayoffs + 4;
+// Monte Carlo launches take the slots of the reduction scratch (block partials + ticket) round-robin, so up to
+// kReduceSlots launches may be in flight on DIFFERENT streams at once; launches on one stream are ordered anyway.
+constexpr int kReduceSlots = 8;
 
 Context& ctx();
 int set_error(int code, const char* fmt, ...);
@@ -68,6 +72,8 @@ int cuda_fail(cudaError_t e, const char* what);
 int arena_reserve(Arena& a, size_t bytes);
 int host_arena_reserve(Arena& a, size_t bytes);  // pinned host memory (cudaHostAlloc), grow-only
 int require_ready();
+// the block-partial buffer and ticket of the next Monte Carlo launch (callers hold the API lock)
+void reduction_scratch(double** partials, unsigned int** ticket);
 
 // The library keeps ONE context (stream, reduction scratch, staging arenas): every C-ABI entry point
 // holds this lock for its whole duration, so calls from several host threads are serialised instead
@@ -138,7 +144,7 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1
     return philox4x32<10>(c0, c1, c2, c3, k0, k1);
 }
 
-// Opt-in generator modes of the fused GBM kernel (optp_set_option("rng_mode", m)); the default is 0 and
+// Opt-in generator modes of the fused GBM and Heston FTE kernels (optp_set_option("rng_mode", m)); the default is 0 and
 // every parity statement in DESIGN.md is made for it.
 //   0  Philox4x32-10, two Box-Muller pairs of (32-bit radius, 32-bit angle) per call  -> 4 normals
 //   1  Philox4x32-7 (the smallest round count Salmon et al. report as Crush-resistant), same mapping

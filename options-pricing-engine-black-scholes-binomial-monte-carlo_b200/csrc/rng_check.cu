@@ -122,15 +122,18 @@ int optp_normal_stats(uint64_t seed, uint64_t path_offset, uint64_t n_paths, uin
     const unsigned long long cap = (unsigned long long)c.n_sm * 8;
     if (blocks > cap) blocks = cap;
     const unsigned int grid = (unsigned int)blocks;
+    double* partials;
+    unsigned int* ticket;
+    reduction_scratch(&partials, &ticket);
     if (rng_mode == RNG_PHILOX7)
-        normal_stats_kernel<RNG_PHILOX7><<<grid, 256, 0, c.stream>>>(seed, path_offset, n_paths, n_blocks, c.partials,
-                                                                     c.ticket, max_bits, out);
+        normal_stats_kernel<RNG_PHILOX7><<<grid, 256, 0, c.stream>>>(seed, path_offset, n_paths, n_blocks, partials,
+                                                                     ticket, max_bits, out);
     else if (rng_mode == RNG_PHILOX10_X6)
         normal_stats_kernel<RNG_PHILOX10_X6><<<grid, 256, 0, c.stream>>>(seed, path_offset, n_paths, n_blocks,
-                                                                         c.partials, c.ticket, max_bits, out);
+                                                                         partials, ticket, max_bits, out);
     else
-        normal_stats_kernel<RNG_PHILOX10><<<grid, 256, 0, c.stream>>>(seed, path_offset, n_paths, n_blocks, c.partials,
-                                                                      c.ticket, max_bits, out);
+        normal_stats_kernel<RNG_PHILOX10><<<grid, 256, 0, c.stream>>>(seed, path_offset, n_paths, n_blocks, partials,
+                                                                      ticket, max_bits, out);
     c.launches++;
     OPTP_CUDA(cudaGetLastError());
     OPTP_CUDA(cudaMemcpyAsync(c.stats_host, out, 16 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));

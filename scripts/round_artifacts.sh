@@ -19,7 +19,7 @@ bench)
       python bench.py --steps 3 --warmup 3 --skip-cpu --skip-extra > $O/ncu_launch_$TAG.log 2>&1 ;;
 ncu)
   # the bench's own launches of the two headline kernels (bench-size), one capture each
-  ncu --set full --clock-control none --import-source on -k regex:path_fp32 -s 4 -c 1 -f -o $O/prof_${TAG}_bench_gbm \
+  ncu --set full --clock-control none --import-source on -k regex:path_fp32 -s 3 -c 1 -f -o $O/prof_${TAG}_bench_gbm \
       python bench.py --steps 1 --warmup 3 --skip-cpu --skip-extra > $O/ncu_full_gbm_$TAG.log 2>&1
   ncu --set full --clock-control none --import-source on -k crr_zone_kernel -s 9 -c 1 -f -o $O/prof_${TAG}_bench_zone \
       python bench.py --steps 1 --warmup 3 --skip-cpu --skip-extra > $O/ncu_full_zone_$TAG.log 2>&1

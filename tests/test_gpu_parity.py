@@ -8,6 +8,7 @@ Tolerances (BASELINE.json north_star):
   CRR                                              1e-10 relative
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -27,7 +28,7 @@ def op():
     import optpricer_b200 as o
     from optpricer_b200 import _native
     _native.init()
-    assert _native.LIB_PATH.endswith("liboptp_b200.so")
+    assert os.path.basename(_native.LIB_PATH).startswith("liboptp_")   # (OPTP_LIB: a variant build of the same library)
     return o
 
 

@@ -162,13 +162,15 @@ def test_device_normals_are_a_function_of_seed_path_block_only(op):
 
 @pytest.mark.parametrize("rng_mode", [1, 2])
 def test_opt_in_generator_modes_price_within_their_own_standard_error(op, rng_mode):
-    """rng_mode 1 / 2 (fp32 GBM path kernel only) are different samples of the same law: prices agree with the
-    default generator within the combined standard error at 2e7 effective paths, and the default is restored."""
+    """rng_mode 1 / 2 (fp32 GBM and Heston FTE path kernels) are different samples of the same law: prices agree with
+    the default generator within the combined standard error at 2e7 effective paths, and the default is restored."""
     from optpricer_b200 import _native as nv, exotics as ex, processes as pr
     specs = [ex.barrier_spec(100.0, "call", 130.0, "up-and-out"), ex.asian_spec(100.0, "call"),
              ex.vanilla_spec(100.0, "call"), ex.lookback_spec("put", 100.0, "fixed")]
-    for n_steps in (252, 50, 7):     # 7: a partial last call in every mode
-        lp = pr.gbm_paths(100.0, 0.05, 0.0, 0.2, 1.0, n_steps, 10_000_000, seed=3)
+    jobs = [pr.gbm_paths(100.0, 0.05, 0.0, 0.2, 1.0, n_steps, 10_000_000, seed=3) for n_steps in (252, 50, 7)]
+    jobs += [pr.heston_paths(100.0, 0.05, 0.0, 0.04, 2.0, 0.04, 0.3, -0.7, 1.0, n_steps, 10_000_000, seed=4)
+             for n_steps in (365, 50, 7)]          # 7: a partial last call in every mode
+    for lp in jobs:
         base = ex.price_payoffs(lp, specs, 0.05, 1.0)
         nv.set_option("rng_mode", rng_mode)
         try:
@@ -179,5 +181,5 @@ def test_opt_in_generator_modes_price_within_their_own_standard_error(op, rng_mo
         assert again == base
         for (pa, sa), (pb, sb) in zip(alt, base):
             assert pa != pb
-            assert abs(pa - pb) <= 4.0 * math.hypot(sa, sb), (rng_mode, n_steps, pa, pb, sa, sb)
+            assert abs(pa - pb) <= 4.0 * math.hypot(sa, sb), (rng_mode, lp, pa, pb, sa, sb)
             assert abs(sa / sb - 1.0) < 5e-3

@@ -298,3 +298,33 @@ def test_heston_qe_against_the_semi_analytic_price_without_an_allowance(op, case
     cv = ex.price_payoffs(lp, [ex.vanilla_spec(100.0, "call")], c["r"], c["T"], control_variate=True)[0]
     assert abs(plain[0] - exact) <= 4.0 * plain[1], (plain, exact)
     assert abs(cv[0] - exact) <= 4.0 * cv[1] + 1e-3, (cv, exact)
+
+
+def test_dev_launches_on_several_streams_overlap_safely(op):
+    """The *_dev Monte Carlo entry points take the slots of the reduction scratch round-robin: launches queued on
+    different streams (no ordering between them) give the statistics of the same launches queued on one stream."""
+    import torch
+    from optpricer_b200 import _native as nv, exotics as ex
+    lib = nv.init()
+    dev = torch.device("cuda", nv.default_device())
+    proc = nv.OptpProcess()
+    proc.kind = nv.PROC_GBM
+    proc.S0, proc.r, proc.q, proc.T, proc.sigma = 100.0, 0.05, 0.0, 1.0, 0.2
+    pay = ex._native_payoffs([ex.barrier_spec(100.0, "call", 130.0, "up-and-out"), ex.asian_spec(100.0, "call")], 0.05, 1.0)
+    n_jobs = 6
+
+    def run(streams):
+        outs = [torch.zeros(2 * nv.NSTATS, dtype=torch.float64, device=dev) for _ in range(n_jobs)]
+        for rep in range(3):
+            for j in range(n_jobs):
+                st = streams[j % len(streams)]
+                nv.check(lib.optp_mc_path_dev(C.byref(proc), pay, 2, 64, 300_000 + 1000 * j, 1, nv.MODE_FP32_PHILOX, 7 + j, 0,
+                                              None, None, None, C.c_void_p(outs[j].data_ptr()), C.c_void_p(st.cuda_stream)),
+                         "optp_mc_path_dev")
+        torch.cuda.synchronize()
+        return [o.cpu().numpy() for o in outs]
+
+    one = run([torch.cuda.Stream(device=dev)])
+    many = run([torch.cuda.Stream(device=dev) for _ in range(n_jobs)])
+    for a, b in zip(one, many):
+        np.testing.assert_array_equal(a, b)
