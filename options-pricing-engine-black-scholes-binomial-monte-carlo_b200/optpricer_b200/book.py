@@ -170,30 +170,30 @@ def shard_items(items, rank, world, load=None):
 def book_stats(items, *, mode="fp32", rank=0, world=1, load=None):
     """Run this rank's share (shard_items) of all Monte Carlo items through optp_mc_book.
     Returns the (n_blocks, 8) statistics array (item order, payoff order inside an item)."""
+    return book_run(book_prepare(items, mode=mode, rank=rank, world=world, load=load))
+
+
+def book_prepare(items, *, mode="fp32", rank=0, world=1, load=None):
+    """Host half of book_stats: deal the items (shard_items), fill the optp_book_item / optp_payoff arrays of this
+    rank's share and stage the sigma tables its local-vol items name.  price_book runs this for slice k+1 while
+    a worker thread is inside optp_mc_book for slice k, so the device never waits for descriptors."""
     shards = shard_items(items, rank, world, load)
     n_blocks = sum(len(it["rows"]) for it in items)
-    stats = np.zeros((n_blocks, nv.NSTATS), dtype=np.float64)
+    prep = dict(items=items, n_blocks=n_blocks, live=0, handles={})
     if not items:
-        return stats
+        return prep
     lib = nv.init()
     arr = (nv.OptpBookItem * len(items))()
     specs = []
     live = 0
-    handles = {}   # id(SigmaTable) -> device table handle, created once per distinct table of this rank's items
-    try:
-        return _book_stats_run(lib, items, shards, arr, specs, live, handles, stats, mode)
-    finally:
-        for h in handles.values():
-            lib.optp_sigma_table_destroy(h)
-
-
-def _book_stats_run(lib, items, shards, arr, specs, live, handles, stats, mode):
+    handles = prep["handles"]   # id(SigmaTable) -> device table handle, one per distinct table of this rank's items
+    skip = []
     for it, (lo, hi) in zip(items, shards):
         a = arr[live]
         if hi == lo:
-            it["_skip"] = True   # this rank has no paths of the item; its blocks stay zero
+            skip.append(True)    # this rank has no paths of the item; its blocks stay zero
             continue
-        it["_skip"] = False
+        skip.append(False)
         live += 1
         a.terminal_only = 1 if it["kind"] == "terminal" else 0
         a.n_base, a.seed, a.path_offset = hi - lo, mc._seed64(it["seed"]), lo
@@ -219,18 +219,35 @@ def _book_stats_run(lib, items, shards, arr, specs, live, handles, stats, mode):
     for j, (s, r, T) in enumerate(specs):
         one = ex._native_payoffs([s], r, T)[0]
         C.memmove(C.byref(pay[j]), C.byref(one), C.sizeof(nv.OptpPayoff))
-    live_blocks = sum(len(it["rows"]) for it in items if not it["_skip"])
-    out = np.zeros((live_blocks, nv.NSTATS), dtype=np.float64)
-    if live:
-        nv.check(lib.optp_mc_book(arr, live, pay, len(specs), nv.ptr(out)), "optp_mc_book")
-    src = dst = 0
-    for it in items:
-        n = len(it["rows"])
-        if not it["_skip"]:
-            stats[dst:dst + n] = out[src:src + n]
-            src += n
-        dst += n
-    return stats
+    prep.update(arr=arr, pay=pay, n_specs=len(specs), live=live, skip=skip)
+    return prep
+
+
+def book_run(prep):
+    """Device half of book_stats: ONE optp_mc_book call (blocking, GIL released) and the scatter of its blocks
+    into item order; destroys the table handles of the slice."""
+    items = prep["items"]
+    stats = np.zeros((prep["n_blocks"], nv.NSTATS), dtype=np.float64)
+    if not items:
+        return stats
+    lib = nv.init()
+    try:
+        live_blocks = sum(len(it["rows"]) for it, sk in zip(items, prep["skip"]) if not sk)
+        out = np.zeros((live_blocks, nv.NSTATS), dtype=np.float64)
+        if prep["live"]:
+            nv.check(lib.optp_mc_book(prep["arr"], prep["live"], prep["pay"], prep["n_specs"], nv.ptr(out)),
+                     "optp_mc_book")
+        src = dst = 0
+        for it, sk in zip(items, prep["skip"]):
+            n = len(it["rows"])
+            if not sk:
+                stats[dst:dst + n] = out[src:src + n]
+                src += n
+            dst += n
+        return stats
+    finally:
+        for h in prep["handles"].values():
+            lib.optp_sigma_table_destroy(h)
 
 
 def estimate_rows(items, stats, control_variate=True):
@@ -298,8 +315,9 @@ def price_book(rows, *, tree_steps=500, mc_paths=100_000, exotic_steps=500, exot
         for lo in range(0, n_rows, max(step, 1)):
             items = _plan_rows(rows, lo, min(lo + step, n_rows), results, crr_groups, tree_steps=tree_steps,
                                mc_paths=mc_paths, exotic_steps=exotic_steps, exotic_paths=exotic_paths, seed=seed)
-            if items:
-                slices.append((items, pool.submit(book_stats, items, mode=mode, rank=rank, world=world, load=load)))
+            if items:   # descriptors are filled HERE, while the worker thread is inside the previous slice's call
+                prep = book_prepare(items, mode=mode, rank=rank, world=world, load=load)
+                slices.append((items, pool.submit(book_run, prep)))
         # --- trees: one batch per american flag (queues behind the slices on the device) ---------------
         for american, group in crr_groups.items():
             cols = [np.array([g[c] for g in group], dtype=np.float64) for c in range(1, 8)]
