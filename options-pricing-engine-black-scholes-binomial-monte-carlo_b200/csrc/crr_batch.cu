@@ -609,9 +609,10 @@ __global__ void __launch_bounds__(kBandWarps * 32, 5) crr_band_kernel(CrrArgs a)
 constexpr int kZoneWarps = 4;
 // Z = [jlo - 30, jlo + 2): 30 nodes below the first continuation node jlo of the segment's first level.
 // RIGOROUSLY the boundary index falls by at most one per level (see above), which would allow segments of 28
-// levels.  Measured (scripts/crr_boundary_drop.py, the exact lattice boundary of config-2-like contracts), it falls
-// by 1/2 + O(1/sqrt(n)) per level n levels from expiry: at most 27 nodes over the FIRST 37 levels, and at most
-// 27 over any later stretch of 46 levels.  The schedule therefore walks kZoneSeg0 levels from level N and
+// levels.  Measured (scripts/crr_boundary_drop.py: the exact lattice boundary of 250 contracts over sigma in
+// [0.05, 1], T in [0.05, 5], r up to 15 %, N = 200 / 1000 / 3000), it falls by 1/2 + O(1/sqrt(n)) per level n
+// levels from expiry: at most 27 nodes over the FIRST 34 levels, and at most 27 over any stretch of 44 levels
+// that starts 32 or more levels from expiry (Z tolerates 29).  The schedule therefore walks kZoneSeg0 levels from level N and
 // kZoneSeg levels per segment after that -- 23 segments per N = 1000 option instead of 36, and the work between
 // segments (tile round trip, band measurement, plan) is a third of the walk.  Exactness does not rest on the
 // measurement: the kernel checks at EVERY level that Z's bottom node chose exercise, and a contract that fails
@@ -632,10 +633,19 @@ static_assert(kZoneSeg0 <= kZoneSeg, "the renormalisation bound L.R >= kZoneSeg 
 // arithmetic applied to a node does not depend on the layout, so neither does the price.
 constexpr int kZoneLaneC = 24;
 __host__ __device__ constexpr int zone_max_m(int G) { return kZoneLaneC / G; }
-// re-pack tile, node-ordered per option: node e lives at e + (e >> 4) (one pad double per 16, so the
-// lane-strided accesses of every layout spread over the banks); 248 = 8 (mod 16) staggers the options
-__host__ __device__ constexpr int zone_group_tile(int G) { return G == 4 ? 248 : G == 2 ? 456 : 856; }
-__device__ __forceinline__ int zone_pad(int e) { return e + (e >> 4); }
+// re-pack tile, node-ordered per option: node e lives at e + (e >> OPTP_ZONE_PAD_SHIFT), one pad double per
+// 2^shift nodes.  A lane's chunk of 4M consecutive nodes then starts 5M doubles after its neighbour's (shift 2):
+// 5M mod 16 runs through distinct bank pairs for the lanes of an option (M != 4), and the tile of the next option
+// starts 8 (mod 16) doubles further, so the two options of a half-warp interleave.
+#ifndef OPTP_ZONE_PAD_SHIFT
+#define OPTP_ZONE_PAD_SHIFT 2
+#endif
+__host__ __device__ constexpr int zone_pad_c(int e) { return e + (e >> OPTP_ZONE_PAD_SHIFT); }
+__host__ __device__ constexpr int zone_group_tile(int G) {
+    // nodes 32 (1 + kMaxM) padded, rounded up to 8 (mod 16)
+    return ((zone_pad_c(32 * (1 + zone_max_m(G))) + 7) & ~15) + 8;
+}
+__device__ __forceinline__ int zone_pad(int e) { return e + (e >> OPTP_ZONE_PAD_SHIFT); }
 // -DOPTP_ZONE_CHECK (OPTP_NVCC_FLAGS, build_native.py --force): every tile access of the two-zone kernel is
 // bounds-checked and traps -- the in-house stand-in for compute-sanitizer, run over the stress tests
 #ifdef OPTP_ZONE_CHECK
@@ -647,9 +657,9 @@ __device__ __forceinline__ int zone_pad_checked(int e, int limit) {
 #else
 #define OPTP_ZP(e) zone_pad(e)
 #endif
-static_assert(32 * (1 + zone_max_m(4)) + (32 * (1 + zone_max_m(4)) >> 4) <= zone_group_tile(4), "tile too small");
-static_assert(32 * (1 + zone_max_m(2)) + (32 * (1 + zone_max_m(2)) >> 4) <= zone_group_tile(2), "tile too small");
-static_assert(32 * (1 + zone_max_m(1)) + (32 * (1 + zone_max_m(1)) >> 4) <= zone_group_tile(1), "tile too small");
+static_assert(zone_pad_c(32 * (1 + zone_max_m(4))) <= zone_group_tile(4) && zone_group_tile(4) % 16 == 8, "tile too small");
+static_assert(zone_pad_c(32 * (1 + zone_max_m(2))) <= zone_group_tile(2) && zone_group_tile(2) % 16 == 8, "tile too small");
+static_assert(zone_pad_c(32 * (1 + zone_max_m(1))) <= zone_group_tile(1) && zone_group_tile(1) % 16 == 8, "tile too small");
 
 // One segment in layout (BZ = G, BC = G*M), M a compile-time constant:
 //   * the lane's C nodes are loaded from the node-ordered tile, which holds level k in the PREVIOUS layout
