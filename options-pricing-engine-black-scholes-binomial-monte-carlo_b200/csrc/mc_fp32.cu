@@ -880,27 +880,34 @@ __global__ void __launch_bounds__(kLvThreads, 4) lv_fp32_kernel(PathArgs a, int 
                 __syncthreads();
             }
             if (active) {
+                // one step of the pair on table row `row`
+                auto step = [&](const Node* row, float zs) {
+                    const float zzh = fmaf(0.5f * zs, zs, -k.hdt);  // (Z^2 - 1) dt / 2
+                    if constexpr (WIN) {
+                        lvm_step_win<MASK, false, WINMODE != 2>(p, row, k, zs, zzh);
+                        if (ANTI) lvm_step_win<MASK, false, WINMODE != 2>(m, row, k, -zs, zzh);
+                    } else {
+                        lv_step<PROC, MASK>(p, row, k, zs, zzh);
+                        if (ANTI) lv_step<PROC, MASK>(m, row, k, -zs, zzh);
+                    }
+                };
+                // full groups of four rows run unguarded with a running row pointer (the per-step bound check
+                // and row-offset multiply were 16 of the 344 instructions of a group); only the table's last
+                // chunk can end in a partial group
+                const unsigned int n4 = nr & ~3u;
+                const Node* row = buf;
+                float z[4];
 #pragma unroll 1
-                for (unsigned int r = 0; r < nr; r += 4) {
-                    float z[4];
+                for (unsigned int r = 0; r < n4; r += 4) {
                     const uint4 wn = philox_words(a.seed, gpath, ((t0 + r) >> 2) + 1, 0u);
                     normals_from_words_scaled(w, k.bm_dt, z);  // z = sqrt(dt) Z (the scale rides in the radius)
                     w = wn;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (r + j < nr) {
-                            const Node* row = buf + (size_t)(r + j) * n_ld;
-                            const float zs = z[j];
-                            const float zzh = fmaf(0.5f * zs, zs, -k.hdt);  // (Z^2 - 1) dt / 2
-                            if constexpr (WIN) {
-                                lvm_step_win<MASK, false, WINMODE != 2>(p, row, k, zs, zzh);
-                                if (ANTI) lvm_step_win<MASK, false, WINMODE != 2>(m, row, k, -zs, zzh);
-                            } else {
-                                lv_step<PROC, MASK>(p, row, k, zs, zzh);
-                                if (ANTI) lv_step<PROC, MASK>(m, row, k, -zs, zzh);
-                            }
-                        }
-                    }
+                    for (int j = 0; j < 4; ++j, row += n_ld) step(row, z[j]);
+                }
+                if (n4 < nr) {
+                    normals_from_words_scaled(w, k.bm_dt, z);
+                    for (unsigned int j = 0; j < nr - n4; ++j, row += n_ld) step(row, z[j]);
                 }
             }
             if (OPTP_LV_TMA) {
@@ -1093,10 +1100,14 @@ static int launch_lv_impl(const PathArgs& a, cudaStream_t st) {
     const size_t acc_bytes = sizeof(double) * (3 + 3 * a.n_pay) * kLvThreads;
     const size_t row_bytes = WIN ? sizeof(float4) * (size_t)(a.n_nodes + 4)
                                  : sizeof(float2) * (size_t)((a.n_nodes + 1) & ~1);
-    // chunk of rows: a multiple of 4 (one Philox call = 4 steps): one ~32 KB buffer, or two ~16 KB
-    // buffers when the TMA double-buffered staging is compiled in
-    static const int chunk_kb = getenv("OPTP_LV_CHUNK_KB") ? atoi(getenv("OPTP_LV_CHUNK_KB")) : 36;  // per buffer
-    int rows = (int)((chunk_kb * 1024) / row_bytes) & ~3;
+    // chunk of rows: a multiple of 4 (one Philox call = 4 steps).  The CTA meets at a barrier once per chunk, so
+    // the chunk is as large as TWO resident CTAs per SM allow (two buffers each with the TMA staging): measured
+    // on B200, config 3 (252 x 260-node rows of 4160 B): 4 rows per chunk (4 CTAs/SM) 5.02e11 path-steps/s,
+    // 8 rows 5.23e11, 12 rows 5.48e11, 16 rows (one CTA per SM) 4.07e11.  OPTP_LV_CHUNK_KB overrides (A/B runs).
+    static const int chunk_kb = getenv("OPTP_LV_CHUNK_KB") ? atoi(getenv("OPTP_LV_CHUNK_KB")) : 0;  // per buffer
+    const size_t per_cta = (227 * 1024) / 2 - 1024;  // dynamic shared memory of one of two resident CTAs
+    const size_t per_buf = per_cta > acc_bytes ? (per_cta - acc_bytes) / (OPTP_LV_TMA ? 2 : 1) : 0;
+    int rows = (int)((chunk_kb > 0 ? (size_t)chunk_kb * 1024 : per_buf) / row_bytes) & ~3;
     if (rows < 4) rows = 4;
     const int max_rows = (int)((a.n_steps + 3) & ~3u);
     if (rows > max_rows) rows = max_rows;
