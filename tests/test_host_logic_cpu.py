@@ -64,3 +64,61 @@ def test_path_payoff_estimator_reproduces_reference_prices():
         assert close(price, ref_price) and close(se, ref_se, 1e-9), key
         checked += 1
     assert checked >= 4
+
+
+# ---- round 2 host logic (no device needed) ---------------------------------------------------------
+def test_validate_contracts_raises_the_reference_text_for_the_first_offender():
+    import numpy as np
+    import pytest
+    from optpricer_b200.core import validate_contracts
+    validate_contracts([100.0, 90.0], [100.0, 95.0], 1.0, 0.2)
+    with pytest.raises(ValueError, match="K must be positive, got 0.0"):
+        validate_contracts([100.0, 90.0, -1.0], [100.0, 0.0, 95.0], 1.0, 0.2)       # contract 1 fails before contract 2
+    with pytest.raises(ValueError, match="S0 must be positive, got -1.0"):
+        validate_contracts([100.0, -1.0], [100.0, 0.0], 1.0, 0.2)                  # S0 is checked before K
+    with pytest.raises(ValueError, match="sigma must be positive"):
+        validate_contracts(100.0, 100.0, 1.0, np.array([0.2, 0.0]))
+    with pytest.raises(ValueError):
+        validate_contracts(np.nan, 100.0, 1.0, 0.2)
+
+
+def test_sigma_table_belongs_to_its_run():
+    import math
+    import numpy as np
+    import pytest
+    from optpricer_b200.processes import SigmaTable
+    tab = SigmaTable.from_callable(lambda S, t: 0.2 + 0.0 * S, S0=100.0, T=1.0, n_steps=12, n_nodes=64, half_width=1.6)
+    tab.check_against(100.0, 1.0, 12)
+    tab.check_against(150.0, 0.5, 6)                      # same dt, S0 still inside the grid
+    with pytest.raises(ValueError, match="fewer rows"):
+        tab.check_against(100.0, 2.0, 24)
+    with pytest.raises(ValueError, match="tabulated for dt"):
+        tab.check_against(100.0, 2.0, 12)
+    with pytest.raises(ValueError, match="outside the table"):
+        tab.check_against(100.0 * math.exp(1.7), 1.0, 12)
+    assert SigmaTable.auto_grid(lambda S, t: 0.25 + 0.0 * S, 100.0, 1.0, 50) == (256, 1.6)
+    n_nodes, half = SigmaTable.auto_grid(lambda S, t: 0.5 + 0.0 * S, 100.0, 4.0, 50)
+    assert half == 6.0 and n_nodes == math.ceil(255 * 6.0 / 1.6) + 1
+    spiky = lambda S, t: np.where(np.isclose(t, 0.5), 5.0, 0.2) + 0.0 * S   # noqa: E731  (one bad slice: the median ignores it)
+    assert SigmaTable.auto_grid(spiky, 100.0, 1.0, 48) == (256, 1.6)
+
+
+def test_control_variate_mean_per_scheme():
+    import math
+    import pytest
+    from optpricer_b200 import exotics as ex, processes as pr
+    gbm = pr.gbm_paths(100.0, 0.08, 0.02, 0.2, 2.0, 10, 5, seed=1)
+    assert ex._expected_y(gbm, 0.08, 2.0) == pytest.approx(100.0 * math.exp(-0.02 * 2.0))          # monte_carlo.py:157
+    mil = pr.gbm_milstein_paths(100.0, 0.08, 0.02, 0.2, 2.0, 10, 5, seed=1)
+    assert ex._expected_y(mil, 0.08, 2.0) == pytest.approx(100.0 * (1.0 + 0.06 * 0.2) ** 10 * math.exp(-0.16))
+    sabr1 = pr.sabr_paths(100.0, 0.08, 0.02, 0.2, 1.0, 0.4, -0.3, 2.0, 10, 5, seed=1)
+    sabr5 = pr.sabr_paths(100.0, 0.08, 0.02, 2.0, 0.5, 0.4, -0.3, 2.0, 10, 5, seed=1)
+    assert ex._expected_y(sabr1, 0.08, 2.0) == pytest.approx(100.0 * math.exp(-0.04))
+    assert ex._expected_y(sabr5, 0.08, 2.0) == pytest.approx(100.0 * 1.012 ** 10 * math.exp(-0.16))
+    qe = pr.heston_paths(100.0, 0.05, 0.0, 0.04, 2.0, 0.04, 0.3, -0.7, 1.0, 8, 5, seed=1, scheme="qe")
+    with pytest.raises(ValueError, match="martingale correction"):
+        ex._expected_y(qe, 0.05, 1.0)
+    qem = pr.heston_paths(100.0, 0.05, 0.0, 0.04, 2.0, 0.04, 0.3, -0.7, 1.0, 8, 5, seed=1, scheme="qe", martingale_correction=True)
+    assert ex._expected_y(qem, 0.05, 1.0) == pytest.approx(100.0)
+    with pytest.raises(ValueError, match="belongs to scheme='qe'"):
+        pr.heston_paths(100.0, 0.05, 0.0, 0.04, 2.0, 0.04, 0.3, -0.7, 1.0, 8, 5, martingale_correction=True)
