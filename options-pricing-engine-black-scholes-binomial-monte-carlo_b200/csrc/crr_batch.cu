@@ -606,7 +606,10 @@ __global__ void __launch_bounds__(kBandWarps * 32, 5) crr_band_kernel(CrrArgs a)
 #ifndef OPTP_ZONE_MINB4
 #define OPTP_ZONE_MINB4 4
 #endif
-constexpr int kZoneWarps = 4;
+#ifndef OPTP_ZONE_WARPS
+#define OPTP_ZONE_WARPS 4
+#endif
+constexpr int kZoneWarps = OPTP_ZONE_WARPS;  // warps per CTA of the two-zone kernel
 // Z = [jlo - 30, jlo + 2): 30 nodes below the first continuation node jlo of the segment's first level.
 // RIGOROUSLY the boundary index falls by at most one per level (see above), which would allow segments of 28
 // levels.  Measured (scripts/crr_boundary_drop.py: the exact lattice boundary of 250 contracts over sigma in
@@ -1350,10 +1353,10 @@ static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st, int sl
             a.op_count = c.crr_op_count;
         }
         const void* fn = (G >= 1) ? zone_fn(G, count) : (const void*)crr_band_kernel;
-        static_assert(kBandWarps == kZoneWarps, "one grid computation for both banded kernels");
-        if (int e = occupancy_cached(fn, kZoneWarps * 32, &per_sm)) return e;
+        const int cta_warps = (G >= 1) ? kZoneWarps : kBandWarps;
+        if (int e = occupancy_cached(fn, cta_warps * 32, &per_sm)) return e;
         const unsigned long long per_warp = (G > 0) ? (unsigned long long)G : 1ull;
-        const unsigned long long want = (a.n + kBandWarps * per_warp - 1) / (kBandWarps * per_warp);
+        const unsigned long long want = (a.n + cta_warps * per_warp - 1) / (cta_warps * per_warp);
         const unsigned long long cap = (unsigned long long)c.n_sm * per_sm;
         const unsigned int grid = (unsigned int)(want < cap ? want : cap);
         if (G >= 1)
