@@ -340,24 +340,47 @@ int optp_mc_book(const optp_book_item* items, uint64_t n_items, const optp_payof
     const size_t bytes = sizeof(double) * OPTP_NSTATS * n_blocks;
     if (int e = arena_reserve(c.out1, bytes)) return e;
     double* stats_dev = (double*)c.out1.p;
+    // The launches are dealt over four streams: an item of 1e5 paths does not fill the machine and its tail would
+    // otherwise sit in front of the next item's head.  The reduction scratch has kReduceSlots = 8 slots taken
+    // round-robin, so launches i and i + 8 share a slot -- and a stream (8 is a multiple of 4): ordered.
+    constexpr int kBookStreams = 4;
+    static_assert(kReduceSlots % kBookStreams == 0, "slot reuse must stay on one stream");
+    const bool spread = n_items >= 2 * kBookStreams;
+    cudaStream_t streams[kBookStreams] = {c.stream, c.stream, c.stream, c.stream};
+    if (spread) {
+        for (int i = 0; i < 3; ++i) {
+            if (!c.book_stream[i]) OPTP_CUDA(cudaStreamCreateWithFlags(&c.book_stream[i], cudaStreamNonBlocking));
+            if (!c.book_event[i]) OPTP_CUDA(cudaEventCreateWithFlags(&c.book_event[i], cudaEventDisableTiming));
+            streams[i + 1] = c.book_stream[i];
+        }
+        // whatever the context's stream still has queued (table uploads) comes first
+        OPTP_CUDA(cudaEventRecord(c.book_event[0], c.stream));
+        for (int i = 0; i < 3; ++i) OPTP_CUDA(cudaStreamWaitEvent(c.book_stream[i], c.book_event[0], 0));
+    }
     uint64_t blk = 0;
     for (uint64_t i = 0; i < n_items; ++i) {
         const optp_book_item& it = items[i];
         double* dst = stats_dev + blk * OPTP_NSTATS;
+        cudaStream_t st = streams[i % kBookStreams];
         if (it.terminal_only) {
             if (int e = optp_mc_terminal_dev(it.proc.S0, it.K, it.proc.T, it.proc.r, it.proc.q,
                                              it.proc.sigma, it.is_call, it.n_base, it.antithetic, it.mode,
-                                             0, it.seed, it.path_offset, nullptr, dst, c.stream))
+                                             0, it.seed, it.path_offset, nullptr, dst, st))
                 return e;
             blk += 1;
         } else {
             if (int e = mc_path_dev_slot(&it.proc, payoffs + it.first_payoff, (uint32_t)it.n_payoffs, it.n_steps,
                                          it.n_base, it.antithetic, it.mode, it.seed, it.path_offset, nullptr, nullptr,
-                                         nullptr, dst, c.stream, is_lv(it.proc.kind) ? it.table_handle : 0))
+                                         nullptr, dst, st, is_lv(it.proc.kind) ? it.table_handle : 0))
                 return e;
             blk += (uint64_t)it.n_payoffs;
         }
     }
+    if (spread)
+        for (int i = 0; i < 3; ++i) {
+            OPTP_CUDA(cudaEventRecord(c.book_event[i], c.book_stream[i]));
+            OPTP_CUDA(cudaStreamWaitEvent(c.stream, c.book_event[i], 0));
+        }
     OPTP_CUDA(cudaMemcpyAsync(stats_out, stats_dev, bytes, cudaMemcpyDeviceToHost, c.stream));
     OPTP_CUDA(cudaStreamSynchronize(c.stream));
     return 0;

@@ -147,6 +147,10 @@ static void release_resources(Context& c) {
     if (c.stream2) cudaStreamDestroy(c.stream2);
     if (c.stream3) cudaStreamDestroy(c.stream3);
     if (c.stream4) cudaStreamDestroy(c.stream4);
+    for (int i = 0; i < 3; ++i) {
+        if (c.book_stream[i]) cudaStreamDestroy(c.book_stream[i]);
+        if (c.book_event[i]) cudaEventDestroy(c.book_event[i]);
+    }
     for (int i = 0; i < c.n_events; ++i) cudaEventDestroy(c.events[i]);
     cudaGetLastError();
     c = Context();
@@ -185,6 +189,8 @@ int optp_shutdown(void) {
     if (c.stream2) cudaStreamSynchronize(c.stream2);
     if (c.stream3) cudaStreamSynchronize(c.stream3);
     if (c.stream4) cudaStreamSynchronize(c.stream4);
+    for (int i = 0; i < 3; ++i)
+        if (c.book_stream[i]) cudaStreamSynchronize(c.book_stream[i]);
     comm_release();
     release_resources(c);
     return 0;

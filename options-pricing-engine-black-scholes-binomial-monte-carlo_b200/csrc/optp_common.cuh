@@ -32,6 +32,8 @@ struct Context {
     cudaStream_t stream2 = nullptr;  // host->device copies of the sliced CRR batch pipeline (created on demand)
     cudaStream_t stream3 = nullptr;  // its device->host copies
     cudaStream_t stream4 = nullptr;  // the kernels of its odd slices (even slices: `stream`)
+    cudaStream_t book_stream[3] = {};  // optp_mc_book deals its launches over `stream` and these (created on demand)
+    cudaEvent_t book_event[3] = {};
     cudaEvent_t events[384] = {};    // its per-slice events (copy-in done, kernels done, copy-out done)
     int n_events = 0;
     double* partials = nullptr;   // [kReduceSlots][kMaxBlocks][kMaxVals]
