@@ -187,6 +187,16 @@ def book_prepare(items, *, mode="fp32", rank=0, world=1, load=None):
     specs = []
     live = 0
     handles = prep["handles"]   # id(SigmaTable) -> device table handle, one per distinct table of this rank's items
+    try:
+        return _fill_descriptors(lib, prep, items, shards, arr, specs, live, handles, mode)
+    except BaseException:
+        for h in handles.values():   # nothing will run this slice: do not leave its tables staged
+            lib.optp_sigma_table_destroy(h)
+        handles.clear()
+        raise
+
+
+def _fill_descriptors(lib, prep, items, shards, arr, specs, live, handles, mode):
     skip = []
     for it, (lo, hi) in zip(items, shards):
         a = arr[live]
