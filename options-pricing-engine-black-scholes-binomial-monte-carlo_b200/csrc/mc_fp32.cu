@@ -63,14 +63,15 @@ struct TermConst {
     float c0, sg2, sgn, sgnK;
 };
 
+// (sum XY is not accumulated: pay * S_T = pay^2 + K pay for a call and K pay - pay^2 for a put -- both sides
+// vanish where the payoff does -- so sum XY = +-sum X^2 + K sum X, formed once per thread from the fp64 totals)
 __device__ __forceinline__ void term_accum(float st, const TermConst& k, float& sx, float& sxx,
-                                           float& sy, float& syy, float& sxy) {
+                                           float& sy, float& syy) {
     const float pay = fmaxf(fmaf(k.sgn, st, k.sgnK), 0.0f);
     sx += pay;
     sxx = fmaf(pay, pay, sxx);
     sy += st;
     syy = fmaf(st, st, syy);
-    sxy = fmaf(pay, st, sxy);
 }
 
 template <bool ANTI>
@@ -89,11 +90,11 @@ __global__ void __launch_bounds__(256) terminal_fp32_kernel(TermArgs a) {
     const unsigned long long first = a.path_offset, last = a.path_offset + a.n_base;  // [first,last)
     const unsigned long long g_lo = first >> 2, g_hi = (last + 3) >> 2;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    double dsx = 0, dsxx = 0, dsy = 0, dsyy = 0, dsxy = 0;
+    double dsx = 0, dsxx = 0, dsy = 0, dsyy = 0;
     constexpr int kFlush = 8;
     unsigned long long g = g_lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     while (g < g_hi) {
-        float sx = 0, sxx = 0, sy = 0, syy = 0, sxy = 0;
+        float sx = 0, sxx = 0, sy = 0, syy = 0;
         uint4 w = philox_words(a.seed, g, 0u, kTermStream);
 #pragma unroll 1
         for (int it = 0; it < kFlush && g < g_hi; ++it, g += stride) {
@@ -106,16 +107,16 @@ __global__ void __launch_bounds__(256) terminal_fp32_kernel(TermArgs a) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float x = z[j];
-                    term_accum(mufu_ex2(k.c0 + x), k, sx, sxx, sy, syy, sxy);
-                    if (ANTI) term_accum(mufu_ex2(k.c0 - x), k, sx, sxx, sy, syy, sxy);
+                    term_accum(mufu_ex2(k.c0 + x), k, sx, sxx, sy, syy);
+                    if (ANTI) term_accum(mufu_ex2(k.c0 - x), k, sx, sxx, sy, syy);
                 }
             } else {
                 for (int j = 0; j < 4; ++j) {
                     const unsigned long long p = (g << 2) + j;
                     if (p < first || p >= last) continue;
                     const float x = z[j];
-                    term_accum(mufu_ex2(k.c0 + x), k, sx, sxx, sy, syy, sxy);
-                    if (ANTI) term_accum(mufu_ex2(k.c0 - x), k, sx, sxx, sy, syy, sxy);
+                    term_accum(mufu_ex2(k.c0 + x), k, sx, sxx, sy, syy);
+                    if (ANTI) term_accum(mufu_ex2(k.c0 - x), k, sx, sxx, sy, syy);
                 }
             }
         }
@@ -123,8 +124,9 @@ __global__ void __launch_bounds__(256) terminal_fp32_kernel(TermArgs a) {
         dsxx += (double)sxx;
         dsy += (double)sy;
         dsyy += (double)syy;
-        dsxy += (double)sxy;
     }
+    const double Kf = fabs((double)k.sgnK);  // the strike as the payoff above used it (rounded to fp32)
+    const double dsxy = a.is_call ? dsxx + Kf * dsx : Kf * dsx - dsxx;
     double vals[5] = {dsx * df, dsxx * df * df, dsy * df, dsyy * df * df, dsxy * df * df};
     for (int i = 0; i < 5; ++i) {
         const double t = block_sum(vals[i], red);
