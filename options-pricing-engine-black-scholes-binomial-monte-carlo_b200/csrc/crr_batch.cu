@@ -42,6 +42,11 @@ struct CrrArgs {
     const unsigned int* wl_in_n;
     unsigned int* wl_out;
     unsigned int* wl_out_n;
+    // contracts whose exercise boundary fell faster than the segment schedule allows (the per-level bottom test
+    // failed) are appended here and walked again by a pass on the RIGOROUS schedule (28-level segments: the
+    // boundary cannot fall by more than one node per level), instead of going to the full-width kernel; or null
+    unsigned int* wl_rig;
+    unsigned int* wl_rig_n;
     // {number of contracts left at status 2, at status 3} by the two-zone passes, or null: a full-width
     // filter pass with nothing to do returns at once instead of scanning n status bytes
     unsigned int* decl_count;
@@ -750,8 +755,10 @@ __device__ __forceinline__ unsigned int zone_segment(double (&z)[G], double (&c)
     return mask;
 }
 
-template <int G, bool COUNT = false>
+template <int G, bool COUNT = false, bool RIG = false>
 __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_kernel(CrrArgs a) {
+    // segment schedule: the measured one, or (RIG, the retry pass) the rigorous one of kZoneBelow - 2 levels
+    constexpr int kSeg = RIG ? (kZoneBelow - 2) : kZoneSeg, kSeg0 = RIG ? (kZoneBelow - 2) : kZoneSeg0;
     constexpr int LG = 32 / G, BZ = G, BCMAX = kZoneLaneC, kMaxM = zone_max_m(G), kGroupTile = zone_group_tile(G);
     __shared__ double tiles[kZoneWarps][G * kGroupTile];
     const int lane = threadIdx.x & 31;
@@ -853,11 +860,11 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
         const double sS0 = L.sgn * L.S0;  // (exact: sgn = -1 for every option that is walked)
         const double thr = K * 8.2718061255302767e-25;  // 2^-80 K (K itself is not kept across the walk)
         const double ln_u = log(L.u);
-        double back_full = 1.0;  // pd^kZoneSeg by square-and-multiply
+        double back_full = 1.0;  // pd^kSeg by square-and-multiply
         {
             double sq = L.pd;
 #pragma unroll
-            for (int e = kZoneSeg; e > 0; e >>= 1) {
+            for (int e = kSeg; e > 0; e >>= 1) {
                 if (e & 1) back_full *= sq;
                 sq *= sq;
             }
@@ -976,7 +983,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             // puts a BRA.DIV convergence check and a dozen register moves into every level loop below)
             if (k == 0 || __reduce_or_sync(0xffffffffu, fail ? 0u : 1u) == 0u) break;  // nothing left to walk in this warp
             // ---- next segment: levels k-1 ... k-nlev, fixed schedule -------------------------------
-            const int nlev = min(k == N ? kZoneSeg0 : kZoneSeg, k);
+            const int nlev = min(k == N ? kSeg0 : kSeg, k);
             const int top = min(jhi, k + 1);  // exclusive; node `top` of level k is 0 (or dead)
             // Z's bottom sits kZoneBelow nodes under the boundary (see kZoneSeg)
             int w0n = max(0, jlo - kZoneBelow);
@@ -1015,7 +1022,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             M = Mn;
             int n_ex0 = 0, t_exT = 0x7fffffff;
             double back = back_full;
-            if (nlev != kZoneSeg) {  // last, partial segment: pd^nlev by square-and-multiply
+            if (nlev != kSeg) {  // first or last (partial) segment: pd^nlev by square-and-multiply
                 back = 1.0;
                 double sq = L.pd;
                 for (int e = nlev; e > 0; e >>= 1) {
@@ -1046,7 +1053,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             const int bottom_ex = __shfl_sync(0xffffffffu, n_ex0, gb);
             const int top_ex = __shfl_sync(0xffffffffu, t_exT, gb + LG - 1);
             if (w0 > 0 && bottom_ex != nlev) fail = true;
-            if (top_ex < n_chk) fail = true;  // (exercise events while Z's top node is outside the tree do not count)
+            if (top_ex < n_chk) fail = true;  // (exercise events while Z's top node is outside the tree do not count)  // (exercise events while Z's top node is outside the tree do not count)
             if (COUNT) {
                 // per lane and level: Z nodes 2 DFMA + 1 DSETP each, C nodes 1 DFMA each, 2 scaling DMULs
                 cnt_fp64 += (unsigned int)(nlev * (3 * G + G * M + 2));
@@ -1064,8 +1071,13 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
         const double v0 = __shfl_sync(0xffffffffu, z[0], gb);
         if (wanted && L.ok && gl == 0) {
             if (fail) {
-                if (too_wide && G > 1) {
-                    a.wl_out[atomicAdd(a.wl_out_n, 1u)] = (unsigned int)o;  // status is settled by a later pass
+                // too wide for this lane layout: the next narrower pass walks it.  Otherwise, on the measured
+                // schedule, a walk that failed one of its per-level tests -- almost always the boundary outran the
+                // schedule (small r dt: the bottom test) -- is settled by the rigorous-schedule pass; contracts that
+                // never qualified ride along and are declined there.  (One append path: status is settled later.)
+                unsigned int* const list = (too_wide && G > 1) ? a.wl_out : (!too_wide && !RIG) ? a.wl_rig : nullptr;
+                if (list) {
+                    list[atomicAdd((too_wide && G > 1) ? a.wl_out_n : a.wl_rig_n, 1u)] = (unsigned int)o;
                 } else {
                     const unsigned char dc = declined_code();
                     a.status[o] = dc;
@@ -1277,7 +1289,7 @@ static size_t crr_worklist_bytes(unsigned long long n) {
     return ((size_t)n * sizeof(unsigned int) + 255) & ~(size_t)255;
 }
 static int crr_reserve_worklists(unsigned long long n) {
-    return arena_reserve(ctx().work, 2 * (256 + 2 * crr_worklist_bytes(n)) + 512);  // two slots of {header, list, list}
+    return arena_reserve(ctx().work, 2 * (256 + 3 * crr_worklist_bytes(n)) + 512);  // two slots of {header, 3 lists}
 }
 
 // the two-zone kernel for G options per warp; COUNT = with the executed-work counters (diagnostics)
@@ -1286,6 +1298,13 @@ static const void* zone_fn(int G, bool count) {
                                                                                : (const void*)crr_zone_kernel<1, true>;
     return (G == 4) ? (const void*)crr_zone_kernel<4> : (G == 2) ? (const void*)crr_zone_kernel<2>
                                                                  : (const void*)crr_zone_kernel<1>;
+}
+static const void* zone_rig_fn(bool count) {
+    return count ? (const void*)crr_zone_kernel<1, true, true> : (const void*)crr_zone_kernel<1, false, true>;
+}
+static void zone_rig_launch(bool count, unsigned int grid, const CrrArgs& a, cudaStream_t st) {
+    if (count) crr_zone_kernel<1, true, true><<<grid, dim3(kZoneWarps * 32), 0, st>>>(a);
+    else crr_zone_kernel<1, false, true><<<grid, dim3(kZoneWarps * 32), 0, st>>>(a);
 }
 static void zone_launch(int G, bool count, unsigned int grid, const CrrArgs& a, cudaStream_t st) {
     const dim3 blk(kZoneWarps * 32);
@@ -1308,6 +1327,7 @@ static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st, int sl
     a.todo_only = 0;
     a.wl_in = a.wl_in_n = nullptr;
     a.wl_out = a.wl_out_n = nullptr;
+    a.wl_rig = a.wl_rig_n = nullptr;
     a.decl_count = nullptr;
     a.cta_scratch = nullptr;
     a.op_count = nullptr;
@@ -1338,7 +1358,9 @@ static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st, int sl
             wl[1] = (unsigned int*)(base + 256 + list_bytes);
             a.decl_count = hdr + 2;
             a.next_group = hdr + 4;   // hdr[4..6]: the ticket counters of the (up to three) two-zone passes
-            OPTP_CUDA(cudaMemsetAsync(hdr, 0, 8 * sizeof(unsigned int), st));
+            a.wl_rig = (unsigned int*)(base + 256 + 2 * list_bytes);  // hdr[7]: its count, hdr[8]: its pass's tickets
+            a.wl_rig_n = hdr + 7;
+            OPTP_CUDA(cudaMemsetAsync(hdr, 0, 16 * sizeof(unsigned int), st));
             if (G >= 2) {
                 a.wl_out = wl[0];
                 a.wl_out_n = hdr;
@@ -1379,6 +1401,20 @@ static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st, int sl
             const unsigned long long cap2 = (unsigned long long)c.n_sm * per_sm;
             const unsigned int grid2 = (unsigned int)(want2 < cap2 ? want2 : cap2);
             zone_launch(g2, count, grid2, a, st);
+            c.launches++;
+            OPTP_CUDA(cudaGetLastError());
+        }
+        if (G >= 1) {
+            // contracts whose boundary outran the measured schedule: one option per warp on the rigorous schedule
+            a.wl_in = a.wl_rig;
+            a.wl_in_n = a.wl_rig_n;
+            a.wl_out = a.wl_out_n = nullptr;
+            a.wl_rig = a.wl_rig_n = nullptr;
+            a.next_group = hdr + 8;
+            if (int e = occupancy_cached(zone_rig_fn(count), kZoneWarps * 32, &per_sm)) return e;
+            const unsigned long long want3 = (a.n + kZoneWarps - 1) / kZoneWarps;
+            const unsigned long long cap3 = (unsigned long long)c.n_sm * per_sm;
+            zone_rig_launch(count, (unsigned int)(want3 < cap3 ? want3 : cap3), a, st);
             c.launches++;
             OPTP_CUDA(cudaGetLastError());
         }

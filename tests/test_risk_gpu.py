@@ -41,8 +41,9 @@ def test_numerical_greeks_tree_and_check_mode_mc_match_reference(op):
         before = nv.launch_count()
         got = op.numerical_greeks(_pricer(op, c, mode="check"), *_args(c), bump_pct=c["bump_pct"])
         if c["pricer"] == "tree":
-            # ONE batch: banded pass + European pass of the never-exercised calls + full-width fallback pass
-            assert nv.launch_count() - before <= 3
+            # ONE batch: banded pass + its rigorous-schedule retry pass + European pass of the never-exercised calls +
+            # full-width fallback pass
+            assert nv.launch_count() - before <= 4
         assert set(got) == set(c["result"])
         for k, v in c["result"].items():
             assert _close(got[k], v), (c, k, got[k], v)
