@@ -328,3 +328,41 @@ def test_dev_launches_on_several_streams_overlap_safely(op):
     many = run([torch.cuda.Stream(device=dev) for _ in range(n_jobs)])
     for a, b in zip(one, many):
         np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("N", [250, 1000, 1500])
+def test_crr_measured_segment_schedule_under_random_stress(op, N):
+    """The two-zone kernel walks 32 + 44 + 44 ... levels per segment on the MEASURED speed of the exercise boundary
+    (csrc/crr_batch.cu: kZoneSeg); exactness rests on its per-level checks, and contracts that fail them are retried
+    on the rigorous schedule.  Wide random parameters (r dt down to 1e-8, 1.5 volatility, 10 years, deep in and out of
+    the money, dividends, 30 % calls): every price equals the full-width kernel's, statuses are identical, and no
+    eligible put is left to the full-width kernel at N >= 1000."""
+    from optpricer_b200 import _native as nv
+    n = 60_000
+    g = np.random.default_rng(2026 + N)
+    S0 = g.uniform(20.0, 200.0, n)
+    K = S0 * np.exp(g.uniform(-0.6, 0.6, n))
+    T = np.exp(g.uniform(np.log(0.01), np.log(10.0), n))
+    sig = np.exp(g.uniform(np.log(0.03), np.log(1.5), n))
+    r = np.exp(g.uniform(np.log(0.001), np.log(0.3), n))
+    q = np.where(g.random(n) < 0.5, 0.0, g.uniform(0.0, 0.12, n))
+    is_call = (g.random(n) < 0.3).astype(np.uint8)
+    band, st = op.crr_batch(S0, K, T, r, q, sig, is_call, N, american=True, return_status=True)
+    nv.set_option("crr_band_only", 1)
+    try:
+        _, st_only = op.crr_batch(S0, K, T, r, q, sig, is_call, N, american=True, return_status=True)
+    finally:
+        nv.set_option("crr_band_only", 0)
+    nv.set_option("crr_band", 0)
+    try:
+        full, st_full = op.crr_batch(S0, K, T, r, q, sig, is_call, N, american=True, return_status=True)
+    finally:
+        nv.set_option("crr_band", 1)
+    np.testing.assert_array_equal(st, st_full)
+    ok = st == 0
+    assert ok.sum() > 0.99 * n
+    np.testing.assert_allclose(band[ok], full[ok], rtol=1e-10, atol=1e-10)
+    assert np.max(np.abs(band[ok] - full[ok]) / np.maximum(np.abs(full[ok]), 1e-8 * K[ok])) < 5e-10
+    puts = ok & (is_call == 0) & (r > q)
+    left = int(((st_only == 2) & puts).sum())
+    assert left <= (0 if N >= 1000 else 40), left
