@@ -57,7 +57,8 @@ def init_comm():
     if rank == 0:
         nv.check(lib.optp_comm_unique_id(buf), "optp_comm_unique_id")
     box = [bytes(buf.raw)]
-    dist.broadcast_object_list(box, src=0)
+    import torch
+    dist.broadcast_object_list(box, src=0, device=torch.device("cuda", nv.default_device()))
     nv.check(lib.optp_comm_init(rank, size, box[0]), "optp_comm_init")
     _comm_world = size
     return True

@@ -76,7 +76,9 @@ class SigmaTable:
         med = float(np.median(np.clip(at, 1e-8, 10.0)))
         half = max(1.6, 6.0 * med * float(np.sqrt(T)))
         n_nodes = int(np.ceil(255 * half / 1.6)) + 1
-        return min(n_nodes, 2048), half
+        # rows are staged in shared memory four at a time, twice (double buffering): 1024 nodes x 16 B is what fits;
+        # beyond half_width 6.4 the node spacing grows instead
+        return min(n_nodes, 1024), half
 
     @classmethod
     def from_callable(cls, sigma_loc, *, S0, T, n_steps, n_nodes=256, half_width=1.6):
