@@ -21,7 +21,7 @@ ncu)
   # the bench's own launches of the two headline kernels (bench-size), one capture each
   ncu --set full --clock-control none --import-source on -k regex:path_fp32 -s 3 -c 1 -f -o $O/prof_${TAG}_bench_gbm \
       python bench.py --steps 1 --warmup 3 --skip-cpu --skip-extra > $O/ncu_full_gbm_$TAG.log 2>&1
-  ncu --set full --clock-control none --import-source on -k crr_zone_kernel -s 9 -c 1 -f -o $O/prof_${TAG}_bench_zone \
+  ncu --set full --clock-control none --import-source on -k crr_zone_kernel -s 12 -c 1 -f -o $O/prof_${TAG}_bench_zone \
       python bench.py --steps 1 --warmup 3 --skip-cpu --skip-extra > $O/ncu_full_zone_$TAG.log 2>&1
   # every production kernel at a size ncu replays quickly (third repetition of scripts/profile_target.py)
   ncu --set full --clock-control none -k regex:"path_fp32|lv_fp32|terminal_fp32|crr_warp|crr_zone|crr_euro_sum" -s 20 -c 10 -f \
