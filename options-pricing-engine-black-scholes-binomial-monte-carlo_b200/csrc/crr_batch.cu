@@ -625,16 +625,41 @@ constexpr int kZoneWarps = OPTP_ZONE_WARPS;  // warps per CTA of the two-zone ke
 // segments (tile round trip, band measurement, plan) is a third of the walk.  Exactness does not rest on the
 // measurement: the kernel checks at EVERY level that Z's bottom node chose exercise, and a contract that fails
 // keeps status 2 and is priced by the full-width kernel.
+// OPTP_ZONE_DRIFT = 1: the window FOLLOWS the boundary inside a segment.  A lattice line of constant S falls by half a
+// node per level, and so does the exercise boundary up to O(1/sqrt(n)); a window with a fixed origin therefore needs
+// nlev/2 nodes of Z just to absorb that trend.  The drifting walk alternates two kinds of level:
+//     A (origin stays):     new[m] = pu*old[m+1] + pd*old[m]       (the classic in-place update, ascending)
+//     B (origin one lower): new[m] = pu*old[m]   + pd*old[m-1]     (position m now holds node j-1; descending)
+// so position m keeps the same S up to one factor u, the boundary stays where it was in the window (the emulation
+// scripts/crr_drift_emu.py sees it move by at most 5 positions over 64 levels, 10 over the first 32), and Z shrinks
+// from 32 to 16 nodes: 13 below the first continuation node, 2 above.  The node that enters at the bottom in a B
+// level takes the exercise value of the node below the window (justified by the same bottom test as before); the
+// node that leaves at the top must be dead, so the window is laid out nlev/2 nodes above the live top of the
+// segment's first level (values at a fixed index only shrink going back).  The window origin may go NEGATIVE: the
+// walk then runs on the tree extended downwards (nodes j < 0 at S0*u^(2j-k), a consistent lattice on which every
+// argument above holds and on which nothing below a node ever enters its value), so there is no second code path
+// for windows pinned at node 0.
+#ifndef OPTP_ZONE_DRIFT
+#define OPTP_ZONE_DRIFT 0
+#endif
+constexpr bool kZoneDrift = OPTP_ZONE_DRIFT != 0;
 #ifndef OPTP_ZONE_SEG
-#define OPTP_ZONE_SEG 44
+#define OPTP_ZONE_SEG (OPTP_ZONE_DRIFT ? 64 : 44)
 #endif
 #ifndef OPTP_ZONE_SEG0
 #define OPTP_ZONE_SEG0 32
 #endif
-constexpr int kZoneBelow = 30;                // Z nodes below the first continuation node
+constexpr int kZoneBelow = kZoneDrift ? 13 : 30;  // Z nodes below the first continuation node
 constexpr int kZoneSeg = OPTP_ZONE_SEG;       // levels per segment
 constexpr int kZoneSeg0 = OPTP_ZONE_SEG0;     // levels of the first segment (from level N)
+// rigorous schedule of the retry pass: the boundary falls by at most one node per level -- relative to a drifting
+// window by at most half a node per level
+constexpr int kZoneSegRig = kZoneDrift ? 2 * (kZoneBelow - 1) : kZoneBelow - 2;
 static_assert(kZoneSeg0 <= kZoneSeg, "the renormalisation bound L.R >= kZoneSeg covers the first segment too");
+static_assert(!kZoneDrift || (kZoneSeg % 2 == 0 && kZoneSeg0 % 2 == 0), "the drifting walk steps in pairs of levels");
+// Z nodes per lane and width of Z for G options per warp
+__host__ __device__ constexpr int zone_bz(int G) { return kZoneDrift ? (G >= 2 ? G / 2 : 1) : G; }
+__host__ __device__ constexpr int zone_zw(int G) { return zone_bz(G) * (32 / G); }
 // A lane holds at most 24 C nodes: 6 chunks of 32 nodes per option at four options per warp (band up to
 // 224 nodes), 12 at two (416), 24 at one (800).  A contract whose band is too wide for the layout it was
 // tried in keeps status 4 and is walked again by the next narrower-group pass (launch_crr); the
@@ -755,17 +780,137 @@ __device__ __forceinline__ unsigned int zone_segment(double (&z)[G], double (&c)
     return mask;
 }
 
+// The drifting walk (OPTP_ZONE_DRIFT): `npairs` pairs of levels (A then B, see above) in layout (BZ, BC = G*M).
+// Scaled recursion: an A level divides by pd (A[m] = (pu/pd)*A[m+1] + A[m]), a B level by pu
+// (A[m] = A[m] + (pd/pu)*A[m-1]), so both kinds spend ONE DFMA per node; back = (pd*pu)^npairs undoes it.
+// kB.rho2 = pd/pu, kB.inv_pu = 1/pu, kB.d_pu = 1/(u*pu) (position m moves to a node whose S is one factor u lower),
+// ulo_below = u^-2 (the node below the window, relative to the first lane's base).  Tile I/O as in zone_segment.
+struct DriftConsts {
+    double rho2, inv_pu, d_pu, ulo_below;
+};
+template <int G, int M>
+__device__ __forceinline__ unsigned int zone_segment_drift(double (&z)[zone_bz(G)], double (&c)[kZoneLaneC],
+                                                           const double (&ulo)[zone_bz(G)], const Lattice& L,
+                                                           const DriftConsts& kB, double ub, int gl, int src_up,
+                                                           int src_dn, double sb, int npairs, double back, double* tile, int jr0,
+                                                           int lim, int& n_ex0_out, int& t_exT_out) {
+    constexpr int BZ = zone_bz(G), BC = G * M, LG = 32 / G, ZW = BZ * LG;
+    constexpr int kMaxM = zone_max_m(G);  // (OPTP_ZP's bound in -DOPTP_ZONE_CHECK builds)
+    (void)kMaxM;
+#pragma unroll
+    for (int i = 0; i < BC; ++i) {
+        const int jr = jr0 + i;
+        c[i] = ((unsigned int)jr < (unsigned int)lim) ? tile[OPTP_ZP(jr)] : 0.0;
+    }
+    __syncwarp();  // every lane has read level k before this segment's stores overwrite the tile
+    double sbg = sb, sKg = L.sK;
+    const double rho = L.rho, rho2 = kB.rho2;
+    const bool last = (gl == LG - 1), first = (gl == 0);
+    // the exercise test covers the first 16 nodes whatever G is (at G = 1 Z holds 32): which nodes may choose
+    // exercise must not depend on the layout, or a tie in the last bit could be resolved differently
+    const bool ztest = (ZW <= 16) || (gl * BZ < 16);
+    // Cross links of the two rings (Z and C) as zero multipliers (x + 0*y = x exactly, every y is finite):
+    // A level: a lane's top node takes the next lane's first node (ra_nb; nothing above the window), and Z's top
+    //          node in the option's last lane takes C's first node, which the ring shuffle of c[0] delivers (ra_x);
+    // B level: a lane's first node takes the previous lane's last node (rb_nb); in the option's first lane Z's
+    //          first node takes the node below the window and C's first node takes Z's top node, which the ring
+    //          shuffle of z[BZ-1] delivers (rb_x).
+    const double ra_nb = last ? 0.0 : rho;
+    const double ra_x = (BC > 0 && last) ? rho : 0.0;
+    const double rb_nb = first ? 0.0 : rho2;
+    const double rb_x = first ? rho2 : 0.0;
+    int n_ex0 = 0, t_exT = 0x7fffffff;
+    double nbz = __shfl_sync(0xffffffffu, z[0], src_up);
+    double nbc = 0.0;
+    if (BC > 0) nbc = __shfl_sync(0xffffffffu, c[0], src_up);
+    for (int p = 0; p < npairs; ++p) {
+        double cz[BZ], ez[BZ];
+        // ---- A level
+        sbg *= L.u_pd;
+        sKg *= L.inv_pd;
+#pragma unroll
+        for (int i = 0; i < BZ; ++i) {
+            if (i + 1 < BZ) cz[i] = fma(rho, z[i + 1], z[i]);
+            else if (BC > 0) cz[i] = fma(ra_nb, nbz, fma(ra_x, nbc, z[i]));
+            else cz[i] = fma(ra_nb, nbz, z[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < BZ; ++i) ez[i] = fma(sbg, ulo[i], sKg);
+#pragma unroll
+        for (int i = 0; i < BC; ++i) c[i] = (i + 1 < BC) ? fma(rho, c[i + 1], c[i]) : fma(ra_nb, nbc, c[i]);
+#pragma unroll
+        for (int i = 0; i < BZ; ++i) {
+            const bool ex = (ZW <= 16) ? (ez[i] > cz[i]) : (ztest && ez[i] > cz[i]);
+            if (i == 0) n_ex0 += ex ? 1 : 0;
+            if (i == BZ - 1) t_exT = ex ? min(t_exT, 2 * p) : t_exT;
+            z[i] = ex ? ez[i] : cz[i];
+        }
+        const double pbz = __shfl_sync(0xffffffffu, z[BZ - 1], src_dn);
+        double pbc = 0.0;
+        if (BC > 0) pbc = __shfl_sync(0xffffffffu, c[BC - 1], src_dn);
+        // ---- B level
+        // the node below the window, at the level just computed: its exercise value (ub = u^-2) -- or, in the regime
+        // without exercise nodes (ub = 0, see k_pin), the strike: what enters below node 0 there is never used by a
+        // node of the tree, but it must stay ABOVE the values of the tree so that the live nodes remain a prefix of
+        // the window (measure_band)
+        const double eb = fma(sbg, ub, sKg);
+        sbg *= kB.d_pu;
+        sKg *= kB.inv_pu;
+#pragma unroll
+        for (int i = BZ - 1; i >= 0; --i) {
+            if (i > 0) cz[i] = fma(rho2, z[i - 1], z[i]);
+            else cz[i] = fma(rb_x, eb, fma(rb_nb, pbz, z[i]));
+        }
+#pragma unroll
+        for (int i = 0; i < BZ; ++i) ez[i] = fma(sbg, ulo[i], sKg);
+#pragma unroll
+        for (int i = BC - 1; i >= 0; --i) c[i] = (i > 0) ? fma(rho2, c[i - 1], c[i]) : fma(rb_x, pbz, fma(rb_nb, pbc, c[i]));
+#pragma unroll
+        for (int i = 0; i < BZ; ++i) {
+            const bool ex = (ZW <= 16) ? (ez[i] > cz[i]) : (ztest && ez[i] > cz[i]);
+            if (i == 0) n_ex0 += ex ? 1 : 0;
+            if (i == BZ - 1) t_exT = ex ? min(t_exT, 2 * p + 1) : t_exT;
+            z[i] = ex ? ez[i] : cz[i];
+        }
+        if (BC > 0) nbc = __shfl_sync(0xffffffffu, c[0], src_up);
+        nbz = __shfl_sync(0xffffffffu, z[0], src_up);
+    }
+    // exercise mask of the last level: a node chose exercise iff it holds the exercise value
+    unsigned int mask = 0;
+#pragma unroll
+    for (int i = 0; i < BZ; ++i) mask |= (z[i] == fma(sbg, ulo[i], sKg)) ? (1u << i) : 0u;
+#pragma unroll
+    for (int i = 0; i < BZ; ++i) z[i] *= back;
+#pragma unroll
+    for (int i = 0; i < BC; ++i) {
+        c[i] *= back;
+        tile[OPTP_ZP(ZW + gl * BC + i)] = c[i];
+    }
+    n_ex0_out = n_ex0;
+    t_exT_out = t_exT;
+    return mask;
+}
+
 template <int G, bool COUNT = false, bool RIG = false>
 __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_kernel(CrrArgs a) {
     // segment schedule: the measured one, or (RIG, the retry pass) the rigorous one of kZoneBelow - 2 levels
-    constexpr int kSeg = RIG ? (kZoneBelow - 2) : kZoneSeg, kSeg0 = RIG ? (kZoneBelow - 2) : kZoneSeg0;
-    constexpr int LG = 32 / G, BZ = G, BCMAX = kZoneLaneC, kMaxM = zone_max_m(G), kGroupTile = zone_group_tile(G);
+    constexpr int kSeg = RIG ? kZoneSegRig : kZoneSeg, kSeg0 = RIG ? kZoneSegRig : kZoneSeg0;
+    constexpr int LG = 32 / G, BZ = zone_bz(G), ZW = zone_zw(G), BCMAX = kZoneLaneC, kMaxM = zone_max_m(G),
+                  kGroupTile = zone_group_tile(G);
+    static_assert(ZW + 32 * kMaxM <= 32 * (1 + kMaxM), "the tile holds Z and kMaxM chunks of C");
+    // the node whose choice of continuation covers everything above it: the last node of Z -- in the drifting walk
+    // node 15 of the window for every G (at G = 1 Z is 32 nodes wide; a test that depended on G would let a contract
+    // pass in one layout and go to the retry pass, i.e. another rounding, in another)
+    constexpr int ZT = kZoneDrift ? 16 : ZW;
+    static_assert(ZT % BZ == 0 && ZT <= ZW, "the tested node is the last node of a lane");
     __shared__ double tiles[kZoneWarps][G * kGroupTile];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int gl = lane & (LG - 1);        // lane within the option
     const int gb = lane & ~(LG - 1);       // first lane of the option
     const int src = gb | ((gl + 1) & (LG - 1));
+    const int src_dn = gb | ((gl + LG - 1) & (LG - 1));  // (drifting walk: the previous lane of the option)
+    (void)src_dn;
     const unsigned int gmask = (LG == 32) ? 0xffffffffu : ((1u << LG) - 1u);
     double* tile = tiles[wib] + (lane / LG) * kGroupTile;
     const int N = a.N;
@@ -819,7 +964,27 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
         if (one_m_dq > one_m_disc)
             j1 = (int)fmin(fmax(floor(0.5 * ((double)N + log(K * (one_m_disc / one_m_dq) / L.S0) / log(L.u))) + 1.0, 0.0),
                            (double)(N + 1));
-        const bool eligible = wanted && L.ok && (L.sgn < 0.0) && q >= 0.0 && one_m_disc > 1e-9 && L.R >= kZoneSeg;
+        // Drifting walk, q > 0: a node can only choose exercise if S < S1 (cont >= disc*K - S*e^{-q dt} whatever its
+        // children chose).  On the levels k < k_pin even node 0 lies above S1, so NO node of the tree is an exercise
+        // node: the window then starts at node 0 (it still drifts; what enters below node 0 never reaches a node of
+        // the tree) and neither the bottom nor the top test applies.  k only falls, so this regime lasts to level 0.
+        int k_pin = 0;
+#ifndef OPTP_NO_PIN
+        if (kZoneDrift && one_m_dq > 0.0)
+            k_pin = (int)fmin(fmax(ceil(-log(K * (one_m_disc / one_m_dq) / L.S0) / log(L.u) - 0.01), 0.0), (double)(N + 1));
+#endif
+        bool eligible = wanted && L.ok && (L.sgn < 0.0) && q >= 0.0 && one_m_disc > 1e-9;
+        // the scale of a segment stays within 2^+-200: pd^-kSeg -- drifting walk: (pd*pu)^-(kSeg/2), a pair of levels
+        // scales by 1/(pd*pu).  (The retry pass walks shorter segments and takes what fails this on the long ones.)
+        // `retry`: fails only the scale bound of THIS schedule -- for the retry pass, whoever shares its warp
+        bool retry = false;
+        if (kZoneDrift) {
+            const bool scale_ok = (fabs(log(L.pd)) + fabs(log(L.pu))) * (double)kSeg <= 276.0;
+            retry = eligible && !scale_ok && !RIG;
+            eligible = eligible && scale_ok;
+        } else {
+            eligible = eligible && L.R >= kZoneSeg;
+        }
         // An American call on an asset that pays no dividend is never exercised early: with q <= 0 and
         // r > 0, cont >= S*e^{-q dt} - K*disc > S - K at every node, so binomial.py:30-36 always keeps the
         // continuation value.  Such contracts (status 3) go to the European full-width kernel, which is
@@ -837,34 +1002,43 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
         bool fail = !eligible, too_wide = false;
         if (!__any_sync(0xffffffffu, eligible)) {
             if (wanted && L.ok && gl == 0) {
-                const unsigned char dc = declined_code();
-                a.status[o] = dc;
-                if (a.decl_count) atomicAdd(&a.decl_count[dc - 2], 1u);
+                if (retry && a.wl_rig) {
+                    a.wl_rig[atomicAdd(a.wl_rig_n, 1u)] = (unsigned int)o;
+                } else {
+                    const unsigned char dc = declined_code();
+                    a.status[o] = dc;
+                    if (a.decl_count) atomicAdd(&a.decl_count[dc - 2], 1u);
+                }
             }
             continue;
         }
         // exercise values: node m of Z (m = index - w0) is sgn*S0*u^(2*(w0 + (m & ~3)) - k) * u^(2*(m & 3)),
         // the first factor through exp(), the second from {1, u^2, u^4, u^6} -- the SAME two factors
         // whatever G is, so that a node's arithmetic does not depend on the lane layout
-        double ulo[G];
+        double ulo[BZ];
         {
             const double u2 = L.u * L.u;
             const double t4[4] = {1.0, u2, u2 * u2, u2 * u2 * u2};
 #pragma unroll
-            for (int i = 0; i < G; ++i) {
-                const int b = (gl * G + i) & 3;
+            for (int i = 0; i < BZ; ++i) {
+                const int b = (gl * BZ + i) & 3;
                 ulo[i] = (b == 0) ? t4[0] : (b == 1) ? t4[1] : (b == 2) ? t4[2] : t4[3];
             }
         }
-        const int quad0 = (gl * G) & ~3;  // first node of this lane's quad, relative to w0
+        const int quad0 = (gl * BZ) & ~3;  // first node of this lane's quad, relative to w0
+        DriftConsts kB;
+        kB.inv_pu = 1.0 / L.pu;
+        kB.rho2 = L.pd * kB.inv_pu;
+        kB.d_pu = kB.inv_pu / L.u;
+        kB.ulo_below = 1.0 / (L.u * L.u);
         const double sS0 = L.sgn * L.S0;  // (exact: sgn = -1 for every option that is walked)
         const double thr = K * 8.2718061255302767e-25;  // 2^-80 K (K itself is not kept across the walk)
         const double ln_u = log(L.u);
-        double back_full = 1.0;  // pd^kSeg by square-and-multiply
+        double back_full = 1.0;  // pd^kSeg by square-and-multiply (drifting walk: (pd*pu)^(kSeg/2))
         {
-            double sq = L.pd;
+            double sq = kZoneDrift ? L.pd * L.pu : L.pd;
 #pragma unroll
-            for (int e = kSeg; e > 0; e >>= 1) {
+            for (int e = kZoneDrift ? kSeg / 2 : kSeg; e > 0; e >>= 1) {
                 if (e & 1) back_full *= sq;
                 sq *= sq;
             }
@@ -883,9 +1057,12 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             // q > r and more than one option per warp: by level 0 the band reaches from below S1 to ~10.2
             // standard deviations above the strike, i.e. at least (jz - j1) + 5.1 sqrt(N) nodes.  A contract
             // that cannot fit this layout goes to the next one now instead of after a wasted partial walk.
-            if (G > 1 && !fail && j1 <= N + 1 && (jz - (double)j1) + 4.6 * sqrt((double)N) > (double)(32 * (1 + kMaxM)))
+            if (G > 1 && !fail && j1 <= N + 1 && (jz - (double)j1) + 4.6 * sqrt((double)N) > (double)(ZW + 32 * kMaxM))
                 fail = too_wide = true;
-            const double w = fmin(fmax(floor(jz) - 28.0, 0.0), (double)max(0, N + 1 - 32));
+            // (drifting walk: the origin may be negative -- the tree extended downwards, see OPTP_ZONE_DRIFT)
+            // (the same origin whatever G is: the two factors of a node's exercise value depend on it)
+            const double w = kZoneDrift ? fmin(fmax(floor(jz) - 12.0, -268435456.0), (double)(N + 1 - 16))
+                                        : fmin(fmax(floor(jz) - 28.0, 0.0), (double)max(0, N + 1 - 32));
             w0 = fail ? 0 : (int)w;
             const double sbN = sS0 * exp(ln_u * (double)(2 * (w0 + quad0) - N));
 #pragma unroll
@@ -908,20 +1085,22 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             // jlo = first node that did not choose exercise
             const unsigned int contm = ~exmask & ((1u << BZ) - 1u);
             const int first_cont = contm ? (__ffs(contm) - 1) : BZ;
-            const unsigned int has_cont = (__ballot_sync(0xffffffffu, first_cont < BZ) >> gb) & gmask;
+            // (the boundary is looked for among the first ZT nodes whatever G is, see ZT)
+            constexpr unsigned int zt_mask = (ZT / BZ >= 32) ? 0xffffffffu : ((1u << (ZT / BZ)) - 1u);
+            const unsigned int has_cont = (__ballot_sync(0xffffffffu, first_cont < BZ) >> gb) & gmask & zt_mask;
             const int f_cont = has_cont ? (__ffs(has_cont) - 1) : 0;  // always one of the option's lanes
             const int s_cont = __shfl_sync(0xffffffffu, first_cont, gb + f_cont);
-            jlo = has_cont ? (w0 + f_cont * BZ + s_cont) : (w0 + 32);
+            jlo = has_cont ? (w0 + f_cont * BZ + s_cont) : (w0 + ZT);
             // jhi = 1 + last node worth more than 2^-80 K.  A put's value falls with the node index, so
             // the live nodes are a prefix of the window: find the last lane whose FIRST node is live
             // from the registers, then count the live nodes of that lane's chunk from the tile.
-            const bool c0_live = (BC > 0) && c[0] > thr && (w0 + 32 + gl * BC) <= k;
+            const bool c0_live = (BC > 0) && c[0] > thr && (w0 + ZW + gl * BC) <= k;
             const bool z0_live = z[0] > thr && (w0 + gl * BZ) <= k;
             const unsigned int liveC = (__ballot_sync(0xffffffffu, c0_live) >> gb) & gmask;
             const unsigned int liveZ = (__ballot_sync(0xffffffffu, z0_live) >> gb) & gmask;
             int chunk0, chunk_n;  // the chunk that holds the last live node (window-relative), its length
             if (liveC) {
-                chunk0 = 32 + (31 - __clz(liveC)) * BC;
+                chunk0 = ZW + (31 - __clz(liveC)) * BC;
                 chunk_n = BC;
             } else {
                 chunk0 = liveZ ? (31 - __clz(liveZ)) * BZ : 0;
@@ -938,12 +1117,13 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             }
             jhi = w0 + chunk0 + n_live;
             if (jhi < jlo) jhi = jlo;
-            // the window bottom must still be inside the exercise region (or be node 0)
-            if (w0 > 0 && jlo <= w0) fail = true;
+            // the window bottom must still be inside the exercise region (or be node 0; the drifting walk runs on
+            // the tree extended downwards, where there always is a node below)
+            if ((kZoneDrift ? (k >= k_pin) : (w0 > 0)) && jlo <= w0) fail = true;
         };
         measure_band();
         unsigned int cnt_fp64 = 0, cnt_nodes = 0;  // per lane; COUNT builds only
-        int width_old = 32;  // M = 0 at level N
+        int width_old = ZW;  // M = 0 at level N
         if (k > 0 && __reduce_or_sync(0xffffffffu, (j1 <= N + 1 && !fail) ? 1u : 0u) != 0u) {
             // q > r (see `jump`): from level N-1 on the boundary is the first node above S1, far below
             // the strike.  Level N is re-tabulated in the tile from a lower origin, so that the
@@ -952,9 +1132,9 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             int wl = w0, span = 0;
             if (mine) {
                 jlo = j1;
-                wl = max(0, j1 - kZoneBelow);
-                span = w0 + 32 - wl;
-                if (span > 32 * (1 + kMaxM)) fail = too_wide = true;
+                wl = kZoneDrift ? ((N < k_pin) ? 0 : j1 - kZoneBelow) : max(0, j1 - kZoneBelow);
+                span = w0 + ZW - wl;
+                if (span > ZW + 32 * kMaxM) fail = too_wide = true;
             }
             const bool refill = mine && !fail && wl < w0;
             if (!refill) span = 0;
@@ -981,24 +1161,35 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
         while (true) {
             // (REDUX, not a vote: ptxas treats the result of __any_sync as divergent, and a divergent exit here
             // puts a BRA.DIV convergence check and a dozen register moves into every level loop below)
-            if (k == 0 || __reduce_or_sync(0xffffffffu, fail ? 0u : 1u) == 0u) break;  // nothing left to walk in this warp
+            // (the drifting walk steps in pairs of levels; an odd last level is taken in closed form after the loop)
+            if (k <= (kZoneDrift ? 1 : 0) || __reduce_or_sync(0xffffffffu, fail ? 0u : 1u) == 0u) break;  // nothing left to walk in this warp
             // ---- next segment: levels k-1 ... k-nlev, fixed schedule -------------------------------
-            const int nlev = min(k == N ? kSeg0 : kSeg, k);
+            const int nlev = kZoneDrift ? (min(k == N ? kSeg0 : kSeg, k) & ~1) : min(k == N ? kSeg0 : kSeg, k);
             const int top = min(jhi, k + 1);  // exclusive; node `top` of level k is 0 (or dead)
             // Z's bottom sits kZoneBelow nodes under the boundary (see kZoneSeg)
-            int w0n = max(0, jlo - kZoneBelow);
+            const bool pinned = kZoneDrift && k < k_pin;  // no exercise node left in the tree (see k_pin)
+            int w0n = kZoneDrift ? (pinned ? 0 : jlo - kZoneBelow) : max(0, jlo - kZoneBelow);
             int need = 0, n_chk = 0;
-            if (top > w0n + 32) {
-                need = (top - (w0n + 32) + 31) >> 5;
-                // the top test is evaluated while Z's top node exists: level >= w0n + 31
-                n_chk = min(nlev, max(0, k - (w0n + 31)));
+            // drifting walk: the window's top falls by nlev/2 nodes over the segment and must not fall below `top`
+            const int drift = kZoneDrift ? (nlev >> 1) : 0;
+            if (top + drift > w0n + ZW) {
+                need = (top + drift - (w0n + ZW) + 31) >> 5;
                 if (!fail && need > kMaxM) fail = too_wide = true;
             }
+            // the top test is evaluated while the tested node exists: its index w0n + ZT - 1 (minus one per B level)
+            // is at most the level.  (ZT, not ZW: whether a contract passes must not depend on G.)
+            if (!pinned && top + drift > w0n + ZT)
+                n_chk = kZoneDrift ? min(nlev, max(0, 2 * (k - (w0n + ZT - 1)))) : min(nlev, max(0, k - (w0n + ZT - 1)));
             if (fail) {
                 w0n = 0;
                 need = 0;
                 n_chk = 0;
             }
+#ifdef OPTP_ZONE_DEBUG
+            if (gl == 0 && wanted)
+                printf("o=%llu G=%d k=%d nlev=%d pinned=%d k_pin=%d jlo=%d jhi=%d top=%d w0=%d w0n=%d need=%d n_chk=%d fail=%d wide=%d M_old=%d width_old=%d\n",
+                       o, G, k, nlev, (int)pinned, k_pin, jlo, jhi, top, w0, w0n, need, n_chk, (int)fail, (int)too_wide, M, width_old);
+#endif
             const int Mn = __reduce_max_sync(0xffffffffu, need);
             const int BCn = G * Mn;
             // ---- re-pack level k from (w0, M) to (w0n, Mn) ------------------------------------------
@@ -1016,7 +1207,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
                 else val = tile[OPTP_ZP(jr)];
                 z[i] = val;
             }
-            const int jr0 = w0n + 32 + gl * BCn - w0;
+            const int jr0 = w0n + ZW + gl * BCn - w0;
             const int lim = max(0, min(width_old, top - w0));
             w0 = w0n;
             M = Mn;
@@ -1024,16 +1215,21 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             double back = back_full;
             if (nlev != kSeg) {  // first or last (partial) segment: pd^nlev by square-and-multiply
                 back = 1.0;
-                double sq = L.pd;
-                for (int e = nlev; e > 0; e >>= 1) {
+                double sq = kZoneDrift ? L.pd * L.pu : L.pd;
+                for (int e = kZoneDrift ? (nlev >> 1) : nlev; e > 0; e >>= 1) {
                     if (e & 1) back *= sq;
                     sq *= sq;
                 }
             }
 #define OPTP_ZONE_CASE(m)                                                                                          \
     case m:                                                                                                        \
-        if constexpr ((m) <= kMaxM)                                                                                \
-            exmask = zone_segment<G, ((m) <= kMaxM ? (m) : 0)>(z, c, ulo, L, gl, src, sb, nlev, back, tile, jr0, lim, n_ex0, t_exT); \
+        if constexpr ((m) <= kMaxM) {                                                                              \
+            if constexpr (kZoneDrift)                                                                              \
+                exmask = zone_segment_drift<G, ((m) <= kMaxM ? (m) : 0)>(z, c, ulo, L, kB, pinned ? 0.0 : kB.ulo_below, gl, src, src_dn, sb, nlev >> 1, \
+                                                                         back, tile, jr0, lim, n_ex0, t_exT);      \
+            else                                                                                                   \
+                exmask = zone_segment<G, ((m) <= kMaxM ? (m) : 0)>(z, c, ulo, L, gl, src, sb, nlev, back, tile, jr0, lim, n_ex0, t_exT); \
+        }                                                                                                          \
         break;
             switch (M) {
                 OPTP_ZONE_CASE(0) OPTP_ZONE_CASE(1) OPTP_ZONE_CASE(2) OPTP_ZONE_CASE(3) OPTP_ZONE_CASE(4)
@@ -1051,24 +1247,52 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             // chose exercise at EVERY level; everything in C is a continuation node only while Z's
             // top node chose continuation at every level it exists
             const int bottom_ex = __shfl_sync(0xffffffffu, n_ex0, gb);
-            const int top_ex = __shfl_sync(0xffffffffu, t_exT, gb + LG - 1);
-            if (w0 > 0 && bottom_ex != nlev) fail = true;
-            if (top_ex < n_chk) fail = true;  // (exercise events while Z's top node is outside the tree do not count)  // (exercise events while Z's top node is outside the tree do not count)
+            const int top_ex = __shfl_sync(0xffffffffu, t_exT, gb + ZT / BZ - 1);
+            if ((kZoneDrift ? !pinned : (w0 > 0)) && bottom_ex != nlev) fail = true;
+            if (top_ex < n_chk) fail = true;  // (exercise events while Z's top node is outside the tree do not count)
             if (COUNT) {
-                // per lane and level: Z nodes 2 DFMA + 1 DSETP each, C nodes 1 DFMA each, 2 scaling DMULs
-                cnt_fp64 += (unsigned int)(nlev * (3 * G + G * M + 2));
-                cnt_nodes += (unsigned int)(nlev * (G + G * M));
+                // per lane and level: Z nodes 2 DFMA + 1 DSETP each, C nodes 1 DFMA each, 2 scaling DMULs (drifting
+                // walk, per pair of levels: the exercise value below the window and the cross links, 3 or 5 DFMAs)
+                cnt_fp64 += (unsigned int)(nlev * (3 * BZ + G * M + 2)) + (kZoneDrift ? (unsigned int)((nlev >> 1) * (M > 0 ? 5 : 3)) : 0u);
+                cnt_nodes += (unsigned int)(nlev * (BZ + G * M));
             }
             k -= nlev;
+            if (kZoneDrift) w0 -= nlev >> 1;  // the origin fell by one node per B level
             measure_band();
-            width_old = 32 * (1 + M);
+            width_old = ZW + 32 * M;
         }
         if (COUNT && lane == 0 && a.op_count) {
             atomicAdd(&a.op_count[0], 32ull * cnt_fp64);
             atomicAdd(&a.op_count[1], 32ull * cnt_nodes);
         }
         // level 0: node 0 is in the window (w0 == 0) or below it (then it is an exercise node)
-        const double v0 = __shfl_sync(0xffffffffu, z[0], gb);
+        double v0 = __shfl_sync(0xffffffffu, z[0], gb);
+        bool v0_below = (w0 != 0);
+        if (kZoneDrift) {
+            // the tile holds level k (0, or 1 when N is odd) in node order; node j sits at j - w0, is an exercise node
+            // below the window and dead above it
+            auto node = [&](int j) -> double {
+                const int pos = j - w0;
+                if (pos < 0) return fma(sS0, exp(ln_u * (double)(2 * j - k)), L.sK);
+                if (pos >= width_old) return 0.0;
+                return tile[OPTP_ZP(pos)];
+            };
+            v0 = node(0);
+            v0_below = (w0 > 0);
+            if (k == 1) {  // binomial.py:28-36 for the one node of level 0
+                const double cont = fma(L.pu, node(1), L.pd * v0);
+                const double e0 = sS0 + L.sK;
+#ifdef OPTP_ZONE_DEBUG
+                if (gl == 0 && wanted) printf("o=%llu G=%d FINAL node0=%.17g node1=%.17g cont=%.17g e0=%.17g pu=%.17g pd=%.17g\n", o, G, v0, node(1), cont, e0, L.pu, L.pd);
+#endif
+                v0 = e0 > cont ? e0 : cont;
+                v0_below = false;
+            }
+            __syncwarp();  // the tile is free for the next group of contracts
+        }
+#ifdef OPTP_ZONE_DEBUG
+        if (gl == 0 && wanted) printf("o=%llu G=%d END k=%d w0=%d width_old=%d v0=%g below=%d fail=%d\n", o, G, k, w0, width_old, v0, (int)v0_below, (int)fail);
+#endif
         if (wanted && L.ok && gl == 0) {
             if (fail) {
                 // too wide for this lane layout: the next narrower pass walks it.  Otherwise, on the measured
@@ -1086,7 +1310,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             } else {
                 // below the window at level 0: immediate exercise, K - S0 (for a call, through its dual put, S0 - K)
                 const double intrinsic = (a.is_call[o] != 0) ? (a.S0[o] - a.K[o]) : (a.K[o] - a.S0[o]);
-                a.price[o] = (w0 == 0) ? v0 : intrinsic;
+                a.price[o] = v0_below ? intrinsic : v0;
                 a.status[o] = 0;
             }
         }

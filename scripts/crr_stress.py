@@ -6,6 +6,7 @@ full-width kernel anyway: a decline costs time, never accuracy).  Usage: python 
 import json
 import os
 import sys
+import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "options-pricing-engine-black-scholes-binomial-monte-carlo_b200")]
@@ -24,6 +25,9 @@ for N in (64, 250, 1000, 1023, 2500):
     q = np.where(g.random(n) < 0.5, 0.0, g.uniform(0.0, 0.12, n))
     is_call = (g.random(n) < 0.3).astype(np.uint8)
     band, st = bn.crr_batch(S0, K, T, r, q, sig, is_call, N, american=True, return_status=True)
+    t0 = time.perf_counter()
+    bn.crr_batch(S0, K, T, r, q, sig, is_call, N, american=True)
+    secs = time.perf_counter() - t0
     nv.set_option("crr_band_only", 1)
     _, st_only = bn.crr_batch(S0, K, T, r, q, sig, is_call, N, american=True, return_status=True)
     nv.set_option("crr_band_only", 0)
@@ -37,4 +41,4 @@ for N in (64, 250, 1000, 1023, 2500):
                       "status_equal": bool(np.array_equal(st, st_full)),
                       "max_rel_err_vs_full_width": float(err.max()), "declined_by_two_zone_passes": int((st_only == 2).sum()),
                       "declined_puts_r_gt_q": int(((st_only == 2) & puts).sum()), "puts_r_gt_q": int(puts.sum()),
-                      "never_exercised": int((st_only == 3).sum())}), flush=True)
+                      "never_exercised": int((st_only == 3).sum()), "seconds_host_api": round(secs, 4)}), flush=True)
