@@ -640,7 +640,7 @@ constexpr int kZoneWarps = OPTP_ZONE_WARPS;  // warps per CTA of the two-zone ke
 // argument above holds and on which nothing below a node ever enters its value), so there is no second code path
 // for windows pinned at node 0.
 #ifndef OPTP_ZONE_DRIFT
-#define OPTP_ZONE_DRIFT 0
+#define OPTP_ZONE_DRIFT 1
 #endif
 constexpr bool kZoneDrift = OPTP_ZONE_DRIFT != 0;
 #ifndef OPTP_ZONE_SEG
@@ -664,8 +664,25 @@ __host__ __device__ constexpr int zone_zw(int G) { return zone_bz(G) * (32 / G);
 // 224 nodes), 12 at two (416), 24 at one (800).  A contract whose band is too wide for the layout it was
 // tried in keeps status 4 and is walked again by the next narrower-group pass (launch_crr); the
 // arithmetic applied to a node does not depend on the layout, so neither does the price.
-constexpr int kZoneLaneC = 24;
-__host__ __device__ constexpr int zone_max_m(int G) { return kZoneLaneC / G; }
+#ifndef OPTP_ZONE_LANEC
+#define OPTP_ZONE_LANEC (OPTP_ZONE_DRIFT ? 28 : 24)
+#endif
+constexpr int kZoneLaneC = OPTP_ZONE_LANEC;
+static_assert(kZoneLaneC <= 28 && kZoneLaneC % 4 == 0, "the segment dispatch covers M <= 28");
+// C grows in chunks of zone_ch(G) nodes per option, zone_bcu(G) nodes per lane; M counts chunks.  Chunks of 32 nodes.
+// (-DOPTP_ZONE_CH16=1, drifting walk with two or four options per warp: chunks of 16.  It trims ~8 of ~140 C nodes per
+// level and was measured SLOWER, 42.9 M against 49.4 M options/s on config 2: twice as many segment bodies for the
+// instruction caches, and lane chunks of 2, 6, 10 ... doubles that the tile padding was not laid out for.)
+#ifndef OPTP_ZONE_CH16
+#define OPTP_ZONE_CH16 0
+#endif
+__host__ __device__ constexpr int zone_ch(int G) { return (kZoneDrift && OPTP_ZONE_CH16 && G >= 2) ? 16 : 32; }
+__host__ __device__ constexpr int zone_bcu(int G) { return zone_ch(G) * G / 32; }
+__host__ __device__ constexpr int zone_max_m(int G) { return kZoneLaneC / zone_bcu(G); }
+__host__ __device__ constexpr int zone_cap(int G) { return 32 + zone_ch(G) * zone_max_m(G); }  // nodes of a window
+// nodes of C that are not band: the drifting walk starts C 3 nodes above the boundary and keeps nlev/2 nodes above the
+// live top; with a fixed origin C starts 2 nodes above the boundary
+__host__ __device__ constexpr int zone_overhead() { return kZoneDrift ? (kZoneSeg / 2 - 3) : -2; }
 // re-pack tile, node-ordered per option: node e lives at e + (e >> OPTP_ZONE_PAD_SHIFT), one pad double per
 // 2^shift nodes.  A lane's chunk of 4M consecutive nodes then starts 5M doubles after its neighbour's (shift 2):
 // 5M mod 16 runs through distinct bank pairs for the lanes of an option (M != 4), and the tile of the next option
@@ -675,8 +692,8 @@ __host__ __device__ constexpr int zone_max_m(int G) { return kZoneLaneC / G; }
 #endif
 __host__ __device__ constexpr int zone_pad_c(int e) { return e + (e >> OPTP_ZONE_PAD_SHIFT); }
 __host__ __device__ constexpr int zone_group_tile(int G) {
-    // nodes 32 (1 + kMaxM) padded, rounded up to 8 (mod 16)
-    return ((zone_pad_c(32 * (1 + zone_max_m(G))) + 7) & ~15) + 8;
+    // zone_cap(G) nodes padded, rounded up to 8 (mod 16)
+    return ((zone_pad_c(zone_cap(G)) + 7) & ~15) + 8;
 }
 __device__ __forceinline__ int zone_pad(int e) { return e + (e >> OPTP_ZONE_PAD_SHIFT); }
 // -DOPTP_ZONE_CHECK (OPTP_NVCC_FLAGS, build_native.py --force): every tile access of the two-zone kernel is
@@ -686,13 +703,13 @@ __device__ __forceinline__ int zone_pad_checked(int e, int limit) {
     if ((unsigned int)e >= (unsigned int)limit) __trap();
     return zone_pad(e);
 }
-#define OPTP_ZP(e) zone_pad_checked((e), 32 * (1 + kMaxM))
+#define OPTP_ZP(e) zone_pad_checked((e), zone_cap(G))
 #else
 #define OPTP_ZP(e) zone_pad(e)
 #endif
-static_assert(zone_pad_c(32 * (1 + zone_max_m(4))) <= zone_group_tile(4) && zone_group_tile(4) % 16 == 8, "tile too small");
-static_assert(zone_pad_c(32 * (1 + zone_max_m(2))) <= zone_group_tile(2) && zone_group_tile(2) % 16 == 8, "tile too small");
-static_assert(zone_pad_c(32 * (1 + zone_max_m(1))) <= zone_group_tile(1) && zone_group_tile(1) % 16 == 8, "tile too small");
+static_assert(zone_pad_c(zone_cap(4)) <= zone_group_tile(4) && zone_group_tile(4) % 16 == 8, "tile too small");
+static_assert(zone_pad_c(zone_cap(2)) <= zone_group_tile(2) && zone_group_tile(2) % 16 == 8, "tile too small");
+static_assert(zone_pad_c(zone_cap(1)) <= zone_group_tile(1) && zone_group_tile(1) % 16 == 8, "tile too small");
 
 // One segment in layout (BZ = G, BC = G*M), M a compile-time constant:
 //   * the lane's C nodes are loaded from the node-ordered tile, which holds level k in the PREVIOUS layout
@@ -710,7 +727,7 @@ __device__ __forceinline__ unsigned int zone_segment(double (&z)[G], double (&c)
                                                      const double (&ulo)[G], const Lattice& L, int gl,
                                                      int src, double sb, int nlev, double back, double* tile,
                                                      int jr0, int lim, int& n_ex0_out, int& t_exT_out) {
-    constexpr int BZ = G, BC = G * M, LG = 32 / G;
+    constexpr int BZ = G, BC = zone_bcu(G) * M, LG = 32 / G;
     constexpr int kMaxM = zone_max_m(G);  // (OPTP_ZP's bound in -DOPTP_ZONE_CHECK builds)
     (void)kMaxM;
 #pragma unroll
@@ -794,7 +811,7 @@ __device__ __forceinline__ unsigned int zone_segment_drift(double (&z)[zone_bz(G
                                                            const DriftConsts& kB, double ub, int gl, int src_up,
                                                            int src_dn, double sb, int npairs, double back, double* tile, int jr0,
                                                            int lim, int& n_ex0_out, int& t_exT_out) {
-    constexpr int BZ = zone_bz(G), BC = G * M, LG = 32 / G, ZW = BZ * LG;
+    constexpr int BZ = zone_bz(G), BC = zone_bcu(G) * M, LG = 32 / G, ZW = BZ * LG;
     constexpr int kMaxM = zone_max_m(G);  // (OPTP_ZP's bound in -DOPTP_ZONE_CHECK builds)
     (void)kMaxM;
 #pragma unroll
@@ -897,13 +914,15 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
     constexpr int kSeg = RIG ? kZoneSegRig : kZoneSeg, kSeg0 = RIG ? kZoneSegRig : kZoneSeg0;
     constexpr int LG = 32 / G, BZ = zone_bz(G), ZW = zone_zw(G), BCMAX = kZoneLaneC, kMaxM = zone_max_m(G),
                   kGroupTile = zone_group_tile(G);
-    static_assert(ZW + 32 * kMaxM <= 32 * (1 + kMaxM), "the tile holds Z and kMaxM chunks of C");
+    constexpr int CH = zone_ch(G), BCU = zone_bcu(G);
+    static_assert(ZW + CH * kMaxM <= zone_cap(G) && BCU * kMaxM <= BCMAX, "the tile holds Z and kMaxM chunks of C");
     // the node whose choice of continuation covers everything above it: the last node of Z -- in the drifting walk
     // node 15 of the window for every G (at G = 1 Z is 32 nodes wide; a test that depended on G would let a contract
     // pass in one layout and go to the retry pass, i.e. another rounding, in another)
     constexpr int ZT = kZoneDrift ? 16 : ZW;
     static_assert(ZT % BZ == 0 && ZT <= ZW, "the tested node is the last node of a lane");
     __shared__ double tiles[kZoneWarps][G * kGroupTile];
+    __shared__ double stash_all[kZoneWarps][G][4];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int gl = lane & (LG - 1);        // lane within the option
@@ -1031,18 +1050,30 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
         kB.rho2 = L.pd * kB.inv_pu;
         kB.d_pu = kB.inv_pu / L.u;
         kB.ulo_below = 1.0 / (L.u * L.u);
-        const double sS0 = L.sgn * L.S0;  // (exact: sgn = -1 for every option that is walked)
-        const double thr = K * 8.2718061255302767e-25;  // 2^-80 K (K itself is not kept across the walk)
-        const double ln_u = log(L.u);
-        double back_full = 1.0;  // pd^kSeg by square-and-multiply (drifting walk: (pd*pu)^(kSeg/2))
+        // Four per-option constants that are only used BETWEEN segments live in shared memory, not in registers (the
+        // level loops need every register: 28 C nodes + 2 Z nodes + 13 multipliers per lane at four options per warp)
+        volatile double* const stash = stash_all[wib][lane / LG];
         {
+            double bf = 1.0;  // pd^kSeg by square-and-multiply (drifting walk: (pd*pu)^(kSeg/2))
             double sq = kZoneDrift ? L.pd * L.pu : L.pd;
 #pragma unroll
             for (int e = kZoneDrift ? kSeg / 2 : kSeg; e > 0; e >>= 1) {
-                if (e & 1) back_full *= sq;
+                if (e & 1) bf *= sq;
                 sq *= sq;
             }
+            __syncwarp();  // (the previous group's readers are done)
+            if (gl == 0) {
+                stash[0] = L.sgn * L.S0;                  // (exact: sgn = -1 for every option that is walked)
+                stash[1] = K * 8.2718061255302767e-25;    // 2^-80 K (K itself is not kept across the walk)
+                stash[2] = log(L.u);
+                stash[3] = bf;
+            }
+            __syncwarp();
         }
+#define sS0 (stash[0])
+#define thr (stash[1])
+#define ln_u (stash[2])
+#define back_full (stash[3])
         double z[BZ], c[BCMAX];
 #pragma unroll
         for (int i = 0; i < BCMAX; ++i) c[i] = 0.0;
@@ -1057,7 +1088,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             // q > r and more than one option per warp: by level 0 the band reaches from below S1 to ~10.2
             // standard deviations above the strike, i.e. at least (jz - j1) + 5.1 sqrt(N) nodes.  A contract
             // that cannot fit this layout goes to the next one now instead of after a wasted partial walk.
-            if (G > 1 && !fail && j1 <= N + 1 && (jz - (double)j1) + 4.6 * sqrt((double)N) > (double)(ZW + 32 * kMaxM))
+            if (G > 1 && !fail && j1 <= N + 1 && (jz - (double)j1) + 4.6 * sqrt((double)N) + (double)zone_overhead() > (double)(CH * kMaxM))
                 fail = too_wide = true;
             // (drifting walk: the origin may be negative -- the tree extended downwards, see OPTP_ZONE_DRIFT)
             // (the same origin whatever G is: the two factors of a node's exercise value depend on it)
@@ -1081,7 +1112,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
         __syncwarp();
         auto measure_band = [&]() {
             // ---- level k goes to the tile (node-ordered); measure its band [jlo, jhi) per option -----
-            const int BC = G * M;
+            const int BC = BCU * M;
             // jlo = first node that did not choose exercise
             const unsigned int contm = ~exmask & ((1u << BZ) - 1u);
             const int first_cont = contm ? (__ffs(contm) - 1) : BZ;
@@ -1134,7 +1165,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
                 jlo = j1;
                 wl = kZoneDrift ? ((N < k_pin) ? 0 : j1 - kZoneBelow) : max(0, j1 - kZoneBelow);
                 span = w0 + ZW - wl;
-                if (span > ZW + 32 * kMaxM) fail = too_wide = true;
+                if (span > ZW + CH * kMaxM) fail = too_wide = true;
             }
             const bool refill = mine && !fail && wl < w0;
             if (!refill) span = 0;
@@ -1173,7 +1204,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             // drifting walk: the window's top falls by nlev/2 nodes over the segment and must not fall below `top`
             const int drift = kZoneDrift ? (nlev >> 1) : 0;
             if (top + drift > w0n + ZW) {
-                need = (top + drift - (w0n + ZW) + 31) >> 5;
+                need = (top + drift - (w0n + ZW) + CH - 1) / CH;
                 if (!fail && need > kMaxM) fail = too_wide = true;
             }
             // the top test is evaluated while the tested node exists: its index w0n + ZT - 1 (minus one per B level)
@@ -1185,13 +1216,8 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
                 need = 0;
                 n_chk = 0;
             }
-#ifdef OPTP_ZONE_DEBUG
-            if (gl == 0 && wanted)
-                printf("o=%llu G=%d k=%d nlev=%d pinned=%d k_pin=%d jlo=%d jhi=%d top=%d w0=%d w0n=%d need=%d n_chk=%d fail=%d wide=%d M_old=%d width_old=%d\n",
-                       o, G, k, nlev, (int)pinned, k_pin, jlo, jhi, top, w0, w0n, need, n_chk, (int)fail, (int)too_wide, M, width_old);
-#endif
             const int Mn = __reduce_max_sync(0xffffffffu, need);
-            const int BCn = G * Mn;
+            const int BCn = BCU * Mn;
             // ---- re-pack level k from (w0, M) to (w0n, Mn) ------------------------------------------
             // this lane's first Z node of the new layout at level k: sgn*S0*u^(2j - k).  (A running product
             // sb *= (u^2)^m instead of this exp() -- five predicated square-and-multiply steps -- was tried: no
@@ -1237,6 +1263,7 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
                 OPTP_ZONE_CASE(10) OPTP_ZONE_CASE(11) OPTP_ZONE_CASE(12) OPTP_ZONE_CASE(13) OPTP_ZONE_CASE(14)
                 OPTP_ZONE_CASE(15) OPTP_ZONE_CASE(16) OPTP_ZONE_CASE(17) OPTP_ZONE_CASE(18) OPTP_ZONE_CASE(19)
                 OPTP_ZONE_CASE(20) OPTP_ZONE_CASE(21) OPTP_ZONE_CASE(22) OPTP_ZONE_CASE(23) OPTP_ZONE_CASE(24)
+                OPTP_ZONE_CASE(25) OPTP_ZONE_CASE(26) OPTP_ZONE_CASE(27) OPTP_ZONE_CASE(28)
                 default: break;
             }
 #undef OPTP_ZONE_CASE
@@ -1253,13 +1280,13 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             if (COUNT) {
                 // per lane and level: Z nodes 2 DFMA + 1 DSETP each, C nodes 1 DFMA each, 2 scaling DMULs (drifting
                 // walk, per pair of levels: the exercise value below the window and the cross links, 3 or 5 DFMAs)
-                cnt_fp64 += (unsigned int)(nlev * (3 * BZ + G * M + 2)) + (kZoneDrift ? (unsigned int)((nlev >> 1) * (M > 0 ? 5 : 3)) : 0u);
-                cnt_nodes += (unsigned int)(nlev * (BZ + G * M));
+                cnt_fp64 += (unsigned int)(nlev * (3 * BZ + BCU * M + 2)) + (kZoneDrift ? (unsigned int)((nlev >> 1) * (M > 0 ? 5 : 3)) : 0u);
+                cnt_nodes += (unsigned int)(nlev * (BZ + BCU * M));
             }
             k -= nlev;
             if (kZoneDrift) w0 -= nlev >> 1;  // the origin fell by one node per B level
             measure_band();
-            width_old = ZW + 32 * M;
+            width_old = ZW + CH * M;
         }
         if (COUNT && lane == 0 && a.op_count) {
             atomicAdd(&a.op_count[0], 32ull * cnt_fp64);
@@ -1282,17 +1309,11 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
             if (k == 1) {  // binomial.py:28-36 for the one node of level 0
                 const double cont = fma(L.pu, node(1), L.pd * v0);
                 const double e0 = sS0 + L.sK;
-#ifdef OPTP_ZONE_DEBUG
-                if (gl == 0 && wanted) printf("o=%llu G=%d FINAL node0=%.17g node1=%.17g cont=%.17g e0=%.17g pu=%.17g pd=%.17g\n", o, G, v0, node(1), cont, e0, L.pu, L.pd);
-#endif
                 v0 = e0 > cont ? e0 : cont;
                 v0_below = false;
             }
             __syncwarp();  // the tile is free for the next group of contracts
         }
-#ifdef OPTP_ZONE_DEBUG
-        if (gl == 0 && wanted) printf("o=%llu G=%d END k=%d w0=%d width_old=%d v0=%g below=%d fail=%d\n", o, G, k, w0, width_old, v0, (int)v0_below, (int)fail);
-#endif
         if (wanted && L.ok && gl == 0) {
             if (fail) {
                 // too wide for this lane layout: the next narrower pass walks it.  Otherwise, on the measured
@@ -1318,6 +1339,11 @@ __global__ void __launch_bounds__(kZoneWarps * 32, OPTP_ZONE_MINB4) crr_zone_ker
 }
 
 // ---------------------------------------------------------------- generic N: one option per CTA
+#undef sS0
+#undef thr
+#undef ln_u
+#undef back_full
+
 template <bool AMER>
 __global__ void __launch_bounds__(256) crr_cta_kernel(CrrArgs a) {
     extern __shared__ double sm[];
@@ -1568,6 +1594,10 @@ static int launch_crr(const CrrArgs& a_in, int american, cudaStream_t st, int sl
             if (G == 0) {
                 const unsigned long long warps = (unsigned long long)c.n_sm * 16;
                 G = (a.n >= 4 * warps) ? 4 : (a.n >= 2 * warps) ? 2 : 1;
+                // by level 0 a band spans ~10.2 standard deviations above the strike, 5.1 sqrt(N) nodes: where that
+                // cannot fit a lane layout, the pass in that layout would be walked in vain (N = 5000: a quarter of it)
+                const double width = 4.6 * sqrt((double)a.N) + (double)zone_overhead();
+                while (G > 1 && width > (double)(zone_ch(G) * zone_max_m(G))) G /= 2;
             }
         }
         unsigned int* wl[2] = {nullptr, nullptr};
