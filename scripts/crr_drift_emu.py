@@ -1,5 +1,10 @@
-"""Option-level emulation of the drift-window two-zone walk (unscaled arithmetic: tests the LOGIC -- window
-placement, virtual nodes, top rule, checks, final read -- not the rounding)."""
+#!/usr/bin/env python3
+"""Option-level emulation of the drifting-window two-zone CRR walk of csrc/crr_batch.cu (OPTP_ZONE_DRIFT) in plain
+unscaled numpy arithmetic: it tests the LOGIC -- window placement under the exercise boundary, A / B levels, nodes
+below node 0, the margin above the live top, the per-level bottom and top tests, the final read -- not the rounding,
+and it is where the schedule (Z width, nodes below the boundary, segment lengths) was chosen before any GPU time was
+spent.  `exact` restates binomial.py:7-38 for a put.
+Usage: python scripts/crr_drift_emu.py N n_contracts cfg2|wide ["seg0=32,seg=64,..."]   (tests/test_crr_drift_emulation_cpu.py)"""
 import sys, numpy as np
 
 def exact(S0, K, T, r, q, sg, N):

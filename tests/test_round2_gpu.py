@@ -332,7 +332,7 @@ def test_dev_launches_on_several_streams_overlap_safely(op):
 
 @pytest.mark.parametrize("N", [250, 1000, 1500])
 def test_crr_measured_segment_schedule_under_random_stress(op, N):
-    """The two-zone kernel walks 32 + 44 + 44 ... levels per segment on the MEASURED speed of the exercise boundary
+    """The two-zone kernel walks 32 + 64 + 64 ... levels per segment on the MEASURED speed of the exercise boundary
     (csrc/crr_batch.cu: kZoneSeg); exactness rests on its per-level checks, and contracts that fail them are retried
     on the rigorous schedule.  Wide random parameters (r dt down to 1e-8, 1.5 volatility, 10 years, deep in and out of
     the money, dividends, 30 % calls): every price equals the full-width kernel's, statuses are identical, and no
@@ -366,3 +366,39 @@ def test_crr_measured_segment_schedule_under_random_stress(op, N):
     puts = ok & (is_call == 0) & (r > q)
     left = int(((st_only == 2) & puts).sum())
     assert left <= (0 if N >= 1000 else 40), left
+
+
+def test_crr_drifting_window_regimes(op):
+    """The regimes of the drifting-window walk (csrc/crr_batch.cu, OPTP_ZONE_DRIFT) against the full-width kernel, in
+    RELATIVE terms down to prices of 1e-30 (an absolute bar hides a band that was lost on the way to level 0):
+    deep out-of-the-money contracts with q > 0, whose last levels run in the regime without exercise nodes (tree above
+    S1 = K(1-disc)/(1-e^{-q dt})) and whose window origin goes negative before that; odd tree depths (one closed-form
+    level at the end); trees narrower than Z; and all of it mixed into one batch with ordinary contracts, so that
+    every contract meets warp mates with wider and narrower bands."""
+    from optpricer_b200 import _native as nv
+    g = np.random.default_rng(77)
+    n = 24_000
+    S0 = g.uniform(20, 300, n)
+    K = S0 * np.exp(g.uniform(-1.3, 1.3, n))
+    T = np.exp(g.uniform(np.log(0.01), np.log(3.0), n))
+    sig = g.uniform(0.05, 0.9, n)
+    r = g.uniform(0.0005, 0.12, n)
+    q = np.where(g.random(n) < 0.25, 0.0, g.uniform(0.0, 0.1, n))
+    is_call = (g.random(n) < 0.3).astype(np.uint8)
+    for N in (1000, 999, 257, 31, 16, 3, 2, 1):
+        nv.set_option("crr_band", 0)
+        try:
+            full, st_f = op.crr_batch(S0, K, T, r, q, sig, is_call, N, american=True, return_status=True)
+        finally:
+            nv.set_option("crr_band", 1)
+        zone, st = op.crr_batch(S0, K, T, r, q, sig, is_call, N, american=True, return_status=True)
+        np.testing.assert_array_equal(st, st_f)
+        ok = st == 0
+        big = ok & (full > 1e-30)
+        rel = np.abs(zone[big] - full[big]) / full[big]
+        # values below 2^-80 K are cut (DESIGN section 4): relative agreement is asked above 1e-18 K, presence above 1e-30
+        firm = full[big] > 1e-18 * K[big]
+        assert rel[firm].max() < 1e-9, (N, rel[firm].max())
+        live = full[big] > 1e-21 * K[big]
+        assert np.all(zone[big][live] > 0.0), N
+        np.testing.assert_allclose(zone[ok], full[ok], rtol=1e-10, atol=1e-10)
