@@ -587,10 +587,11 @@ __global__ void __launch_bounds__(kBandWarps * 32, 5) crr_band_kernel(CrrArgs a)
 // Refinement of the banded kernel above, on three counts.
 //  (1) Inside the band almost every node is a CONTINUATION node: only the few nodes next to the
 //      early-exercise boundary can choose exercise.  The window is split in two zones:
-//        zone Z = [w0, w0 + 32)              full update  max(cont, K - S)   (3 FP64 ops + 2 selects per node)
-//        zone C = [w0 + 32, w0 + 32 + 32*M)  continuation only, A[j] = rho*A[j+1] + A[j]   (ONE DFMA per node)
-//      Z holds the margin below the boundary (the boundary index falls by at most one per level, see
-//      above: nlev + 2 nodes for a segment of nlev levels) and at least two nodes above it.
+//        zone Z = [w0, w0 + ZW)              full update  max(cont, K - S)   (3 FP64 ops + 2 selects per node)
+//        zone C = [w0 + ZW, w0 + ZW + 32*M)  continuation only, A[j] = rho*A[j+1] + A[j]   (ONE DFMA per node)
+//      Z holds the margin below the boundary and at least two nodes above it: ZW = 16 in the default build, whose
+//      window drifts with the boundary (OPTP_ZONE_DRIFT below), ZW = 32 with a fixed origin (-DOPTP_ZONE_DRIFT=0:
+//      the boundary index falls by at most one per level, see above).
 //      Why C needs no exercise test, checked at run time: on every level V + S is non-decreasing in
 //      the node index when q >= 0 (induction: pu*S(j+1) + pd*S(j) = S*e^{-q dt}), so the exercise
 //      nodes of a level are contiguous from the bottom; as long as the TOP node of Z chooses
@@ -601,7 +602,7 @@ __global__ void __launch_bounds__(kBandWarps * 32, 5) crr_band_kernel(CrrArgs a)
 //      keeps status 2 and is priced by the full-width kernel.
 //  (2) The per-level cost of a warp is dominated by instructions that do not depend on how many
 //      lanes do useful work (neighbour shuffles, scaling multiplies, loop control), so G = 4 (or 2)
-//      options share one warp, 32/G lanes each, every lane owning G nodes of Z and G*M nodes of C
+//      options share one warp, 32/G lanes each, every lane owning ZW*G/32 nodes of Z and G*M nodes of C
 //      of ITS option.  All options of a warp walk the same levels with the same layout (M = the
 //      widest C zone among them); everything else (lattice constants, window origin, band limits,
 //      failure flags) is per option.
@@ -615,6 +616,7 @@ __global__ void __launch_bounds__(kBandWarps * 32, 5) crr_band_kernel(CrrArgs a)
 #define OPTP_ZONE_WARPS 4
 #endif
 constexpr int kZoneWarps = OPTP_ZONE_WARPS;  // warps per CTA of the two-zone kernel
+// Fixed origin (-DOPTP_ZONE_DRIFT=0, the kernel of the first half of round 2; the default is the drifting walk below).
 // Z = [jlo - 30, jlo + 2): 30 nodes below the first continuation node jlo of the segment's first level.
 // RIGOROUSLY the boundary index falls by at most one per level (see above), which would allow segments of 28
 // levels.  Measured (scripts/crr_boundary_drop.py: the exact lattice boundary of 250 contracts over sigma in
