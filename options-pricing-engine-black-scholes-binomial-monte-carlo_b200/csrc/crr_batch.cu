@@ -1762,15 +1762,21 @@ extern "C" int optp_crr_batch(const double* S0, const double* K, const double* T
     // scratch is reserved before anything is in flight (an arena never grows under a running kernel)
     if (american)
         if (int e = crr_reserve_worklists(step)) return e;
-    const uint64_t group = step * kGroupSlices;
+    // (the very first slice is a quarter of the others: nothing runs on the device until its inputs have arrived)
+    const uint64_t head = (step == slice) ? slice / 4 : step;
+    const uint64_t group = step * (kGroupSlices - 1);
+    auto slice_len = [&](uint64_t lo, uint64_t g1) -> uint64_t {
+        const uint64_t want = (lo == 0) ? head : step;
+        return (g1 - lo < want) ? (g1 - lo) : want;
+    };
     const size_t gcol = (((size_t)(n < group ? n : group) * sizeof(double)) + 255) & ~(size_t)255;
     if (int e = host_arena_reserve(c.pin_out, gcol + (size_t)(n < group ? n : group))) return e;
     char* hout = (char*)c.pin_out.p;
     for (uint64_t g0 = 0; g0 < n; g0 += group) {
         const uint64_t g1 = (n - g0 < group) ? n : g0 + group;
         int s_idx = 0;
-        for (uint64_t lo = g0; lo < g1; lo += step, ++s_idx) {
-            const uint64_t m = (g1 - lo < step) ? (g1 - lo) : step;
+        for (uint64_t lo = g0, m = 0; lo < g1; lo += m, ++s_idx) {
+            m = slice_len(lo, g1);
             cudaEvent_t ev_in = c.events[3 * s_idx], ev_k = c.events[3 * s_idx + 1], ev_out = c.events[3 * s_idx + 2];
             for (int i = 0; i < 6; ++i)
                 OPTP_CUDA(cudaMemcpyAsync(in + i * colp + lo * sizeof(double), src[i] + lo, m * sizeof(double),
@@ -1800,8 +1806,8 @@ extern "C" int optp_crr_batch(const double* S0, const double* K, const double* T
             OPTP_CUDA(cudaEventRecord(ev_out, c.stream3));
         }
         s_idx = 0;
-        for (uint64_t lo = g0; lo < g1; lo += step, ++s_idx) {
-            const uint64_t m = (g1 - lo < step) ? (g1 - lo) : step;
+        for (uint64_t lo = g0, m = 0; lo < g1; lo += m, ++s_idx) {
+            m = slice_len(lo, g1);
             OPTP_CUDA(cudaEventSynchronize(c.events[3 * s_idx + 2]));
             memcpy(price_out + lo, hout + (lo - g0) * sizeof(double), m * sizeof(double));
             memcpy(status_out + lo, hout + gcol + (lo - g0), m);

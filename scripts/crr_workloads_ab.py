@@ -39,6 +39,9 @@ def worker():
         "puts_N5000": tuple(a[:10_000] for a in (S0, K, T, r, q, sig, is_call)) + (5000,),
         "puts_N1001": (S0, K, T, r, q, sig, is_call, 1001),
     }
+    if os.environ.get("AB_1M"):
+        big = cfg2_contracts(1_000_000)
+        cases = {"puts_N1000_1M_host_api": tuple(big) + (1000,), "puts_N1000_600k_host_api": tuple(a[:600_000] for a in big) + (1000,)}
     for name, a in cases.items():
         t, p = best(lambda: bn.crr_batch(*a[:7], a[7], american=True))
         out[name] = {"options_per_s": round(len(a[0]) / t), "checksum": float(np.sum(p[:1000]))}
