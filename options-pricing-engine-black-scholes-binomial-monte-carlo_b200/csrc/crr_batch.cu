@@ -817,10 +817,26 @@ __device__ __forceinline__ unsigned int zone_segment_drift(double (&z)[zone_bz(G
     constexpr int kMaxM = zone_max_m(G);  // (OPTP_ZP's bound in -DOPTP_ZONE_CHECK builds)
     (void)kMaxM;
 #pragma unroll
+#if defined(OPTP_ZONE_CHECK) || OPTP_ZONE_PAD_SHIFT != 2 || defined(OPTP_ZONE_PLAIN_IO)
     for (int i = 0; i < BC; ++i) {
         const int jr = jr0 + i;
         c[i] = ((unsigned int)jr < (unsigned int)lim) ? tile[OPTP_ZP(jr)] : 0.0;
     }
+#else
+    {
+        // zone_pad(jr0 + i) = e + (e >> 2) without per-element address arithmetic: with b = jr0 & ~3, r = jr0 & 3 it
+        // is [b + (b >> 2) + r] + [i + (i >> 2)] + (((i & 3) + r) >> 2) -- four base pointers (one per i & 3, the
+        // carry of the low bits) and a compile-time offset per element
+        const int r = jr0 & 3, b = jr0 - r;
+        const double* const t0 = tile + (b + (b >> 2) + r);
+        const double* const tb[4] = {t0, t0 + (r == 3 ? 1 : 0), t0 + (r >= 2 ? 1 : 0), t0 + (r >= 1 ? 1 : 0)};
+#pragma unroll
+        for (int i = 0; i < BC; ++i) {
+            const int jr = jr0 + i;
+            c[i] = ((unsigned int)jr < (unsigned int)lim) ? tb[i & 3][i + (i >> 2)] : 0.0;
+        }
+    }
+#endif
     __syncwarp();  // every lane has read level k before this segment's stores overwrite the tile
     double sbg = sb, sKg = L.sK;
     const double rho = L.rho, rho2 = kB.rho2;
@@ -903,7 +919,14 @@ __device__ __forceinline__ unsigned int zone_segment_drift(double (&z)[zone_bz(G
 #pragma unroll
     for (int i = 0; i < BC; ++i) {
         c[i] *= back;
+#if defined(OPTP_ZONE_CHECK) || OPTP_ZONE_PAD_SHIFT != 2 || defined(OPTP_ZONE_PLAIN_IO)
         tile[OPTP_ZP(ZW + gl * BC + i)] = c[i];
+#else
+        // (a lane's chunk starts at a multiple of 4 nodes when BC is one: the pad of node base + i is then the pad
+        // of the base plus i >> 2, a compile-time offset)
+        if (BC % 4 == 0) tile[zone_pad(ZW + gl * BC) + i + (i >> 2)] = c[i];
+        else tile[OPTP_ZP(ZW + gl * BC + i)] = c[i];
+#endif
     }
     n_ex0_out = n_ex0;
     t_exT_out = t_exT;
