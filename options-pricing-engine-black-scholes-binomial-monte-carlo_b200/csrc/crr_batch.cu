@@ -18,6 +18,7 @@
 // Kernel 2 (any N up to the shared-memory limit): one option per CTA, ping-pong level
 //   arrays in shared memory.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include "optp_common.cuh"
 
@@ -1772,7 +1773,13 @@ extern "C" int optp_crr_batch(const double* S0, const double* K, const double* T
     // of slices i+1 and i-1 overlap the kernels of slice i, and the host never blocks on a pageable copy: it
     // moves a slice's results from the staging buffer to the caller's arrays as soon as that slice's event
     // has fired.  A contract's price does not depend on the slice it is in.
-    const uint64_t slice = 1ull << 17;
+    // (OPTP_CRR_SLICE_LOG2 in the environment: slice size for A/B runs, 14 ... 20)
+    static const int slice_log2 = [] {
+        const char* e = getenv("OPTP_CRR_SLICE_LOG2");
+        const int v = e ? atoi(e) : 17;
+        return (v >= 14 && v <= 20) ? v : 17;
+    }();
+    const uint64_t slice = 1ull << slice_log2;
     const uint64_t step = (n >= 4 * slice) ? slice : n;
     constexpr uint64_t kGroupSlices = kMaxEvents / 3;  // slices in flight per group (bounds staging and events)
     if (!c.stream2) OPTP_CUDA(cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking));
