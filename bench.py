@@ -786,7 +786,7 @@ def main():
             # reference's level array) per second over the measured LDS.64 bandwidth.  It exceeds 1 because the
             # levels live in registers and 72 % of the node updates are provably skipped.
             "algorithmic_smem_frac": crr_rate_gpu * CRR_SMEM_BYTES_PER_OPTION / peaks["smem_lds64_bytes"],
-            "traffic": 51_331_840 if n_c == 1_000_000 else None,   # ncu --set full (profiles/r2_ncu_full_bench_zone.md): dram read 49.1 MB + write 2.2 MB per launch
+            "traffic": 52_163_840 if n_c == 1_000_000 else None,   # ncu --set full (profiles/r2_ncu_full_bench_zone.md): dram read 49.1 MB + write 3.1 MB per launch (the write-back of the 9 MB of results is partly caught by the L2: 2.2-3.7 MB between captures)
             "peak_source": "optp_microbench DFMA issue rate measured in this run (= 148 x 64 lanes x clock to 1 %)"}
         line = {
             "metric": "mc_path_steps_per_sec", "value": mc_value, "unit": "path-steps/s", "n_gpus": world,
@@ -804,7 +804,7 @@ def main():
                          # peak = what the FP32 pipes can issue: 148 SMs x 128 lanes x the SM clock sampled during the
                          # timed region (MEASURED_PEAKS.json has no FP32-pipe figure; B200_PROFILING's nominal)
                          "peak": p32_nominal / 1e12, "unit": "T lane-ops/s", "frac": mc_kernel_rate * gbm_ops / p32_nominal,
-                         "traffic": 108288,  # ncu --set full of THIS launch (profiles/r2_ncu_full_bench_gbm.md): dram read 108 KB, write 0 (0.1-0.5 MB between captures: background traffic, the kernel has no HBM operands)
+                         "traffic": 105728,  # ncu --set full of THIS launch (profiles/r2_ncu_full_bench_gbm.md): dram read 106 KB, write 0 (0.1-0.5 MB between captures: background traffic, the kernel has no HBM operands)
                          "peak_measured_ffma": peaks["fp32_ffma_lane_ops"] / 1e12,
                          "frac_vs_measured_ffma": mc_kernel_rate * gbm_ops / peaks["fp32_ffma_lane_ops"],
                          # ncu counts 11.4 executed lane-instructions per path-step (12.08e9 warp instructions per
