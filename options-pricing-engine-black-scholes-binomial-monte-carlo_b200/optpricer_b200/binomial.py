@@ -39,11 +39,13 @@ def crr_batch(S0, K, T, r, q, sigma, is_call, N=500, *, american=False, return_s
     """
     if N <= 0:
         raise ValueError("N must be positive.")
-    cols = np.broadcast_arrays(*[np.asarray(x, dtype=np.float64) for x in (S0, K, T, r, q, sigma)],
-                               np.asarray(is_call, dtype=np.float64))
-    shape = cols[0].shape
-    flat = [np.ascontiguousarray(c.reshape(-1), dtype=np.float64) for c in cols[:6]]
-    call = np.ascontiguousarray(cols[6].reshape(-1) != 0.0, dtype=np.uint8)
+    # (no pass over the data unless a column has to be broadcast or converted: at 1M contracts a detour of the flag
+    # column through float64 cost 2.5 ms of a 22 ms call)
+    vals = [np.asarray(x, dtype=np.float64) for x in (S0, K, T, r, q, sigma)]
+    flag = np.asarray(is_call)
+    shape = np.broadcast_shapes(*[v.shape for v in vals], flag.shape)
+    flat = [np.ascontiguousarray(np.broadcast_to(v, shape).reshape(-1)) for v in vals]
+    call = np.ascontiguousarray(np.broadcast_to(flag != 0, shape).reshape(-1)).view(np.uint8)
     n = flat[0].size
     price = np.empty(n, dtype=np.float64)
     status = np.zeros(n, dtype=np.uint8)
@@ -82,5 +84,5 @@ def crr_vec(S0, K, T, r, q, sigma, kind, N=500, *, american=False):
     if kind.shape != K.shape:
         kind = np.broadcast_to(kind, K.shape)
     _check_lattice(T, r, q, sigma, N)
-    is_call = np.array([str(k) == "call" for k in kind.flat], dtype=np.uint8).reshape(K.shape)
+    is_call = (kind.astype(str) == "call").astype(np.uint8).reshape(K.shape)   # (anything else prices a put)
     return crr_batch(S0, K, T, r, q, sigma, is_call, N, american=american)
