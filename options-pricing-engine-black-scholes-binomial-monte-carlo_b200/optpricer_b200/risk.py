@@ -14,6 +14,9 @@ euro_price_mc on every call).  A plain callable is evaluated point by point exac
 """
 from __future__ import annotations
 
+from functools import reduce
+from operator import add
+
 import numpy as np
 
 from . import monte_carlo as mc
@@ -32,8 +35,13 @@ class TreePricer:
         self.N, self.american = int(N), bool(american)
 
     def batch(self, S, K, T, r, q, sigma, kind):
+        is_call = np.fromiter((k == "call" for k in kind), dtype=bool, count=len(kind))   # binomial.py:22-25
+        return self.batch_flags(S, K, T, r, q, sigma, is_call)
+
+    def batch_flags(self, S, K, T, r, q, sigma, is_call):
+        """`batch` with the kinds already reduced to flags (1 = call): the callers below bump every contract eight
+        times, and 160k string compares cost more than pricing 160k trees."""
         validate_contracts(S, K, T, sigma)   # the OptionSpec(...) a reference pricer_func builds per point
-        is_call = np.array([1 if k == "call" else 0 for k in kind], dtype=np.uint8)   # binomial.py:22-25
         price, status = crr_batch(S, K, T, r, q, sigma, is_call, self.N, american=self.american,
                                   return_status=True)
         if status.any():
@@ -137,6 +145,10 @@ def _reprice(pricer_func, S, K, T, r, q, sigma, kinds, bump_pct):
                 else:
                     P[i, j] = float(pricer_func(*[float(m[i, j]) for m in mats], kinds[i]))
         return P, eps
+    if hasattr(pricer_func, "batch_flags"):
+        flags = np.repeat(np.fromiter((k == "call" for k in kinds), dtype=bool, count=len(kinds)), _SLOTS)
+        P = np.asarray(pricer_func.batch_flags(*[m.reshape(-1) for m in mats], flags), dtype=float)
+        return P.reshape(mats[0].shape), eps
     flat_kinds = [k for k in kinds for _ in range(_SLOTS)]
     P = _price_points(pricer_func, [m.reshape(-1) for m in mats], flat_kinds).reshape(mats[0].shape)
     return P, eps
@@ -174,18 +186,15 @@ def portfolio_risk(instruments, pricer_func, *, bump_pct=0.01):
         g = _greeks_from_prices(P, eps)
     else:
         P, g = np.empty((0, _SLOTS)), {k: np.empty(0) for k in ("delta", "gamma", "vega", "theta", "rho")}
-    totals = {"delta": 0.0, "gamma": 0.0, "vega": 0.0, "theta": 0.0, "rho": 0.0}
-    total_value = 0.0
-    inst_greeks = []
-    names = list(totals)
-    scaled_cols = {k: (pos * g[k]).tolist() for k in names}
+    names = ("delta", "gamma", "vega", "theta", "rho")
+    scaled_cols = [(pos * g[k]).tolist() for k in names]
     values = (pos * P[:, 0]).tolist()   # risk.py:188-191 re-prices the unbumped contract: the same number
-    for i in range(len(instruments)):   # summed in instrument order, like the reference
-        scaled = {k: scaled_cols[k][i] for k in names}
-        for k in names:
-            totals[k] += scaled[k]
-        total_value += values[i]
-        inst_greeks.append({**scaled, "price": values[i]})
+    # summed in instrument order from 0.0 with plain additions, like the reference's loop (builtin sum() compensates
+    # since Python 3.12, numpy sums pairwise: both would differ from it in the last digits)
+    totals = {k: reduce(add, col, 0.0) for k, col in zip(names, scaled_cols)}
+    total_value = reduce(add, values, 0.0)
+    inst_greeks = [{"delta": a, "gamma": b, "vega": c, "theta": d, "rho": e, "price": v}
+                   for a, b, c, d, e, v in zip(*scaled_cols, values)]
     return {"total_delta": totals["delta"], "total_gamma": totals["gamma"], "total_vega": totals["vega"],
             "total_theta": totals["theta"], "total_rho": totals["rho"], "total_value": total_value,
             "instrument_greeks": inst_greeks}
