@@ -99,3 +99,53 @@ def test_portfolio_risk_hands_one_batch_with_flags_and_sums_like_the_reference_l
     assert list(out["instrument_greeks"][0]) == list(ref["instrument_greeks"][0])
     for a, b in zip(out["instrument_greeks"], ref["instrument_greeks"]):
         assert a == b
+
+
+def test_python_constants_mirror_the_header():
+    """Every OPTP_PROC_* / OPTP_PAY_* / OPTP_F_* / OPTP_MODE_* value of include/optp_b200.h against the constants the
+    wrappers pass (optpricer_b200/_native.py): a renumbering on one side only would still load and run."""
+    import os
+    import re
+    from optpricer_b200 import _native as nv
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "include", "optp_b200.h")).read()
+    defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define OPTP_([A-Z0-9_]+) (\d+)u?\b", text)}
+    assert defs["ABI_VERSION"] == nv.ABI_VERSION and defs["NSTATS"] == nv.NSTATS
+    seen = 0
+    for name, value in defs.items():
+        if name.split("_")[0] in ("PROC", "PAY", "F", "MODE"):
+            assert getattr(nv, name) == value, name
+            seen += 1
+    assert seen == 9 + 5 + 5 + 3
+
+
+def test_payoff_descriptors_follow_the_reference_arguments():
+    """exotics.py:33-96, 102-163, 169-209, 215-273: every argument combination of the four payoff pricers lands in the
+    kind / flags / level fields the kernels read (mc_kernels.cuh eval_payoff), and bad arguments raise before any call."""
+    from optpricer_b200 import _native as nv, exotics as ex
+    for kind, kf in (("call", nv.F_CALL), ("put", 0)):
+        for bt in ("up-and-out", "up-and-in", "down-and-out", "down-and-in"):
+            s = ex.barrier_spec(100.0, kind, 120.0, bt, rebate=1.5)
+            want = kf | (nv.F_UP if bt.startswith("up") else 0) | (nv.F_IN if bt.endswith("in") else 0)
+            assert (s["kind"], s["flags"], s["K"], s["barrier"], s["rebate"]) == (nv.PAY_BARRIER, want, 100.0, 120.0, 1.5)
+        for avg in ("arithmetic", "geometric"):
+            for st in ("fixed", "floating"):
+                s = ex.asian_spec(100.0, kind, avg, st)
+                want = kf | (nv.F_GEOMETRIC if avg == "geometric" else 0) | (nv.F_FLOATING if st == "floating" else 0)
+                assert (s["kind"], s["flags"]) == (nv.PAY_ASIAN, want)
+        for st in ("floating", "fixed"):
+            s = ex.lookback_spec(kind, 95.0, st)
+            assert (s["kind"], s["flags"], s["K"]) == (nv.PAY_LOOKBACK, kf | (nv.F_FLOATING if st == "floating" else 0), 95.0)
+        s = ex.digital_spec(100.0, kind, payout=7.0)
+        assert (s["kind"], s["flags"], s["payout"]) == (nv.PAY_DIGITAL, kf, 7.0)
+        assert ex.vanilla_spec(100.0, kind)["kind"] == nv.PAY_VANILLA
+    arr = ex._native_payoffs([ex.barrier_spec(100.0, "call", 130.0, "up-and-out", 2.0), ex.digital_spec(90.0, "put", 3.0)],
+                             0.05, 2.0)
+    assert (arr[0].kind, arr[0].flags, arr[0].K, arr[0].barrier, arr[0].rebate) == (nv.PAY_BARRIER, nv.F_CALL | nv.F_UP, 100.0, 130.0, 2.0)
+    assert (arr[1].kind, arr[1].flags, arr[1].K, arr[1].payout) == (nv.PAY_DIGITAL, 0, 90.0, 3.0)
+    assert all((a.r_disc, a.T_disc) == (0.05, 2.0) for a in arr)
+    for bad in (lambda: ex.barrier_spec(100.0, "call", 120.0, "sideways"), lambda: ex.asian_spec(100.0, "call", "harmonic"),
+                lambda: ex.asian_spec(100.0, "call", "arithmetic", "sticky"), lambda: ex.lookback_spec("call", 0.0, "sticky"),
+                lambda: ex.digital_spec(100.0, "straddle")):
+        with pytest.raises(ValueError):
+            bad()
