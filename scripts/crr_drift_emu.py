@@ -24,6 +24,12 @@ def drift_walk(S0, K, T, r, q, sg, N, ZW=16, P=13, seg0=32, seg=44, maxM=6, stat
     ln_u = np.log(u); thr = K * 2.0 ** -80
     E = lambda j, k: K - S0 * np.exp(ln_u * (2.0 * j - k))
     jz = 0.5 * (N + np.log(K / S0) / ln_u)
+    # q > 0: a node can only choose exercise if S < S1 = K(1-disc)/(1-e^{-q dt}); on the levels k < k_pin even node 0
+    # lies above S1 (the kernel's regime without exercise nodes: window from node 0, no per-level tests)
+    k_pin = 0
+    if q > 0.0:
+        S1 = K * (-np.expm1(-r * dt)) / (-np.expm1(-q * dt))
+        k_pin = int(min(max(np.ceil(-np.log(S1 / S0) / ln_u - 0.01), 0.0), N + 1))
     w0 = int(min(np.floor(jz) - (ZW - 4), N + 1 - ZW))
     k = N; M = 0
     W = ZW
@@ -45,7 +51,8 @@ def drift_walk(S0, K, T, r, q, sg, N, ZW=16, P=13, seg0=32, seg=44, maxM=6, stat
         nlev = min(seg0 if k == N else seg, k)
         nB = nlev >> 1
         top = min(jhi, k + 1)
-        w0n = jlo - P
+        pinned = k < k_pin
+        w0n = 0 if pinned else jlo - P
         need = 0
         if top + nB > w0n + ZW:
             need = (top + nB - (w0n + ZW) + CH - 1) // CH
@@ -61,7 +68,7 @@ def drift_walk(S0, K, T, r, q, sg, N, ZW=16, P=13, seg0=32, seg=44, maxM=6, stat
         vn[inside] = v[jr[inside]]
         v = vn; w = w0n; W = Wn; M = need
         D = k - w0n - (ZW - 1)
-        n_chk = int(np.clip(2 * D, 0, nlev))
+        n_chk = 0 if pinned else int(np.clip(2 * D, 0, nlev))
         ok = True
         for t in range(1, nlev + 1):
             kk = k - t
@@ -69,7 +76,7 @@ def drift_walk(S0, K, T, r, q, sg, N, ZW=16, P=13, seg0=32, seg=44, maxM=6, stat
                 up = np.append(v[1:], 0.0)
                 cont = a * up + b * v
             else:       # B step: origin - 1
-                eb = E(w - 1, kk + 1)
+                eb = K if pinned else E(w - 1, kk + 1)   # (pinned: anything above the tree's values, never used by it)
                 low = np.append(eb, v[:-1])
                 cont = a * v + b * low
                 w -= 1
@@ -78,7 +85,7 @@ def drift_walk(S0, K, T, r, q, sg, N, ZW=16, P=13, seg0=32, seg=44, maxM=6, stat
             exz = ex[:ZW] > cont[:ZW]
             v = cont.copy()
             v[:ZW] = np.where(exz, ex[:ZW], cont[:ZW])
-            if not exz[0]: ok = False; why = 'bottom'
+            if not exz[0] and not pinned: ok = False; why = 'bottom'
             if exz[ZW - 1] and t <= n_chk: ok = False; why = 'top'
             nodes_z += ZW; nodes_c += W - ZW
         if not ok: return None, why
@@ -86,7 +93,7 @@ def drift_walk(S0, K, T, r, q, sg, N, ZW=16, P=13, seg0=32, seg=44, maxM=6, stat
         idx = w0 + np.arange(W)
         exm = np.zeros(W, bool); exm[:ZW] = v[:ZW] == E(idx[:ZW], k)
         jlo, jhi = measure(v, exm, w0, W, k)
-        if jlo <= w0: return None, 'bottom_m'
+        if jlo <= w0 and k >= k_pin: return None, 'bottom_m'
     if stats is not None: stats.append((nodes_z, nodes_c, nseg))
     pos = -w0
     if pos < 0: return K - S0, 'ok'

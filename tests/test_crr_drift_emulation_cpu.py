@@ -45,3 +45,26 @@ def test_drifting_walk_reproduces_the_full_lattice():
             worst = max(worst, abs(price - ref) / max(abs(ref), 1e-8 * K))
             walked += 1
     assert walked >= 30 and worst < 1e-12, (walked, worst)
+
+
+def test_regime_without_exercise_nodes():
+    """q > 0, spot far above the strike: near level 0 the whole tree lies above S1 = K(1-disc)/(1-e^{-q dt}), no node can
+    choose exercise, and the walk starts its window at node 0 without the per-level tests (csrc/crr_batch.cu: k_pin)."""
+    g = np.random.default_rng(11)
+    pinned_seen, worst = 0, 0.0
+    for _ in range(16):
+        S0 = g.uniform(80, 160); K = S0 * g.uniform(0.2, 0.45); T = g.uniform(0.1, 0.5)
+        sg = g.uniform(0.3, 0.8); r = g.uniform(0.04, 0.11); q = r * g.uniform(0.8, 0.98)
+        N = 400
+        dt = T / N
+        S1 = K * (-np.expm1(-r * dt)) / (-np.expm1(-q * dt))
+        k_pin = int(np.ceil(-np.log(S1 / S0) / (sg * np.sqrt(dt)) - 0.01))
+        pinned_seen += k_pin > 64
+        price, why = emu.drift_walk(S0, K, T, r, q, sg, N, seg0=32, seg=64, maxM=24)
+        assert price is not None, why
+        ref = emu.exact(S0, K, T, r, q, sg, N)
+        if ref > 1e-18 * K:                 # (values below 2^-80 K are cut on the way)
+            worst = max(worst, abs(price - ref) / ref)
+        else:
+            assert price <= 1e-17 * K
+    assert pinned_seen >= 8 and worst < 1e-6, (pinned_seen, worst)
